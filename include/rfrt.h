@@ -1,0 +1,194 @@
+/*
+ * rfrt.h — C ABI of librfrt.so, the B200 (sm_100a) RF ray-tracing hot path.
+ *
+ * This is the drop-in boundary for the ONE path the reference accelerates on a device:
+ *   tracer.py:22-24   wp.array(vertices) / wp.array(faces) / wp.Mesh(...)      -> rfrt_mesh_create
+ *   tracer.py:26-30   Tracer._generate_rx_mesh (icosphere -> wp.Mesh)          -> rfrt_rxset_create
+ *   tracer.py:75-80   wp.launch(kernel.trace_paths_kernel, dim=(N,1,1), inputs=[env.id, tx_pos,
+ *                     rx.id, max_bounces, traced_paths, received_paths, row_mask]);
+ *                     wp.synchronize_device()                                   -> rfrt_trace_paths_compat
+ *                                                                                  (same 7 inputs, dense)
+ *                                                                               -> rfrt_trace + rfrt_trace_receive
+ *                                                                                  (streaming: no N x (B+1) arrays)
+ *   tracer.py:101-117 impulse-response binning (+ _bounce_amplitude :34-61)     -> fused in rfrt_trace_receive,
+ *                                                                                  rfrt_bin_ir
+ *   main.py:39,46-55 / coverage.py:45-55  RX power from the impulse response    -> rfrt_rx_power
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  Pointers named d_* are DEVICE pointers into buffers
+ *     the CALLER owns (e.g. torch CUDA tensors: tensor.data_ptr()); h_* are host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream); NULL = legacy
+ *     default stream.  Calls only enqueue work; they do not synchronise unless stated.
+ *   - every function returns 0 on success or a negative rfrt_status; rfrt_last_error() gives the
+ *     message of the last failure on the calling thread.  No C++ exception crosses this boundary.
+ *   - the library owns only what lives behind a handle (BVH nodes, re-ordered triangles, receiver
+ *     vertices) and frees it in *_destroy.
+ */
+#ifndef RFRT_H
+#define RFRT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFRT_VERSION 100
+
+#if defined(__GNUC__)
+#define RFRT_API __attribute__((visibility("default")))
+#else
+#define RFRT_API
+#endif
+
+typedef uint64_t rfrt_handle;
+
+enum rfrt_status {
+    RFRT_OK = 0,
+    RFRT_ERR_INVALID = -1,  /* bad argument */
+    RFRT_ERR_CUDA = -2,     /* a CUDA runtime call or launch failed */
+    RFRT_ERR_HANDLE = -3,   /* unknown / stale handle */
+    RFRT_ERR_NO_DEVICE = -4 /* no sm_100 device visible */
+};
+
+/* rfrt_trace flags */
+#define RFRT_FLAG_NONE 0u
+
+/* layout of the u64 counter block written by rfrt_trace / rfrt_trace_receive */
+#define RFRT_CTR_SEGMENTS 0    /* traced ray segments (alive bounce iterations), SURVEY.md 8d */
+#define RFRT_CTR_CANDIDATES 1  /* (ray, receiver) candidates appended (may exceed capacity) */
+#define RFRT_CTR_RECORDS 2     /* received records appended (may exceed capacity) */
+#define RFRT_CTR_ENV_HITS 3    /* environment hits among the segments */
+#define RFRT_CTR_NEXT_RAY 4    /* internal: persistent-kernel ray fetch cursor */
+#define RFRT_CTR_NEXT_CAND 5   /* internal: candidate fetch cursor */
+#define RFRT_CTR_COUNT 8
+
+RFRT_API int rfrt_version(void);
+RFRT_API const char *rfrt_last_error(void);
+
+/* SM count / compute capability of the current device. */
+RFRT_API int rfrt_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Environment mesh + LBVH.   Replaces wp.Mesh(points, velocities=None, indices) at tracer.py:22-24.
+ *   d_vertices_xyz : [n_vertices*3] float32      d_indices : [n_triangles*3] int32
+ * Builds (on `stream`): per-triangle bounds -> 30-bit Morton codes -> 8-bit LSD radix sort ->
+ * Karras hierarchy -> bottom-up refit.  Triangle index == row of d_indices (== STL facet order).
+ * Synchronises the stream once before returning (the handle is ready to use on any stream).
+ * ------------------------------------------------------------------------------------------- */
+RFRT_API int rfrt_mesh_create(const float *d_vertices_xyz, int64_t n_vertices, const int32_t *d_indices,
+                     int64_t n_triangles, void *stream, rfrt_handle *out_mesh);
+RFRT_API int rfrt_mesh_destroy(rfrt_handle mesh);
+/* bounds6 = {lo.xyz, hi.xyz} (unpadded); any output pointer may be NULL. */
+RFRT_API int rfrt_mesh_info(rfrt_handle mesh, int64_t *n_triangles, int64_t *n_nodes, float *h_bounds6,
+                   int32_t *max_depth, float *build_ms);
+/* Debug/test export of the built hierarchy into caller-owned device buffers:
+ *   d_nodes      : [n_nodes*16] float32 (64-byte nodes)  or NULL
+ *   d_tri_order  : [n_triangles] int32 — triangle index stored at each sorted slot  or NULL */
+RFRT_API int rfrt_mesh_export(rfrt_handle mesh, float *d_nodes, int32_t *d_tri_order, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Receiver set.  Replaces Tracer._generate_rx_mesh (tracer.py:26-30), batched over R receivers:
+ * receiver k is the mesh  float32(center_k + radius * unit_vertex_j)  (fp64 arithmetic, one rounding)
+ * with the face table given.  A BVH over the receivers' bounding boxes is built for the trace.
+ *   d_centers_xyz   : [R*3] float64 (device)
+ *   h_unit_vertices : [n_unit_vertices*3] float64 (host) — icosphere(subdivisions=1): 42
+ *   h_faces         : [n_faces*3] int32 (host) — 80 faces
+ * ------------------------------------------------------------------------------------------- */
+RFRT_API int rfrt_rxset_create(const double *d_centers_xyz, int64_t n_receivers, double radius,
+                      const double *h_unit_vertices, int32_t n_unit_vertices, const int32_t *h_faces,
+                      int32_t n_faces, void *stream, rfrt_handle *out_rxset);
+RFRT_API int rfrt_rxset_destroy(rfrt_handle rxset);
+/* copies the generated receiver vertices ([R*n_unit_vertices*3] float32) to a caller device buffer */
+RFRT_API int rfrt_rxset_export(rfrt_handle rxset, float *d_vertices, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Deterministic ray directions (kernel.py:51-52: rand_init(tid) + sample_unit_sphere_surface).
+ *   d_dirs : [(ray_end-ray_begin)*4] float32 (x, y, z, 0)
+ * ------------------------------------------------------------------------------------------- */
+RFRT_API int rfrt_ray_directions(int64_t ray_begin, int64_t ray_end, float *d_dirs, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Streaming trace of the environment trajectory of rays [ray_begin, ray_end)  (kernel.py:48-98 with
+ * the receiver hits factored out): per segment one closest-hit query against the environment BVH
+ * (kernel.py:82) and a receiver test (kernel.py:71,85) against every receiver of `rxset`.  A ray
+ * that hits receiver k before the environment appends the candidate (ray id, k, bounce); candidates
+ * are later replayed literally by rfrt_trace_receive (which drops repeats of a (ray, k) pair).  No N x (B+1) array is ever materialised.
+ *   h_tx_pos        : 3 floats (host)
+ *   d_dir_scratch   : [min(chunk, n)*4] float32 workspace (directions of the chunk in flight)
+ *   chunk_rays      : rays generated per wave (0 = default 2^24)
+ *   d_counters      : [RFRT_CTR_COUNT] uint64, zeroed by the CALLER before the first call of a job;
+ *                     accumulates across calls
+ *   d_candidates    : [cand_capacity*4] uint32 quads (ray id, receiver, bounce, 0) or NULL when rxset == 0
+ *   d_hit_tri/d_hit_t : optional dense [n*max_bounces] parity dumps (int32 triangle index, -1 = miss /
+ *                     dead; float32 hit distance, 0 = miss / dead); NULL to skip
+ * ------------------------------------------------------------------------------------------- */
+RFRT_API int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *h_tx_pos, int32_t max_bounces,
+               int64_t ray_begin, int64_t ray_end, uint32_t flags, float *d_dir_scratch,
+               int64_t chunk_rays, uint64_t *d_counters, uint32_t *d_candidates, int64_t cand_capacity,
+               int32_t *d_hit_tri, float *d_hit_t, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Literal replay of kernel.py:38-98 for each candidate (ray id, receiver k) against (env, receiver k),
+ * followed by the per-path post-processing of tracer.py:90-117 (NaN-prefix strip is implicit: the
+ * record carries n_vertices) — Fresnel amplitude product, fp64 distance, delay bin.
+ *   d_candidates / d_cand_count : pairs from rfrt_trace and the device counter holding their number
+ *                                 (= d_counters + RFRT_CTR_CANDIDATES); at most cand_capacity are read
+ *   amp0            : tx_power / tx_num_rays          (tracer.py:103)
+ *   samples_per_m   : used as bin = int((distance / light_speed) * sample_rate)  (tracer.py:115)
+ * Outputs, one record per RECEIVED (ray, receiver) pair, appended in arbitrary order
+ * (count in d_counters[RFRT_CTR_RECORDS]; records beyond rec_capacity are counted but not stored):
+ *   d_rec_ray [cap] uint32, d_rec_rx [cap] int32, d_rec_nverts [cap] int32, d_rec_bin [cap] int64,
+ *   d_rec_amp [cap] float64, d_rec_dist [cap] float64,
+ *   d_rec_paths [cap*(max_bounces+1)*3] float32 (NaN padded like tracer.py:67-71) or NULL
+ * ------------------------------------------------------------------------------------------- */
+RFRT_API int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const float *h_tx_pos, int32_t max_bounces,
+                       const uint32_t *d_candidates, int64_t cand_capacity, uint64_t *d_counters,
+                       double amp0, double light_speed_mps, double sample_rate_hz, uint32_t *d_rec_ray,
+                       int32_t *d_rec_rx, int32_t *d_rec_nverts, int64_t *d_rec_bin, double *d_rec_amp,
+                       double *d_rec_dist, float *d_rec_paths, int64_t rec_capacity, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Impulse-response binning (tracer.py:101,116-117):  ir[rx][bin] += amp  if bin < n_bins.
+ *   d_ir : [n_receivers*n_bins] float64, zeroed by the caller.
+ *   deterministic != 0 : records must be sorted by (rx, ray id); each receiver's records are then
+ *                        summed by one thread in ray-id order — the reference's own order — so the
+ *                        result is bit-reproducible and independent of the GPU count.
+ *   deterministic == 0 : shared-memory privatised histogram per receiver tile, flushed with atomics.
+ * ------------------------------------------------------------------------------------------- */
+RFRT_API int rfrt_bin_ir(const int32_t *d_rec_rx, const int64_t *d_rec_bin, const double *d_rec_amp, int64_t n_records,
+                int64_t n_receivers, int64_t n_bins, int32_t deterministic, double *d_ir, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * RX power of main.py:39,46-55 / coverage.py:45-55 for each receiver, from its SPARSE arrivals
+ * (the non-zero impulse-response bins):  t = linspace(0, window, n_bins); s_tx = sin(2 pi f t);
+ * s_rx = convolve(ir, s_tx, "same"); power = mean(s_rx[s_rx != 0]^2)   (NaN if nothing is non-zero).
+ *   arrivals are CSR: d_arr_offsets [n_receivers+1] int64, d_arr_bin [nnz] int32 (ascending per
+ *   receiver), d_arr_amp [nnz] float64.
+ *   d_stx_table : [n_bins] float64 scratch (filled with s_tx by this call)
+ *   d_power : [n_receivers] float64 (linear mean-square power; dBm = 10 log10(power / 1e-3))
+ * ------------------------------------------------------------------------------------------- */
+RFRT_API int rfrt_rx_power(const int64_t *d_arr_offsets, const int32_t *d_arr_bin, const double *d_arr_amp,
+                  int64_t n_receivers, int64_t n_bins, double sample_window_s, double carrier_hz,
+                  double *d_stx_table, double *d_power, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Compatibility launch with the reference kernel's exact contract (kernel.py:38-47 as launched at
+ * tracer.py:75-79): dense outputs for ray ids [ray_begin, ray_begin+n_rays) against receiver
+ * `rx_index` of `rxset`.  The caller pre-fills d_traced_paths / d_received_paths with NaN and zeroes
+ * d_row_mask, exactly as tracer.py:67-72 does.
+ *   d_traced_paths, d_received_paths : [n_rays*(max_bounces+1)*3] float32   d_row_mask : [n_rays] uint32
+ * ------------------------------------------------------------------------------------------- */
+RFRT_API int rfrt_trace_paths_compat(rfrt_handle env_mesh, const float *h_tx_pos, rfrt_handle rxset, int64_t rx_index,
+                            int32_t max_bounces, int64_t ray_begin, int64_t n_rays, float *d_traced_paths,
+                            float *d_received_paths, uint32_t *d_row_mask, void *stream);
+
+/* Single-query probe for tests: closest hit of n rays (d_origins/d_dirs [n*3]) against the mesh BVH.
+ *   d_t [n] float32 (max_t where missed), d_face [n] int32 (-1 where missed) */
+RFRT_API int rfrt_query_closest(rfrt_handle mesh, const float *d_origins, const float *d_dirs, int64_t n, float max_t,
+                       float *d_t, int32_t *d_face, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFRT_H */

@@ -1,0 +1,75 @@
+// rfrt_internal.h — host/device structures shared by the translation units of librfrt.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/rfrt.h"
+
+namespace rfrt {
+
+// 64-byte BVH node: the two CHILD boxes live in the parent, so one node fetch (4 x 128-bit loads)
+// decides both descents.  Boxes are stored already padded (see bvh pad rule in DESIGN.md).
+//   q0 = (lo0.x, lo0.y, lo0.z, hi0.x)   q1 = (hi0.y, hi0.z, lo1.x, lo1.y)
+//   q2 = (lo1.z, hi1.x, hi1.y, hi1.z)   q3 = (child0, child1, -, -) as int32
+// child >= 0: internal node index; child < 0: leaf, ~child = sorted primitive slot.
+struct __align__(16) BvhNode {
+    float4 q0, q1, q2;
+    int4 q3;
+};
+static_assert(sizeof(BvhNode) == 64, "node must be 64 bytes");
+
+// 48-byte triangle in sorted (Morton) order: three 128-bit loads.
+//   v0 = (a.x, a.y, a.z, b.x)  v1 = (b.y, b.z, c.x, c.y)  v2 = (c.z, as_float(triangle index), 0, 0)
+struct __align__(16) BvhTri {
+    float4 v0, v1, v2;
+};
+static_assert(sizeof(BvhTri) == 48, "triangle must be 48 bytes");
+
+struct Bvh {
+    BvhNode *nodes = nullptr; // n_nodes = max(n_prims - 1, 1) (0 when n_prims == 0)
+    int32_t *prim_order = nullptr; // sorted slot -> primitive index
+    int64_t n_prims = 0;
+    int64_t n_nodes = 0;
+    int32_t max_depth = 0;
+    float bounds[6] = {0, 0, 0, 0, 0, 0};
+    float pad = 0.0f;
+};
+
+struct Mesh {
+    Bvh bvh;
+    BvhTri *tris = nullptr;      // sorted order, for traversal
+    float *soup = nullptr;       // [n*9] original order (a,b,c) for normals / literal replay
+    float build_ms = 0.0f;
+};
+
+struct RxSet {
+    Bvh bvh;                  // over receiver bounding boxes
+    float *verts = nullptr;   // [R * n_unit * 3] fp32
+    int64_t n_receivers = 0;
+    int32_t n_unit = 0;
+    int32_t n_faces = 0;
+    uint8_t faces[3 * 128];   // host copy of the face table (<= 128 faces), uploaded to __constant__
+    double radius = 0.0;
+    double *centers = nullptr; // [R*3] device copy
+};
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define RFRT_CUDA(call)                                                  \
+    do {                                                                 \
+        cudaError_t _e = (call);                                         \
+        if (_e != cudaSuccess) return ::rfrt::cuda_fail(_e, #call);      \
+    } while (0)
+
+// Builds a BVH over n axis-aligned boxes (device arrays lo/hi as float4 per primitive, w ignored).
+// Allocates bvh.nodes / bvh.prim_order.  Synchronises the stream.
+int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t stream, Bvh *out);
+void free_bvh(Bvh *b);
+
+Mesh *get_mesh(rfrt_handle h);
+RxSet *get_rxset(rfrt_handle h);
+
+} // namespace rfrt

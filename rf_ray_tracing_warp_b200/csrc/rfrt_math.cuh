@@ -1,0 +1,239 @@
+// rfrt_math.cuh — device arithmetic of the hot path (sm_100a).
+//
+// Everything here that decides WHICH triangle a ray hits is written as an explicit sequence of IEEE
+// fp32 operations (the library is compiled with -fmad=false, so the only fused operations are the
+// fmaf() calls written out below).  The sequence restates:
+//   kernel.py:51-52  wp.rand_init / wp.sample_unit_sphere_surface   (PCG hash, 24-bit randf)
+//   kernel.py:71,82  wp.mesh_query_ray -> intersect_ray_tri_woop    (watertight test)
+//   kernel.py:6-8    reflect
+// of /root/reference (warp-lang itself is third-party and not vendored there).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rfrt {
+
+// ---------------------------------------------------------------------------------------------
+// RNG
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pcg_hash(uint32_t s)
+{
+    uint32_t b = s * 747796405u + 2891336453u;
+    uint32_t c = ((b >> ((b >> 28) + 4u)) ^ b) * 277803737u;
+    return (c >> 22) ^ c;
+}
+
+__device__ __forceinline__ float randf(uint32_t &state)
+{
+    state = pcg_hash(state);
+    return __uint2float_rn(state >> 8) * (1.0f / 16777216.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic fp64 sin / cos / acos: IEEE + - * / sqrt / floor only, Horner in a fixed order.
+// Identical bits on any IEEE machine (no libm / libdevice involved).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void det_sincos(double x, double &s_out, double &c_out)
+{
+    const double TWO_OVER_PI = 0.6366197723675814;
+    const double PIO2_1 = 1.5707963267341256;     // first 33 bits of pi/2
+    const double PIO2_1T = 6.077100506506192e-11; // pi/2 - PIO2_1
+    double kf = floor(__dadd_rn(__dmul_rn(x, TWO_OVER_PI), 0.5));
+    int k = (int)kf;
+    double r = __dsub_rn(__dsub_rn(x, __dmul_rn(kf, PIO2_1)), __dmul_rn(kf, PIO2_1T));
+    double w = __dmul_rn(r, r);
+    double ps = 2.8114572543455206e-15;
+    ps = __dadd_rn(-7.647163731819816e-13, __dmul_rn(w, ps));
+    ps = __dadd_rn(1.6059043836821613e-10, __dmul_rn(w, ps));
+    ps = __dadd_rn(-2.505210838544172e-08, __dmul_rn(w, ps));
+    ps = __dadd_rn(2.7557319223985893e-06, __dmul_rn(w, ps));
+    ps = __dadd_rn(-0.0001984126984126984, __dmul_rn(w, ps));
+    ps = __dadd_rn(0.008333333333333333, __dmul_rn(w, ps));
+    ps = __dadd_rn(-0.16666666666666666, __dmul_rn(w, ps));
+    double sn = __dadd_rn(r, __dmul_rn(__dmul_rn(r, w), ps));
+    double pc = -1.5619206968586225e-16;
+    pc = __dadd_rn(4.779477332387385e-14, __dmul_rn(w, pc));
+    pc = __dadd_rn(-1.1470745597729725e-11, __dmul_rn(w, pc));
+    pc = __dadd_rn(2.08767569878681e-09, __dmul_rn(w, pc));
+    pc = __dadd_rn(-2.755731922398589e-07, __dmul_rn(w, pc));
+    pc = __dadd_rn(2.48015873015873e-05, __dmul_rn(w, pc));
+    pc = __dadd_rn(-0.001388888888888889, __dmul_rn(w, pc));
+    pc = __dadd_rn(0.041666666666666664, __dmul_rn(w, pc));
+    pc = __dadd_rn(-0.5, __dmul_rn(w, pc));
+    double cs = __dadd_rn(1.0, __dmul_rn(w, pc));
+    switch (k & 3) {
+    case 0: s_out = sn; c_out = cs; break;
+    case 1: s_out = cs; c_out = -sn; break;
+    case 2: s_out = -sn; c_out = -cs; break;
+    default: s_out = -cs; c_out = sn; break;
+    }
+}
+
+__device__ __forceinline__ double det_asin_small(double x)
+{
+    const double A[29] = {
+        1.0, 0.16666666666666666, 0.075, 0.044642857142857144, 0.030381944444444444, 0.022372159090909092,
+        0.017352764423076924, 0.01396484375, 0.011551800896139705, 0.009761609529194078, 0.008390335809616815,
+        0.0073125258735988454, 0.006447210311889649, 0.005740037670841924, 0.005153309682319905,
+        0.004660143486915096, 0.004240907093679363, 0.003880964558837669, 0.0035692053938259347,
+        0.003297059503473485, 0.0030578216492580306, 0.002846178401108942, 0.00265787063820729,
+        0.0024894486782468836, 0.002338091892111975, 0.0022014739737101384, 0.0020776610325181676,
+        0.0019650336162772837, 0.0018622264064031275};
+    double w = __dmul_rn(x, x);
+    double p = A[28];
+#pragma unroll
+    for (int j = 27; j >= 0; --j) p = __dadd_rn(A[j], __dmul_rn(w, p));
+    return __dmul_rn(x, p);
+}
+
+__device__ __forceinline__ double det_acos(double z)
+{
+    const double PI = 3.141592653589793;
+    const double PIO2 = 1.5707963267948966;
+    if (z > 0.5) return __dmul_rn(2.0, det_asin_small(__dsqrt_rn(__dmul_rn(__dsub_rn(1.0, z), 0.5))));
+    if (z < -0.5)
+        return __dsub_rn(PI, __dmul_rn(2.0, det_asin_small(__dsqrt_rn(__dmul_rn(__dadd_rn(1.0, z), 0.5)))));
+    return __dsub_rn(PIO2, det_asin_small(z));
+}
+
+// kernel.py:51-52
+__device__ __forceinline__ float3 ray_direction(uint32_t tid)
+{
+    uint32_t state = pcg_hash(tid);
+    float u1 = randf(state);
+    float u2 = randf(state);
+    float phi = __double2float_rn(det_acos(__dsub_rn(1.0, __dmul_rn(2.0, (double)u1))));
+    float theta = __fmul_rn(6.2831854820251465f, u2);
+    double s, c;
+    det_sincos((double)phi, s, c);
+    float sp = __double2float_rn(s), cp = __double2float_rn(c);
+    det_sincos((double)theta, s, c);
+    float st = __double2float_rn(s), ct = __double2float_rn(c);
+    return make_float3(__fmul_rn(ct, sp), __fmul_rn(st, sp), cp);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Watertight ray/triangle test (Woop, Benthin, Wald 2013) in the operation order of warp's
+// intersect_ray_tri_woop.  The per-ray part (dominant axis, shear) is hoisted out of the
+// per-triangle part; the arithmetic performed per triangle is unchanged.
+// ---------------------------------------------------------------------------------------------
+struct WoopRay {
+    int kx, ky, kz;
+    float Sx, Sy, Sz;
+    float px, py, pz; // ray origin
+};
+
+__device__ __forceinline__ float sel3(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
+
+__device__ __forceinline__ WoopRay woop_setup(float3 p, float3 d)
+{
+    WoopRay r;
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int kz;
+    if (ax > ay && ax > az) kz = 0;
+    else if (ay > az) kz = 1;
+    else kz = 2;
+    int kx = kz + 1; if (kx == 3) kx = 0;
+    int ky = kx + 1; if (ky == 3) ky = 0;
+    float dkz = sel3(d.x, d.y, d.z, kz);
+    if (dkz < 0.0f) { int tmp = kx; kx = ky; ky = tmp; }
+    r.kx = kx; r.ky = ky; r.kz = kz;
+    r.Sx = __fdiv_rn(sel3(d.x, d.y, d.z, kx), dkz);
+    r.Sy = __fdiv_rn(sel3(d.x, d.y, d.z, ky), dkz);
+    r.Sz = __fdiv_rn(1.0f, dkz);
+    r.px = p.x; r.py = p.y; r.pz = p.z;
+    return r;
+}
+
+__device__ __forceinline__ float diff_product(float a, float b, float c, float d)
+{
+    float cd = __fmul_rn(c, d);
+    float diff = __fmaf_rn(a, b, -cd);
+    float err = __fmaf_rn(-c, d, cd);
+    return __fadd_rn(diff, err);
+}
+
+// returns true and t when the triangle is hit (any sign of t that the reference accepts here:
+// callers apply  t >= 0 && t < best).
+__device__ __forceinline__ bool woop_hit(const WoopRay &r, float3 a, float3 b, float3 c, float &t_out)
+{
+    float A0 = __fsub_rn(a.x, r.px), A1 = __fsub_rn(a.y, r.py), A2 = __fsub_rn(a.z, r.pz);
+    float B0 = __fsub_rn(b.x, r.px), B1 = __fsub_rn(b.y, r.py), B2 = __fsub_rn(b.z, r.pz);
+    float C0 = __fsub_rn(c.x, r.px), C1 = __fsub_rn(c.y, r.py), C2 = __fsub_rn(c.z, r.pz);
+    float Akx = sel3(A0, A1, A2, r.kx), Aky = sel3(A0, A1, A2, r.ky), Akz = sel3(A0, A1, A2, r.kz);
+    float Bkx = sel3(B0, B1, B2, r.kx), Bky = sel3(B0, B1, B2, r.ky), Bkz = sel3(B0, B1, B2, r.kz);
+    float Ckx = sel3(C0, C1, C2, r.kx), Cky = sel3(C0, C1, C2, r.ky), Ckz = sel3(C0, C1, C2, r.kz);
+
+    float Ax = __fsub_rn(Akx, __fmul_rn(r.Sx, Akz));
+    float Ay = __fsub_rn(Aky, __fmul_rn(r.Sy, Akz));
+    float Bx = __fsub_rn(Bkx, __fmul_rn(r.Sx, Bkz));
+    float By = __fsub_rn(Bky, __fmul_rn(r.Sy, Bkz));
+    float Cx = __fsub_rn(Ckx, __fmul_rn(r.Sx, Ckz));
+    float Cy = __fsub_rn(Cky, __fmul_rn(r.Sy, Ckz));
+
+    float U = diff_product(Cx, By, Cy, Bx);
+    float V = diff_product(Ax, Cy, Ay, Cx);
+    float W = diff_product(Bx, Ay, By, Ax);
+
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        // products of two floats are exact in fp64; one rounding for the difference, one to fp32
+        double CxBy = __dmul_rn((double)Cx, (double)By);
+        double CyBx = __dmul_rn((double)Cy, (double)Bx);
+        U = __double2float_rn(__dsub_rn(CxBy, CyBx));
+        double AxCy = __dmul_rn((double)Ax, (double)Cy);
+        double AyCx = __dmul_rn((double)Ay, (double)Cx);
+        V = __double2float_rn(__dsub_rn(AxCy, AyCx));
+        double BxAy = __dmul_rn((double)Bx, (double)Ay);
+        double ByAx = __dmul_rn((double)By, (double)Ax);
+        W = __double2float_rn(__dsub_rn(BxAy, ByAx));
+    }
+
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+
+    float det = __fadd_rn(__fadd_rn(U, V), W);
+    if (det == 0.0f) return false;
+
+    float Az = __fmul_rn(r.Sz, Akz);
+    float Bz = __fmul_rn(r.Sz, Bkz);
+    float Cz = __fmul_rn(r.Sz, Ckz);
+    float T = __fadd_rn(__fadd_rn(__fmul_rn(U, Az), __fmul_rn(V, Bz)), __fmul_rn(W, Cz));
+
+    // xorf(T, sign_mask(det)) < 0 -> reject (so T == +-0 and NaN pass)
+    float x = __uint_as_float(__float_as_uint(T) ^ (__float_as_uint(det) & 0x80000000u));
+    if (x < 0.0f) return false;
+
+    float rcp_det = __fdiv_rn(1.0f, det);
+    t_out = __fmul_rn(T, rcp_det);
+    return true;
+}
+
+// normalize(cross(b-a, c-a)); zero vector when degenerate  (normal returned by mesh_query_ray)
+__device__ __forceinline__ float3 tri_normal(float3 a, float3 b, float3 c)
+{
+    float abx = __fsub_rn(b.x, a.x), aby = __fsub_rn(b.y, a.y), abz = __fsub_rn(b.z, a.z);
+    float acx = __fsub_rn(c.x, a.x), acy = __fsub_rn(c.y, a.y), acz = __fsub_rn(c.z, a.z);
+    float cx = __fsub_rn(__fmul_rn(aby, acz), __fmul_rn(abz, acy));
+    float cy = __fsub_rn(__fmul_rn(abz, acx), __fmul_rn(abx, acz));
+    float cz = __fsub_rn(__fmul_rn(abx, acy), __fmul_rn(aby, acx));
+    float l = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
+    if (l > 0.0f) return make_float3(__fdiv_rn(cx, l), __fdiv_rn(cy, l), __fdiv_rn(cz, l));
+    return make_float3(0.0f, 0.0f, 0.0f);
+}
+
+// kernel.py:6-8   v - 2*dot(v,n)*n
+__device__ __forceinline__ float3 reflect(float3 v, float3 n)
+{
+    float d = __fadd_rn(__fadd_rn(__fmul_rn(v.x, n.x), __fmul_rn(v.y, n.y)), __fmul_rn(v.z, n.z));
+    float s = __fmul_rn(2.0f, d);
+    return make_float3(__fsub_rn(v.x, __fmul_rn(s, n.x)), __fsub_rn(v.y, __fmul_rn(s, n.y)),
+                       __fsub_rn(v.z, __fmul_rn(s, n.z)));
+}
+
+// pos + dir*t   (kernel.py:87,94)
+__device__ __forceinline__ float3 advance(float3 p, float3 d, float t)
+{
+    return make_float3(__fadd_rn(p.x, __fmul_rn(d.x, t)), __fadd_rn(p.y, __fmul_rn(d.y, t)),
+                       __fadd_rn(p.z, __fmul_rn(d.z, t)));
+}
+
+} // namespace rfrt

@@ -1,0 +1,623 @@
+// rfrt_trace.cu — the trace kernels (sm_100a) and their C-ABI launchers.
+//
+//   k_gen_dirs      kernel.py:51-52  directions of a chunk of rays (fp64 deterministic math, no divergence)
+//   k_trace_env     kernel.py:57-98  persistent wavefront kernel: every lane owns one ray, runs one bounce
+//                                    iteration per loop trip and is refilled with a fresh ray (warp-
+//                                    aggregated fetch: ballot + popc + one atomic per warp) as soon as its
+//                                    ray misses the environment or exhausts its bounces
+//   k_trace_receive kernel.py:38-98  literal replay for the rare (ray, receiver) candidates + the per-path
+//                                    post-processing of tracer.py:102-115
+//   k_trace_compat  kernel.py:38-98  the reference kernel's dense contract (tracer.py:75-79)
+//   k_query         test probe for closest_hit
+#include <cmath>
+
+#include "rfrt_trace.cuh"
+
+namespace rfrt {
+
+__constant__ uint8_t c_rx_faces[3 * 128];
+
+namespace {
+
+constexpr int TRACE_THREADS = 128;
+constexpr int MAX_RECV_BOUNCES = 32;
+
+struct TraceParams {
+    const BvhNode *nodes;
+    const BvhTri *tris;
+    int64_t n_tris;
+    // receivers
+    const BvhNode *rx_nodes;
+    const int32_t *rx_order;
+    const float *rx_verts;
+    const double *rx_centers;
+    int64_t n_rx;
+    int32_t n_unit;
+    int32_t n_faces;
+    float rx_radius;
+    // rays
+    float3 tx;
+    int32_t max_bounces;
+    int64_t chunk_begin; // global id of the first ray of this chunk
+    int64_t chunk_n;
+    const float4 *dirs;
+    // outputs
+    unsigned long long *counters;
+    uint4 *candidates;
+    int64_t cand_capacity;
+    int32_t *hit_tri; // dense dumps, row = ray - dump_begin
+    float *hit_t;
+    int64_t dump_begin;
+    int32_t stack_depth;
+};
+
+__global__ void k_gen_dirs(int64_t ray_begin, int64_t n, float4 *__restrict__ dirs)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 d = ray_direction((uint32_t)(ray_begin + i));
+    dirs[i] = make_float4(d.x, d.y, d.z, 0.0f);
+}
+
+// Conservative sphere filter in front of the exact 80-triangle receiver query: can the segment
+// [0, t_limit] of the ray come within the receiver's bounding sphere?
+__device__ __forceinline__ bool rx_sphere_filter(float3 p, float3 d, float cx, float cy, float cz, float radius,
+                                                 float t_limit)
+{
+    float ox = cx - p.x, oy = cy - p.y, oz = cz - p.z;
+    float dd = d.x * d.x + d.y * d.y + d.z * d.z;
+    float od = ox * d.x + oy * d.y + oz * d.z;
+    float oo = ox * ox + oy * oy + oz * oz;
+    float r = radius * 1.01f + 1.0e-5f * (sqrtf(oo) + 1.0f);
+    float r2 = r * r;
+    if (oo <= r2) return true; // origin inside the (inflated) sphere
+    float tc = od / dd;
+    if (tc < 0.0f) return false;
+    float perp2 = oo - tc * od;
+    if (perp2 > r2 * 1.01f + 1.0e-12f) return false;
+    float half = sqrtf(fmaxf(r2 * 1.01f - perp2, 0.0f) / dd);
+    return tc - half <= t_limit * 1.0001f + 1.0e-6f;
+}
+
+// Exact receiver test for one segment (kernel.py:71,85) behind a conservative sphere filter; appends the
+// candidate (ray id, receiver, bounce).  Rarely taken, so kept out of line to spare the hot loop's registers.
+__device__ __noinline__ void rx_test_and_emit(const TraceParams &P, int k, float3 pos, float3 dir, const WoopRay &wr,
+                                              bool hit_env, float t_env, float t_limit, uint32_t gid, int bounce)
+{
+    float cx = (float)__ldg(P.rx_centers + 3 * k), cy = (float)__ldg(P.rx_centers + 3 * k + 1),
+          cz = (float)__ldg(P.rx_centers + 3 * k + 2);
+    if (!rx_sphere_filter(pos, dir, cx, cy, cz, P.rx_radius, t_limit)) return;
+    float t_rx;
+    if (!rx_query(P.rx_verts + (int64_t)k * P.n_unit * 3, c_rx_faces, P.n_faces, wr, 1.0e6f, t_rx)) return;
+    if (hit_env && !(t_env > t_rx)) return;
+    unsigned long long slot = atomicAdd(&P.counters[RFRT_CTR_CANDIDATES], 1ull);
+    if ((int64_t)slot < P.cand_capacity) P.candidates[slot] = make_uint4(gid, (uint32_t)k, (uint32_t)bounce, 0u);
+}
+
+template <bool DUMP>
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P)
+{
+    extern __shared__ int s_stack_raw[];
+    int *stack = s_stack_raw + threadIdx.x;
+    float *stack_t = reinterpret_cast<float *>(s_stack_raw + P.stack_depth * TRACE_THREADS) + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+
+    bool has_ray = false;
+    bool exhausted = false; // warp-uniform
+    float3 pos = make_float3(0.f, 0.f, 0.f), dir = make_float3(0.f, 0.f, 1.f);
+    int bounce = 0;
+    int64_t ray = 0;
+    unsigned int n_seg = 0, n_hit = 0;
+
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, !has_ray);
+        if (idle != 0u && !exhausted) {
+            int cnt = __popc(idle);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&P.counters[RFRT_CTR_NEXT_RAY], (unsigned long long)cnt);
+            base = __shfl_sync(FULL, base, 0);
+            if (!has_ray) {
+                int64_t r = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
+                if (r < P.chunk_n) {
+                    float4 d4 = __ldg(P.dirs + r);
+                    dir = make_float3(d4.x, d4.y, d4.z);
+                    pos = P.tx;
+                    bounce = 0;
+                    ray = r;
+                    has_ray = true;
+                }
+            }
+            if ((int64_t)base + cnt >= P.chunk_n) exhausted = true;
+        }
+        if (!__any_sync(FULL, has_ray)) break;
+        if (!has_ray) continue;
+
+        // ---- one bounce iteration (kernel.py:57-98, environment branch) -----------------------
+        WoopRay wr = woop_setup(pos, dir);
+        SlabRay sr = slab_setup(pos, dir);
+        Hit h;
+        h.t = 1.0e6f; h.face = -1; h.slot = -1;
+        closest_hit(P.nodes, P.tris, P.n_tris, wr, sr, stack, stack_t, TRACE_THREADS, h);
+        const bool hit_env = h.face >= 0;
+        ++n_seg;
+
+        if (P.n_rx > 0) {
+            // kernel.py:71,85: receivers hit strictly before the environment (or at all, if it is missed)
+            const float t_limit = hit_env ? h.t : 1.0e6f;
+            const uint32_t gid = (uint32_t)(P.chunk_begin + ray);
+            if (P.n_rx == 1) {
+                rx_test_and_emit(P, 0, pos, dir, wr, hit_env, h.t, t_limit, gid, bounce);
+            } else {
+                // enumerate every receiver whose box overlaps the segment [0, t_limit]
+                int sp = 0;
+                int node = 0;
+                for (;;) {
+                    const float4 *np = reinterpret_cast<const float4 *>(P.rx_nodes + node);
+                    float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+                    int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
+                    float tn0, tn1;
+                    bool h0 = slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_limit, tn0);
+                    bool h1 = slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_limit, tn1);
+                    int c0 = q3.x, c1 = q3.y;
+                    if (c1 == c0) h1 = false;
+                    if (h0) {
+                        if (c0 < 0) rx_test_and_emit(P, __ldg(P.rx_order + (~c0)), pos, dir, wr, hit_env, h.t, t_limit, gid, bounce);
+                        else { stack[sp * TRACE_THREADS] = c0; ++sp; }
+                    }
+                    if (h1) {
+                        if (c1 < 0) rx_test_and_emit(P, __ldg(P.rx_order + (~c1)), pos, dir, wr, hit_env, h.t, t_limit, gid, bounce);
+                        else { stack[sp * TRACE_THREADS] = c1; ++sp; }
+                    }
+                    if (sp == 0) break;
+                    --sp;
+                    node = stack[sp * TRACE_THREADS];
+                }
+            }
+        }
+
+        if (DUMP) {
+            int64_t row = (P.chunk_begin + ray - P.dump_begin) * P.max_bounces + bounce;
+            if (P.hit_tri) P.hit_tri[row] = hit_env ? h.face : -1;
+            if (P.hit_t) P.hit_t[row] = hit_env ? h.t : 0.0f;
+        }
+
+        if (hit_env) {
+            ++n_hit;
+            pos = advance(pos, dir, h.t);                 // kernel.py:94
+            float3 a, b, c; int idx;
+            tri_vertices(P.tris, h.slot, a, b, c, idx);
+            dir = reflect(dir, tri_normal(a, b, c));      // kernel.py:96
+            ++bounce;
+            if (bounce >= P.max_bounces) has_ray = false;
+        } else {
+            has_ray = false; // a miss repeats forever in the reference (kernel.py:97-98): nothing more to do
+        }
+    }
+
+    // warp-reduced counters
+    for (int o = 16; o > 0; o >>= 1) {
+        n_seg += __shfl_xor_sync(FULL, n_seg, o);
+        n_hit += __shfl_xor_sync(FULL, n_hit, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&P.counters[RFRT_CTR_SEGMENTS], (unsigned long long)n_seg);
+        atomicAdd(&P.counters[RFRT_CTR_ENV_HITS], (unsigned long long)n_hit);
+    }
+}
+
+// ---- literal replay ------------------------------------------------------------------------------
+struct LiteralEnv {
+    const BvhNode *nodes;
+    const BvhTri *tris;
+    int64_t n_tris;
+};
+
+// kernel.py:38-98 for one ray and one receiver.  Sink receives the vertex writes and RX-hit events.
+template <class Sink>
+__device__ __forceinline__ void literal_trace(const LiteralEnv &E, const float *__restrict__ rx_verts, int n_faces,
+                                              float3 tx, int max_bounces, uint32_t tid, int *stack, float *stack_t,
+                                              int stride, Sink &sink)
+{
+    float3 dir = ray_direction(tid); // kernel.py:51-52
+    float3 pos = tx;                 // :53
+    sink.vertex(0, pos);             // :55
+    for (int bounce = 0; bounce < max_bounces; ++bounce) {
+        WoopRay wr = woop_setup(pos, dir);
+        SlabRay sr = slab_setup(pos, dir);
+        float t_rx = 0.0f;
+        bool maybe_hit_rx = rx_verts ? rx_query(rx_verts, c_rx_faces, n_faces, wr, 1.0e6f, t_rx) : false; // :71
+        Hit h;
+        h.t = 1.0e6f; h.face = -1; h.slot = -1;
+        closest_hit(E.nodes, E.tris, E.n_tris, wr, sr, stack, stack_t, stride, h);                          // :82
+        bool maybe_hit_env = h.face >= 0;
+        bool hit_recv = maybe_hit_rx && (!maybe_hit_env || h.t > t_rx);                                     // :85
+        if (hit_recv) {
+            pos = advance(pos, dir, t_rx);  // :87
+            sink.vertex(bounce + 1, pos);   // :88
+            sink.received(bounce);          // :89-91
+        } else if (maybe_hit_env) {
+            pos = advance(pos, dir, h.t);   // :94
+            sink.vertex(bounce + 1, pos);   // :95
+            float3 a, b, c; int idx;
+            tri_vertices(E.tris, h.slot, a, b, c, idx);
+            dir = reflect(dir, tri_normal(a, b, c)); // :96
+        }
+    }
+}
+
+struct CompatSink {
+    float *traced;
+    float *recv_row;
+    uint32_t *mask;
+    __device__ __forceinline__ void vertex(int i, float3 p)
+    {
+        traced[3 * i] = p.x; traced[3 * i + 1] = p.y; traced[3 * i + 2] = p.z;
+    }
+    __device__ __forceinline__ void received(int bounce)
+    {
+        for (int i = 0; i < 3 * (bounce + 2); ++i) recv_row[i] = traced[i]; // kernel.py:89-90
+        *mask = 1u;                                                         // :91
+    }
+};
+
+__global__ void __launch_bounds__(TRACE_THREADS)
+k_trace_compat(LiteralEnv E, const float *__restrict__ rx_verts, int n_faces, float3 tx, int max_bounces,
+               int64_t ray_begin, int64_t n_rays, float *traced, float *received, uint32_t *mask, int stack_depth)
+{
+    extern __shared__ int s_stack_raw[];
+    int *stack = s_stack_raw + threadIdx.x;
+    float *stack_t = reinterpret_cast<float *>(s_stack_raw + stack_depth * TRACE_THREADS) + threadIdx.x;
+    const int64_t row = 3 * (int64_t)(max_bounces + 1);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_rays; i += (int64_t)gridDim.x * blockDim.x) {
+        CompatSink sink{traced + i * row, received + i * row, mask + i};
+        literal_trace(E, rx_verts, n_faces, tx, max_bounces, (uint32_t)(ray_begin + i), stack, stack_t,
+                      TRACE_THREADS, sink);
+    }
+}
+
+struct RecordSink {
+    float path[3 * (MAX_RECV_BOUNCES + 1)];
+    int last_rx_bounce;
+    int first_rx_bounce;
+    __device__ __forceinline__ void vertex(int i, float3 p)
+    {
+        path[3 * i] = p.x; path[3 * i + 1] = p.y; path[3 * i + 2] = p.z;
+    }
+    __device__ __forceinline__ void received(int bounce)
+    {
+        if (first_rx_bounce < 0) first_rx_bounce = bounce;
+        last_rx_bounce = bounce;
+    }
+};
+
+__device__ __forceinline__ float norm3_f32(float x, float y, float z)
+{
+    return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+}
+
+// tracer.py:34-61
+__device__ __forceinline__ double bounce_amplitude(double angle_between)
+{
+    if (isnan(angle_between)) return 0.0;
+    const double PI = 3.141592653589793;
+    double theta = PI / 2 - angle_between / 2;
+    const double n_1 = 5.0, n_2 = 1.0;
+    double theta_i = asin((n_2 * sin(theta)) / n_1);
+    double num = n_2 * cos(theta_i) - n_1 * cos(theta);
+    double denom = n_2 * cos(theta_i) + n_1 * cos(theta);
+    double q = num / denom;
+    double amp = -(q * q);
+    if (amp < -1) amp = -1;
+    if (isnan(amp)) return 0.0;
+    return -amp;
+}
+
+struct ReceiveParams {
+    LiteralEnv env;
+    const float *rx_verts;
+    int32_t n_unit;
+    int32_t n_faces;
+    float3 tx;
+    int32_t max_bounces;
+    const uint4 *candidates;
+    int64_t cand_capacity;
+    unsigned long long *counters;
+    double amp0, light_speed, sample_rate;
+    uint32_t *rec_ray;
+    int32_t *rec_rx;
+    int32_t *rec_nverts;
+    int64_t *rec_bin;
+    double *rec_amp;
+    double *rec_dist;
+    float *rec_paths;
+    int64_t rec_capacity;
+    int32_t stack_depth;
+};
+
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_receive(const ReceiveParams P)
+{
+    extern __shared__ int s_stack_raw[];
+    int *stack = s_stack_raw + threadIdx.x;
+    float *stack_t = reinterpret_cast<float *>(s_stack_raw + P.stack_depth * TRACE_THREADS) + threadIdx.x;
+    int64_t n_cand = (int64_t)P.counters[RFRT_CTR_CANDIDATES];
+    if (n_cand > P.cand_capacity) n_cand = P.cand_capacity;
+    const int row = 3 * (P.max_bounces + 1);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_cand; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 cand = P.candidates[i];
+        RecordSink sink;
+        sink.last_rx_bounce = -1;
+        sink.first_rx_bounce = -1;
+        literal_trace(P.env, P.rx_verts + (int64_t)cand.y * P.n_unit * 3, P.n_faces, P.tx, P.max_bounces, cand.x,
+                      stack, stack_t, TRACE_THREADS, sink);
+        // a candidate raised at a later bounce than the replay's first receiver hit is a duplicate
+        if (sink.last_rx_bounce < 0 || sink.first_rx_bounce != (int)cand.z) continue;
+        int nverts = sink.last_rx_bounce + 2;
+        // tracer.py:90-97: strip at the first vertex containing a NaN
+        for (int v = 0; v < nverts; ++v)
+            if (isnan(sink.path[3 * v]) || isnan(sink.path[3 * v + 1]) || isnan(sink.path[3 * v + 2])) { nverts = v; break; }
+        // tracer.py:102-115
+        double amplitude = P.amp0;
+        double distance = 0.0;
+        const float *p = sink.path;
+        if (nverts >= 2) {
+            for (int v = 0; v + 2 < nverts; ++v) {
+                float s1x = __fsub_rn(p[3 * v + 3], p[3 * v]), s1y = __fsub_rn(p[3 * v + 4], p[3 * v + 1]),
+                      s1z = __fsub_rn(p[3 * v + 5], p[3 * v + 2]);
+                float s2x = __fsub_rn(p[3 * v + 6], p[3 * v + 3]), s2y = __fsub_rn(p[3 * v + 7], p[3 * v + 4]),
+                      s2z = __fsub_rn(p[3 * v + 8], p[3 * v + 5]);
+                float l1 = norm3_f32(s1x, s1y, s1z);
+                float l2 = norm3_f32(s2x, s2y, s2z);
+                float dot = __fadd_rn(__fadd_rn(__fmul_rn(s1x, s2x), __fmul_rn(s1y, s2y)), __fmul_rn(s1z, s2z));
+                float q = __fdiv_rn(dot, __fmul_rn(l1, l2));
+                float angle = (q > 1.0f || q < -1.0f || isnan(q)) ? __int_as_float(0x7fc00000)
+                                                                   : __double2float_rn(acos((double)q));
+                amplitude *= bounce_amplitude((double)angle);
+                distance = __dadd_rn(distance, (double)l1);
+            }
+            const float *u = p + 3 * (nverts - 2), *w = p + 3 * (nverts - 1);
+            distance = __dadd_rn(distance, (double)norm3_f32(__fsub_rn(u[0], w[0]), __fsub_rn(u[1], w[1]),
+                                                             __fsub_rn(u[2], w[2])));
+        }
+        double samples = __dmul_rn(__ddiv_rn(distance, P.light_speed), P.sample_rate);
+        long long bin = (long long)samples; // int() truncation, tracer.py:115
+        unsigned long long slot = atomicAdd(&P.counters[RFRT_CTR_RECORDS], 1ull);
+        if ((int64_t)slot < P.rec_capacity) {
+            P.rec_ray[slot] = cand.x;
+            P.rec_rx[slot] = (int32_t)cand.y;
+            P.rec_nverts[slot] = nverts;
+            P.rec_bin[slot] = bin;
+            P.rec_amp[slot] = amplitude;
+            P.rec_dist[slot] = distance;
+            if (P.rec_paths) {
+                float *dst = P.rec_paths + (int64_t)slot * row;
+                for (int k = 0; k < row; ++k) dst[k] = k < 3 * nverts ? p[k] : __int_as_float(0x7fc00000);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TRACE_THREADS)
+k_query(LiteralEnv E, const float *__restrict__ origins, const float *__restrict__ dirs, int64_t n, float max_t,
+        float *t_out, int32_t *face_out, int stack_depth)
+{
+    extern __shared__ int s_stack_raw[];
+    int *stack = s_stack_raw + threadIdx.x;
+    float *stack_t = reinterpret_cast<float *>(s_stack_raw + stack_depth * TRACE_THREADS) + threadIdx.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float3 p = make_float3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
+        float3 d = make_float3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
+        WoopRay wr = woop_setup(p, d);
+        SlabRay sr = slab_setup(p, d);
+        Hit h;
+        h.t = max_t; h.face = -1; h.slot = -1;
+        closest_hit(E.nodes, E.tris, E.n_tris, wr, sr, stack, stack_t, TRACE_THREADS, h);
+        t_out[i] = h.t;
+        face_out[i] = h.face;
+    }
+}
+
+int stack_depth_for(const Mesh *m, const RxSet *r)
+{
+    int d = m->bvh.max_depth;
+    if (r && r->bvh.max_depth > d) d = r->bvh.max_depth;
+    d += 2;
+    if (d < 8) d = 8;
+    return d;
+}
+
+size_t stack_bytes(int depth) { return (size_t)depth * TRACE_THREADS * 2 * sizeof(int); }
+
+int grid_for(const void *kernel, size_t smem, int *out_grid)
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    RFRT_CUDA(cudaGetDevice(&dev));
+    RFRT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (smem > 48 * 1024) RFRT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RFRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRACE_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    *out_grid = sms * per_sm;
+    return RFRT_OK;
+}
+
+int upload_faces(const RxSet *r, cudaStream_t stream)
+{
+    RFRT_CUDA(cudaMemcpyToSymbolAsync(c_rx_faces, r->faces, sizeof(uint8_t) * 3 * (size_t)r->n_faces, 0,
+                                      cudaMemcpyHostToDevice, stream));
+    return RFRT_OK;
+}
+
+} // namespace
+} // namespace rfrt
+
+using namespace rfrt;
+
+extern "C" int rfrt_ray_directions(int64_t ray_begin, int64_t ray_end, float *d_dirs, void *stream)
+{
+    int64_t n = ray_end - ray_begin;
+    if (n < 0 || (n > 0 && !d_dirs)) { set_error("rfrt_ray_directions: bad arguments"); return RFRT_ERR_INVALID; }
+    if (n == 0) return RFRT_OK;
+    k_gen_dirs<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ray_begin, n, (float4 *)d_dirs);
+    RFRT_CUDA(cudaGetLastError());
+    return RFRT_OK;
+}
+
+extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *h_tx_pos, int32_t max_bounces,
+                          int64_t ray_begin, int64_t ray_end, uint32_t flags, float *d_dir_scratch,
+                          int64_t chunk_rays, uint64_t *d_counters, uint32_t *d_candidates, int64_t cand_capacity,
+                          int32_t *d_hit_tri, float *d_hit_t, void *stream_)
+{
+    (void)flags;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Mesh *m = get_mesh(env_mesh);
+    if (!m) { set_error("rfrt_trace: unknown environment mesh handle"); return RFRT_ERR_HANDLE; }
+    RxSet *r = nullptr;
+    if (rxset) {
+        r = get_rxset(rxset);
+        if (!r) { set_error("rfrt_trace: unknown receiver set handle"); return RFRT_ERR_HANDLE; }
+        if (!d_candidates || cand_capacity <= 0) { set_error("rfrt_trace: candidate buffer required with receivers"); return RFRT_ERR_INVALID; }
+    }
+    int64_t n = ray_end - ray_begin;
+    if (!h_tx_pos || !d_counters || max_bounces < 0 || n < 0 || ray_end > (1ll << 32) || ray_begin < 0) {
+        set_error("rfrt_trace: bad arguments (need tx_pos, counters, 0 <= ray ids <= 2^32)");
+        return RFRT_ERR_INVALID;
+    }
+    if (n == 0 || max_bounces == 0) return RFRT_OK;
+    if (!d_dir_scratch) { set_error("rfrt_trace: d_dir_scratch required"); return RFRT_ERR_INVALID; }
+    if (chunk_rays <= 0) chunk_rays = 1ll << 24;
+
+    TraceParams P;
+    P.nodes = m->bvh.nodes; P.tris = m->tris; P.n_tris = m->bvh.n_prims;
+    P.rx_nodes = r ? r->bvh.nodes : nullptr; P.rx_order = r ? r->bvh.prim_order : nullptr;
+    P.rx_verts = r ? r->verts : nullptr; P.rx_centers = r ? r->centers : nullptr;
+    P.n_rx = r ? r->n_receivers : 0; P.n_unit = r ? r->n_unit : 0; P.n_faces = r ? r->n_faces : 0;
+    P.rx_radius = r ? (float)r->radius : 0.0f;
+    P.tx = make_float3(h_tx_pos[0], h_tx_pos[1], h_tx_pos[2]);
+    P.max_bounces = max_bounces;
+    P.dirs = (const float4 *)d_dir_scratch;
+    P.counters = (unsigned long long *)d_counters;
+    P.candidates = (uint4 *)d_candidates; P.cand_capacity = r ? cand_capacity : 0;
+    P.hit_tri = d_hit_tri; P.hit_t = d_hit_t; P.dump_begin = ray_begin;
+    P.stack_depth = stack_depth_for(m, r);
+    const bool dump = d_hit_tri || d_hit_t;
+    const size_t smem = stack_bytes(P.stack_depth);
+    const void *kern = dump ? (const void *)k_trace_env<true> : (const void *)k_trace_env<false>;
+    int grid = 0;
+    int rc = grid_for(kern, smem, &grid);
+    if (rc) return rc;
+    if (r) { rc = upload_faces(r, stream); if (rc) return rc; }
+
+    for (int64_t c0 = ray_begin; c0 < ray_end; c0 += chunk_rays) {
+        int64_t cn = ray_end - c0 < chunk_rays ? ray_end - c0 : chunk_rays;
+        k_gen_dirs<<<(unsigned)((cn + 255) / 256), 256, 0, stream>>>(c0, cn, (float4 *)d_dir_scratch);
+        RFRT_CUDA(cudaMemsetAsync(d_counters + RFRT_CTR_NEXT_RAY, 0, sizeof(uint64_t), stream));
+        P.chunk_begin = c0; P.chunk_n = cn;
+        int g = grid;
+        int64_t need = (cn + TRACE_THREADS - 1) / TRACE_THREADS;
+        if (need < g) g = (int)need;
+        if (dump) k_trace_env<true><<<g, TRACE_THREADS, smem, stream>>>(P);
+        else k_trace_env<false><<<g, TRACE_THREADS, smem, stream>>>(P);
+    }
+    RFRT_CUDA(cudaGetLastError());
+    return RFRT_OK;
+}
+
+extern "C" int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const float *h_tx_pos,
+                                  int32_t max_bounces, const uint32_t *d_candidates, int64_t cand_capacity,
+                                  uint64_t *d_counters, double amp0, double light_speed_mps, double sample_rate_hz,
+                                  uint32_t *d_rec_ray, int32_t *d_rec_rx, int32_t *d_rec_nverts, int64_t *d_rec_bin,
+                                  double *d_rec_amp, double *d_rec_dist, float *d_rec_paths, int64_t rec_capacity,
+                                  void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Mesh *m = get_mesh(env_mesh);
+    RxSet *r = get_rxset(rxset);
+    if (!m || !r) { set_error("rfrt_trace_receive: unknown handle"); return RFRT_ERR_HANDLE; }
+    if (!h_tx_pos || !d_candidates || !d_counters || !d_rec_ray || !d_rec_rx || !d_rec_nverts || !d_rec_bin ||
+        !d_rec_amp || !d_rec_dist || rec_capacity <= 0 || cand_capacity <= 0) {
+        set_error("rfrt_trace_receive: null buffer or empty capacity");
+        return RFRT_ERR_INVALID;
+    }
+    if (max_bounces < 0 || max_bounces > MAX_RECV_BOUNCES) {
+        set_error("rfrt_trace_receive: max_bounces must be in [0, 32]");
+        return RFRT_ERR_INVALID;
+    }
+    ReceiveParams P;
+    P.env.nodes = m->bvh.nodes; P.env.tris = m->tris; P.env.n_tris = m->bvh.n_prims;
+    P.rx_verts = r->verts; P.n_unit = r->n_unit; P.n_faces = r->n_faces;
+    P.tx = make_float3(h_tx_pos[0], h_tx_pos[1], h_tx_pos[2]);
+    P.max_bounces = max_bounces;
+    P.candidates = (const uint4 *)d_candidates; P.cand_capacity = cand_capacity;
+    P.counters = (unsigned long long *)d_counters;
+    P.amp0 = amp0; P.light_speed = light_speed_mps; P.sample_rate = sample_rate_hz;
+    P.rec_ray = d_rec_ray; P.rec_rx = d_rec_rx; P.rec_nverts = d_rec_nverts; P.rec_bin = d_rec_bin;
+    P.rec_amp = d_rec_amp; P.rec_dist = d_rec_dist; P.rec_paths = d_rec_paths; P.rec_capacity = rec_capacity;
+    P.stack_depth = stack_depth_for(m, nullptr);
+    const size_t smem = stack_bytes(P.stack_depth);
+    int grid = 0;
+    int rc = grid_for((const void *)k_trace_receive, smem, &grid);
+    if (rc) return rc;
+    rc = upload_faces(r, stream);
+    if (rc) return rc;
+    k_trace_receive<<<grid, TRACE_THREADS, smem, stream>>>(P);
+    RFRT_CUDA(cudaGetLastError());
+    return RFRT_OK;
+}
+
+extern "C" int rfrt_trace_paths_compat(rfrt_handle env_mesh, const float *h_tx_pos, rfrt_handle rxset,
+                                       int64_t rx_index, int32_t max_bounces, int64_t ray_begin, int64_t n_rays,
+                                       float *d_traced_paths, float *d_received_paths, uint32_t *d_row_mask,
+                                       void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Mesh *m = get_mesh(env_mesh);
+    if (!m) { set_error("rfrt_trace_paths_compat: unknown environment mesh handle"); return RFRT_ERR_HANDLE; }
+    RxSet *r = nullptr;
+    if (rxset) {
+        r = get_rxset(rxset);
+        if (!r) { set_error("rfrt_trace_paths_compat: unknown receiver set handle"); return RFRT_ERR_HANDLE; }
+        if (rx_index < 0 || rx_index >= r->n_receivers) { set_error("rfrt_trace_paths_compat: rx_index out of range"); return RFRT_ERR_INVALID; }
+    }
+    if (!h_tx_pos || !d_traced_paths || !d_received_paths || !d_row_mask || max_bounces < 0 || n_rays < 0 ||
+        ray_begin < 0 || ray_begin + n_rays > (1ll << 32)) {
+        set_error("rfrt_trace_paths_compat: bad arguments");
+        return RFRT_ERR_INVALID;
+    }
+    if (n_rays == 0) return RFRT_OK;
+    LiteralEnv E{m->bvh.nodes, m->tris, m->bvh.n_prims};
+    int depth = stack_depth_for(m, nullptr);
+    const size_t smem = stack_bytes(depth);
+    int grid = 0;
+    int rc = grid_for((const void *)k_trace_compat, smem, &grid);
+    if (rc) return rc;
+    int64_t need = (n_rays + TRACE_THREADS - 1) / TRACE_THREADS;
+    if (need < grid) grid = (int)need;
+    if (r) { rc = upload_faces(r, stream); if (rc) return rc; }
+    k_trace_compat<<<grid, TRACE_THREADS, smem, stream>>>(
+        E, r ? r->verts + rx_index * r->n_unit * 3 : nullptr, r ? r->n_faces : 0,
+        make_float3(h_tx_pos[0], h_tx_pos[1], h_tx_pos[2]), max_bounces, ray_begin, n_rays, d_traced_paths,
+        d_received_paths, d_row_mask, depth);
+    RFRT_CUDA(cudaGetLastError());
+    return RFRT_OK;
+}
+
+extern "C" int rfrt_query_closest(rfrt_handle mesh, const float *d_origins, const float *d_dirs, int64_t n,
+                                  float max_t, float *d_t, int32_t *d_face, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Mesh *m = get_mesh(mesh);
+    if (!m) { set_error("rfrt_query_closest: unknown mesh handle"); return RFRT_ERR_HANDLE; }
+    if (n < 0 || (n > 0 && (!d_origins || !d_dirs || !d_t || !d_face))) { set_error("rfrt_query_closest: bad arguments"); return RFRT_ERR_INVALID; }
+    if (n == 0) return RFRT_OK;
+    LiteralEnv E{m->bvh.nodes, m->tris, m->bvh.n_prims};
+    int depth = stack_depth_for(m, nullptr);
+    const size_t smem = stack_bytes(depth);
+    int grid = 0;
+    int rc = grid_for((const void *)k_query, smem, &grid);
+    if (rc) return rc;
+    int64_t need = (n + TRACE_THREADS - 1) / TRACE_THREADS;
+    if (need < grid) grid = (int)need;
+    k_query<<<grid, TRACE_THREADS, smem, stream>>>(E, d_origins, d_dirs, n, max_t, d_t, d_face, depth);
+    RFRT_CUDA(cudaGetLastError());
+    return RFRT_OK;
+}

@@ -1,0 +1,136 @@
+// rfrt_trace.cuh — device-side BVH traversal shared by the trace kernels.
+#pragma once
+#include "rfrt_internal.h"
+#include "rfrt_math.cuh"
+
+namespace rfrt {
+
+// Ray constants for the (conservative) slab test.  FMA is fine here: boxes are padded and the slab
+// test never decides a hit, it only prunes.
+struct SlabRay {
+    float ix, iy, iz; // 1/d   (|d| clamped to >= 1e-18 so it stays finite)
+    float ox, oy, oz; // o * (1/d)
+};
+
+__device__ __forceinline__ SlabRay slab_setup(float3 p, float3 d)
+{
+    SlabRay s;
+    // a zero (or denormal-small) component would give inf * 0 = NaN in the fused slab arithmetic; tilt the
+    // ray by 1e-18 instead: a parallel ray then sees (-huge, +huge) inside a slab and (huge, huge) outside
+    const float tiny = 1.0e-18f;
+    float dx = fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x;
+    float dy = fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y;
+    float dz = fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z;
+    s.ix = __fdiv_rn(1.0f, dx); s.iy = __fdiv_rn(1.0f, dy); s.iz = __fdiv_rn(1.0f, dz);
+    s.ox = p.x * s.ix; s.oy = p.y * s.iy; s.oz = p.z * s.iz;
+    return s;
+}
+
+// entry distance of the padded box; hit iff  max(tnear,0) <= min(tfar, t_max).
+__device__ __forceinline__ bool slab_hit(const SlabRay &s, float lx, float ly, float lz, float hx, float hy, float hz,
+                                         float t_max, float &t_near)
+{
+    float t0x = fmaf(lx, s.ix, -s.ox), t1x = fmaf(hx, s.ix, -s.ox);
+    float t0y = fmaf(ly, s.iy, -s.oy), t1y = fmaf(hy, s.iy, -s.oy);
+    float t0z = fmaf(lz, s.iz, -s.oz), t1z = fmaf(hz, s.iz, -s.oz);
+    float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+    float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), t_max));
+    t_near = tn;
+    // a small relative slack keeps FMA rounding from ever culling a box the exact test would enter
+    return tn <= tf * 1.0000004f + 1.0e-30f;
+}
+
+__device__ __forceinline__ void tri_vertices(const BvhTri *__restrict__ tris, int slot, float3 &a, float3 &b,
+                                             float3 &c, int &index)
+{
+    const float4 *p = reinterpret_cast<const float4 *>(tris + slot);
+    float4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
+    a = make_float3(v0.x, v0.y, v0.z);
+    b = make_float3(v0.w, v1.x, v1.y);
+    c = make_float3(v1.z, v1.w, v2.x);
+    index = __float_as_int(v2.y);
+}
+
+struct Hit {
+    float t;   // best distance so far (starts at max_t)
+    int face;  // original triangle index (-1 = none)
+    int slot;  // sorted slot of that triangle
+};
+
+// mesh_query_ray (kernel.py:71,82): closest accepted hit, 0 <= t < max_t; equal t -> lowest index.
+// `stack` / `stack_t` point at this thread's column of the shared-memory stack (stride = blockDim.x).
+__device__ __forceinline__ void closest_hit(const BvhNode *__restrict__ nodes, const BvhTri *__restrict__ tris,
+                                            int64_t n_prims, const WoopRay &wr, const SlabRay &sr, int *stack,
+                                            float *stack_t, int stride, Hit &h)
+{
+    if (n_prims <= 0) return;
+    int sp = 0;
+    int node = 0;
+    for (;;) {
+        const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
+        float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+        int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
+        float tn0, tn1;
+        bool h0 = slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, h.t, tn0);
+        bool h1 = slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, h.t, tn1);
+        int c0 = q3.x, c1 = q3.y;
+        if (h0 && c0 < 0) {
+            float3 a, b, c; int idx; float t;
+            tri_vertices(tris, ~c0, a, b, c, idx);
+            if (woop_hit(wr, a, b, c, t) && t >= 0.0f && (t < h.t || (t == h.t && h.face >= 0 && idx < h.face))) {
+                h.t = t; h.face = idx; h.slot = ~c0;
+            }
+            h0 = false;
+        }
+        if (h1 && c1 < 0 && c1 != c0) {
+            float3 a, b, c; int idx; float t;
+            tri_vertices(tris, ~c1, a, b, c, idx);
+            if (woop_hit(wr, a, b, c, t) && t >= 0.0f && (t < h.t || (t == h.t && h.face >= 0 && idx < h.face))) {
+                h.t = t; h.face = idx; h.slot = ~c1;
+            }
+            h1 = false;
+        }
+        if (c1 < 0) h1 = false;
+        if (h0 && h1) {
+            // descend into the nearer child first, defer the other with its entry distance
+            bool swap = tn1 < tn0;
+            int near_c = swap ? c1 : c0, far_c = swap ? c0 : c1;
+            float far_t = swap ? tn0 : tn1;
+            stack[sp * stride] = far_c;
+            stack_t[sp * stride] = far_t;
+            ++sp;
+            node = near_c;
+            continue;
+        }
+        if (h0) { node = c0; continue; }
+        if (h1) { node = c1; continue; }
+        // pop, skipping entries that the current best already rules out
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            float tn = stack_t[sp * stride];
+            if (tn <= h.t) { node = stack[sp * stride]; found = true; break; }
+        }
+        if (!found) break;
+    }
+}
+
+// Brute-force exact receiver query (kernel.py:71 against the 80-triangle icosphere of receiver k):
+// returns true and the closest t in [0, max_t).
+__device__ __forceinline__ bool rx_query(const float *__restrict__ rx_verts, const uint8_t *faces, int n_faces,
+                                         const WoopRay &wr, float max_t, float &t_out)
+{
+    float best = max_t;
+    for (int f = 0; f < n_faces; ++f) {
+        int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+        float3 a = make_float3(__ldg(rx_verts + 3 * i0), __ldg(rx_verts + 3 * i0 + 1), __ldg(rx_verts + 3 * i0 + 2));
+        float3 b = make_float3(__ldg(rx_verts + 3 * i1), __ldg(rx_verts + 3 * i1 + 1), __ldg(rx_verts + 3 * i1 + 2));
+        float3 c = make_float3(__ldg(rx_verts + 3 * i2), __ldg(rx_verts + 3 * i2 + 1), __ldg(rx_verts + 3 * i2 + 2));
+        float t;
+        if (woop_hit(wr, a, b, c, t) && t < best && t >= 0.0f) best = t;
+    }
+    t_out = best;
+    return best < max_t;
+}
+
+} // namespace rfrt

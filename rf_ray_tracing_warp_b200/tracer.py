@@ -1,0 +1,343 @@
+"""Host side of the hot path: the reference's ``Tracer`` API on top of librfrt.so.
+
+Mirrors /root/reference/tracer.py:
+  * ``Tracer(environment_trimesh, light_speed_mps, sample_rate_hz, sample_window_s, max_bounces, tx_num_rays)``
+    (tracer.py:12) — uploads the mesh and builds the LBVH (replaces wp.Mesh, tracer.py:22-24)
+  * ``Tracer.compute_cir(tx_pos, tx_power, rx_pos, rx_radius) -> (cleaned_paths, impulse_response)``
+    (tracer.py:63,121) — same argument meaning, same return types and ordering (ascending ray id)
+and adds the batched entry points the reference lacks (``compute_cir_multi``, ``coverage``,
+``trace_segments``) plus ``trace_paths_kernel`` — the dense 7-argument launch of tracer.py:75-79.
+
+PyTorch is plumbing only here (device buffers, streams, torch.distributed).  Every computation on the path
+runs in the hand-written CUDA kernels behind the C ABI; there is no CPU fallback.
+"""
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import RfrtError, c_f, c_i32, c_i64, c_u64, check, float3
+from .mesh_io import unit_icosphere
+
+
+def _stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def to_dbm(power):
+    """main.py:12-13"""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return 10 * np.log10(np.asarray(power) / 1e-3)
+
+
+class Tracer:
+    """Drop-in for the reference ``Tracer`` (tracer.py:11-121).
+
+    Keyword-only extras (defaults reproduce the reference):
+      device        torch device (default: current CUDA device)
+      ray_range     (begin, end) global ray ids traced by THIS process; default (0, tx_num_rays), or this
+                    rank's contiguous share when ``shard=True`` and torch.distributed is initialised
+      shard         split rays across torch.distributed ranks and combine the received records
+      chunk_rays    rays generated per wave
+      max_candidates / max_records   initial capacities of the device work lists (grown on overflow)
+      verbose       print the reference's progress line (tracer.py:119)
+    """
+
+    def __init__(self, environment_trimesh, light_speed_mps, sample_rate_hz, sample_window_s, max_bounces,
+                 tx_num_rays, *, device=None, ray_range=None, shard=False, chunk_rays=1 << 24,
+                 max_candidates=1 << 20, max_records=1 << 20, verbose=False):
+        if not torch.cuda.is_available():
+            raise RfrtError("rf_ray_tracing_warp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self._lib = _lib.load()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.light_speed_mps = light_speed_mps
+        self.sample_rate_hz = sample_rate_hz
+        self.sample_window_s = sample_window_s
+        self.max_bounces = int(max_bounces)
+        self.tx_num_rays = int(tx_num_rays)
+        self.chunk_rays = int(chunk_rays)
+        self.max_candidates = int(max_candidates)
+        self.max_records = int(max_records)
+        self.verbose = verbose
+        self.shard = bool(shard)
+        self._world, self._rank = 1, 0
+        if self.shard and torch.distributed.is_available() and torch.distributed.is_initialized():
+            self._world, self._rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        if ray_range is None:
+            n = self.tx_num_rays
+            ray_range = (self._rank * n // self._world, (self._rank + 1) * n // self._world)
+        self.ray_range = (int(ray_range[0]), int(ray_range[1]))
+
+        # tracer.py:22-23: vertices -> vec3 float32, faces.flatten() -> int32
+        vertices = np.ascontiguousarray(np.asarray(environment_trimesh.vertices, dtype=np.float64).astype(np.float32))
+        faces = np.ascontiguousarray(np.asarray(environment_trimesh.faces).reshape(-1).astype(np.int32))
+        with torch.cuda.device(self.device):
+            self._d_vertices = torch.from_numpy(vertices.reshape(-1)).to(self.device)
+            self._d_faces = torch.from_numpy(faces).to(self.device)
+            handle = c_u64(0)
+            check(self._lib.rfrt_mesh_create(_ptr(self._d_vertices), vertices.shape[0], _ptr(self._d_faces),
+                                             faces.shape[0] // 3, _stream_ptr(), handle), "rfrt_mesh_create")
+        self._env = handle.value
+        self._unit_v, self._unit_f = unit_icosphere(1)  # tracer.py:27 (subdivisions=1)
+        self._dir_scratch = None
+        self.last_stats = {}
+
+    # ------------------------------------------------------------------------------------------
+    def __del__(self):
+        env = getattr(self, "_env", 0)
+        if env:
+            try:
+                self._lib.rfrt_mesh_destroy(env)
+            except Exception:
+                pass
+            self._env = 0
+
+    def mesh_info(self):
+        n_tris, n_nodes, depth, ms = c_i64(0), c_i64(0), c_i32(0), c_f(0)
+        bounds = (c_f * 6)()
+        check(self._lib.rfrt_mesh_info(self._env, n_tris, n_nodes, bounds, depth, ms), "rfrt_mesh_info")
+        return dict(n_triangles=n_tris.value, n_nodes=n_nodes.value, bounds=list(bounds), max_depth=depth.value,
+                    build_ms=ms.value)
+
+    def _scratch(self, n_rays):
+        need = min(self.chunk_rays, max(n_rays, 1)) * 4
+        if self._dir_scratch is None or self._dir_scratch.numel() < need:
+            self._dir_scratch = torch.empty(need, dtype=torch.float32, device=self.device)
+        return self._dir_scratch
+
+    def _make_rxset(self, centers, radius):
+        """tracer.py:26-30, batched: centers (R,3) float64 device tensor."""
+        handle = c_u64(0)
+        uv = np.ascontiguousarray(self._unit_v, dtype=np.float64)
+        uf = np.ascontiguousarray(self._unit_f, dtype=np.int32)
+        check(self._lib.rfrt_rxset_create(_ptr(centers), centers.shape[0], float(radius),
+                                          uv.ctypes.data_as(_lib.ctypes.POINTER(_lib.c_d)), uv.shape[0],
+                                          uf.ctypes.data_as(_lib.ctypes.POINTER(c_i32)), uf.shape[0], _stream_ptr(),
+                                          handle), "rfrt_rxset_create")
+        return handle.value
+
+    # ------------------------------------------------------------------------------------------
+    def trace_segments(self, tx_pos, ray_range=None, dump=False):
+        """Environment-only trace (no receivers).  Returns dict(segments, env_hits[, hit_tri, hit_t]).
+        ``dump=True`` adds the dense (n, B) parity arrays (hit triangle index, -1 = miss/dead; hit distance)."""
+        begin, end = ray_range if ray_range is not None else self.ray_range
+        n, B = end - begin, self.max_bounces
+        with torch.cuda.device(self.device):
+            counters = torch.zeros(_lib.CTR_COUNT, dtype=torch.int64, device=self.device)
+            hit_tri = torch.full((n, B), -1, dtype=torch.int32, device=self.device) if dump else None
+            hit_t = torch.zeros((n, B), dtype=torch.float32, device=self.device) if dump else None
+            check(self._lib.rfrt_trace(self._env, 0, float3(tx_pos), B, begin, end, 0, _ptr(self._scratch(n)),
+                                       self.chunk_rays, _ptr(counters), None, 0, _ptr(hit_tri), _ptr(hit_t),
+                                       _stream_ptr()), "rfrt_trace")
+            c = counters.cpu().numpy()
+        out = dict(segments=int(c[_lib.CTR_SEGMENTS]), env_hits=int(c[_lib.CTR_ENV_HITS]))
+        if dump:
+            out.update(hit_tri=hit_tri, hit_t=hit_t)
+        return out
+
+    def _trace_records(self, tx_pos, tx_power, centers, rx_radius, want_paths):
+        """trace + literal replay for this process's ray range -> unsorted device record arrays."""
+        begin, end = self.ray_range
+        n, B = end - begin, self.max_bounces
+        dev = self.device
+        rxset = self._make_rxset(centers, rx_radius)
+        try:
+            cand_cap, rec_cap = self.max_candidates, self.max_records
+            while True:
+                counters = torch.zeros(_lib.CTR_COUNT, dtype=torch.int64, device=dev)
+                cands = torch.empty(cand_cap * 4, dtype=torch.int32, device=dev)
+                rec = dict(ray=torch.empty(rec_cap, dtype=torch.int32, device=dev),
+                           rx=torch.empty(rec_cap, dtype=torch.int32, device=dev),
+                           nverts=torch.empty(rec_cap, dtype=torch.int32, device=dev),
+                           bin=torch.empty(rec_cap, dtype=torch.int64, device=dev),
+                           amp=torch.empty(rec_cap, dtype=torch.float64, device=dev),
+                           dist=torch.empty(rec_cap, dtype=torch.float64, device=dev),
+                           paths=torch.empty((rec_cap, B + 1, 3), dtype=torch.float32, device=dev) if want_paths else None)
+                tx = float3(tx_pos)
+                check(self._lib.rfrt_trace(self._env, rxset, tx, B, begin, end, 0, _ptr(self._scratch(n)),
+                                           self.chunk_rays, _ptr(counters), _ptr(cands), cand_cap, None, None,
+                                           _stream_ptr()), "rfrt_trace")
+                amp0 = tx_power / self.tx_num_rays if self.tx_num_rays else 0.0  # tracer.py:103
+                check(self._lib.rfrt_trace_receive(self._env, rxset, tx, B, _ptr(cands), cand_cap, _ptr(counters),
+                                                   float(amp0), float(self.light_speed_mps), float(self.sample_rate_hz),
+                                                   _ptr(rec["ray"]), _ptr(rec["rx"]), _ptr(rec["nverts"]),
+                                                   _ptr(rec["bin"]), _ptr(rec["amp"]), _ptr(rec["dist"]),
+                                                   _ptr(rec["paths"]), rec_cap, _stream_ptr()), "rfrt_trace_receive")
+                c = counters.cpu().numpy()  # synchronises
+                n_cand, n_rec = int(c[_lib.CTR_CANDIDATES]), int(c[_lib.CTR_RECORDS])
+                if n_cand <= cand_cap and n_rec <= rec_cap:
+                    break
+                cand_cap = max(cand_cap, int(n_cand * 1.25) + 1)  # overflow is reported, never silent: retry
+                rec_cap = max(rec_cap, int(n_cand * 1.25) + 1)
+            self.max_candidates, self.max_records = cand_cap, rec_cap
+        finally:
+            self._lib.rfrt_rxset_destroy(rxset)
+        for k in rec:
+            if rec[k] is not None:
+                rec[k] = rec[k][:n_rec]
+        stats = dict(segments=int(c[_lib.CTR_SEGMENTS]), env_hits=int(c[_lib.CTR_ENV_HITS]), candidates=n_cand,
+                     records=n_rec)
+        return rec, stats
+
+    def _gather_records(self, rec, stats):
+        """Multi-GPU exchange step: every rank ends up with ALL received records (they are sparse), so the
+        ordered binning below gives bit-identical results for any GPU count."""
+        if self._world == 1:
+            return rec, stats
+        dist = torch.distributed
+        n_local = torch.tensor([rec["ray"].shape[0]], dtype=torch.int64, device=self.device)
+        counts = [torch.zeros_like(n_local) for _ in range(self._world)]
+        dist.all_gather(counts, n_local)
+        counts = [int(x.item()) for x in counts]
+        m = max(max(counts), 1)
+        out = {}
+        for k, t in rec.items():
+            if t is None:
+                out[k] = None
+                continue
+            pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
+            pad[: t.shape[0]] = t
+            parts = [torch.empty_like(pad) for _ in range(self._world)]
+            dist.all_gather(parts, pad)
+            out[k] = torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+        tot = torch.tensor([stats["segments"], stats["env_hits"], stats["candidates"], stats["records"]],
+                           dtype=torch.int64, device=self.device)
+        dist.all_reduce(tot)
+        tot = tot.cpu().tolist()
+        return out, dict(segments=tot[0], env_hits=tot[1], candidates=tot[2], records=tot[3])
+
+    @staticmethod
+    def _sort_records(rec):
+        """(rx, ray id) order == the reference's accumulation order per receiver (tracer.py:87,102)."""
+        key = (rec["rx"].to(torch.int64) << 32) | (rec["ray"].to(torch.int64) & 0xFFFFFFFF)
+        order = torch.argsort(key)
+        return {k: (v[order].contiguous() if v is not None else None) for k, v in rec.items()}
+
+    def _records(self, tx_pos, tx_power, rx_positions, rx_radius, want_paths):
+        centers = torch.as_tensor(np.ascontiguousarray(np.asarray(rx_positions, dtype=np.float64).reshape(-1, 3)))
+        with torch.cuda.device(self.device):
+            centers = centers.to(self.device)
+            rec, stats = self._trace_records(tx_pos, tx_power, centers, rx_radius, want_paths)
+            rec, stats = self._gather_records(rec, stats)
+            rec = self._sort_records(rec)
+        self.last_stats = stats
+        return rec, centers.shape[0]
+
+    def _dense_ir(self, rec, n_rx):
+        L = int(self.sample_window_s * self.sample_rate_hz)  # tracer.py:101
+        ir = torch.zeros((n_rx, L), dtype=torch.float64, device=self.device)
+        n = rec["ray"].shape[0]
+        if n and L:
+            check(self._lib.rfrt_bin_ir(_ptr(rec["rx"]), _ptr(rec["bin"]), _ptr(rec["amp"]), n, n_rx, L, 1, _ptr(ir),
+                                        _stream_ptr()), "rfrt_bin_ir")
+        return ir
+
+    # ------------------------------------------------------------------------------------------
+    def compute_cir(self, tx_pos, tx_power, rx_pos, rx_radius):
+        """tracer.py:63-121.  Returns (cleaned_paths: list of (k,3) float32 arrays in ascending ray-id order,
+        impulse_response: (L,) float64)."""
+        start_time = time.perf_counter()
+        rec, _ = self._records(tx_pos, tx_power, np.asarray(rx_pos, dtype=np.float64).reshape(1, 3), rx_radius, True)
+        with torch.cuda.device(self.device):
+            ir = self._dense_ir(rec, 1)[0].cpu().numpy()
+            nverts = rec["nverts"].cpu().numpy()
+            paths = rec["paths"].cpu().numpy()
+        cleaned_paths = [np.array(paths[i, : nverts[i]], dtype=np.float32) for i in range(paths.shape[0])]
+        if self.verbose:
+            print(f"Traced {len(cleaned_paths)} paths in {time.perf_counter() - start_time} seconds")
+        return cleaned_paths, ir
+
+    def compute_cir_multi(self, tx_pos, tx_power, rx_positions, rx_radius, return_paths=False, dense=True):
+        """Batched compute_cir: ONE trace for R receivers, identical per receiver to R separate compute_cir calls.
+        Returns dict(impulse_response (R,L) float64 tensor if dense, records=dict of device tensors sorted by
+        (receiver, ray id): ray, rx, nverts, bin, amp, dist[, paths])."""
+        rec, n_rx = self._records(tx_pos, tx_power, rx_positions, rx_radius, return_paths)
+        out = dict(records=rec, n_receivers=n_rx, stats=dict(self.last_stats))
+        if dense:
+            with torch.cuda.device(self.device):
+                out["impulse_response"] = self._dense_ir(rec, n_rx)
+        return out
+
+    def rx_power(self, rec, n_rx, carrier_hz=2.4e9):
+        """main.py:39,46-55 per receiver, from the sorted records.  Returns (R,) float64 tensor (linear power,
+        NaN where a receiver has no non-zero sample)."""
+        L = int(self.sample_window_s * self.sample_rate_hz)
+        dev = self.device
+        with torch.cuda.device(dev):
+            keep = (rec["bin"] >= 0) & (rec["bin"] < L)
+            rx = rec["rx"][keep].to(torch.int64)
+            b = rec["bin"][keep]
+            amp = rec["amp"][keep]
+            key = rx * L + b
+            order = torch.argsort(key, stable=True)  # keeps ray-id order inside one (receiver, bin)
+            key, amp = key[order], amp[order]
+            ukey, inverse = torch.unique_consecutive(key, return_inverse=True)
+            aamp = torch.zeros(ukey.shape[0], dtype=torch.float64, device=dev).index_add_(0, inverse, amp)
+            nz = aamp != 0  # np.convolve sees the summed impulse response: exact zeros contribute nothing
+            ukey, aamp = ukey[nz], aamp[nz]
+            arx = torch.div(ukey, L, rounding_mode="floor")
+            abin = (ukey - arx * L).to(torch.int32).contiguous()
+            offsets = torch.zeros(n_rx + 1, dtype=torch.int64, device=dev)
+            offsets[1:] = torch.cumsum(torch.bincount(arx, minlength=n_rx), 0)
+            power = torch.empty(n_rx, dtype=torch.float64, device=dev)
+            table = torch.empty(max(L, 1), dtype=torch.float64, device=dev)
+            check(self._lib.rfrt_rx_power(_ptr(offsets), _ptr(abin), _ptr(aamp.contiguous()), n_rx, L,
+                                          float(self.sample_window_s), float(carrier_hz), _ptr(table), _ptr(power),
+                                          _stream_ptr()), "rfrt_rx_power")
+        return power
+
+    def coverage(self, tx_pos, tx_power, rx_positions, rx_radius, carrier_hz=2.4e9):
+        """coverage.py:38-57 without the per-receiver re-trace: one trace, every receiver tested per segment.
+        Returns dict(power (R,) linear, dbm (R,), stats)."""
+        rec, n_rx = self._records(tx_pos, tx_power, rx_positions, rx_radius, False)
+        power = self.rx_power(rec, n_rx, carrier_hz)
+        p = power.cpu().numpy()
+        return dict(power=p, dbm=to_dbm(p), stats=dict(self.last_stats), records=rec)
+
+    # ------------------------------------------------------------------------------------------
+    def trace_paths_kernel(self, tx_pos, rx_pos, rx_radius, ray_range=None):
+        """The reference kernel's dense contract (kernel.py:38-47 launched at tracer.py:75-79): returns
+        (traced_paths (n,B+1,3), received_paths (n,B+1,3), row_mask (n,)) device tensors, NaN / zero
+        initialised exactly as tracer.py:67-72 does.  For small n only (dense arrays)."""
+        begin, end = ray_range if ray_range is not None else self.ray_range
+        n, B = end - begin, self.max_bounces
+        with torch.cuda.device(self.device):
+            traced = torch.full((n, B + 1, 3), float("nan"), dtype=torch.float32, device=self.device)
+            received = torch.full((n, B + 1, 3), float("nan"), dtype=torch.float32, device=self.device)
+            mask = torch.zeros(n, dtype=torch.int32, device=self.device)
+            rxset = 0
+            if rx_pos is not None:
+                centers = torch.as_tensor(np.asarray(rx_pos, dtype=np.float64).reshape(1, 3)).to(self.device)
+                rxset = self._make_rxset(centers, rx_radius)
+            try:
+                check(self._lib.rfrt_trace_paths_compat(self._env, float3(tx_pos), rxset, 0, B, begin, n, _ptr(traced),
+                                                        _ptr(received), _ptr(mask), _stream_ptr()),
+                      "rfrt_trace_paths_compat")
+                torch.cuda.synchronize(self.device)  # tracer.py:80
+            finally:
+                if rxset:
+                    self._lib.rfrt_rxset_destroy(rxset)
+        return traced, received, mask
+
+    def query_closest(self, origins, dirs, max_t=1.0e6):
+        """Test probe: closest hit of arbitrary rays against the environment BVH -> (t, face) tensors."""
+        with torch.cuda.device(self.device):
+            o = torch.as_tensor(np.ascontiguousarray(np.asarray(origins, dtype=np.float32).reshape(-1, 3))).to(self.device)
+            d = torch.as_tensor(np.ascontiguousarray(np.asarray(dirs, dtype=np.float32).reshape(-1, 3))).to(self.device)
+            t = torch.empty(o.shape[0], dtype=torch.float32, device=self.device)
+            f = torch.empty(o.shape[0], dtype=torch.int32, device=self.device)
+            check(self._lib.rfrt_query_closest(self._env, _ptr(o), _ptr(d), o.shape[0], float(max_t), _ptr(t), _ptr(f),
+                                               _stream_ptr()), "rfrt_query_closest")
+        return t, f
+
+    def ray_directions(self, begin, end):
+        with torch.cuda.device(self.device):
+            d = torch.empty((end - begin, 4), dtype=torch.float32, device=self.device)
+            check(self._lib.rfrt_ray_directions(begin, end, _ptr(d), _stream_ptr()), "rfrt_ray_directions")
+        return d[:, :3]
