@@ -53,6 +53,7 @@ enum rfrt_status {
 
 /* rfrt_trace flags */
 #define RFRT_FLAG_NONE 0u
+#define RFRT_FLAG_DIRS_READY 1u /* d_dir_scratch already holds rfrt_ray_directions(ray_begin, ray_end): one wave */
 
 /* layout of the u64 counter block written by rfrt_trace / rfrt_trace_receive */
 #define RFRT_CTR_SEGMENTS 0    /* traced ray segments (alive bounce iterations), SURVEY.md 8d */
@@ -151,13 +152,16 @@ RFRT_API int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const f
 /* ---------------------------------------------------------------------------------------------
  * Impulse-response binning (tracer.py:101,116-117):  ir[rx][bin] += amp  if bin < n_bins.
  *   d_ir : [n_receivers*n_bins] float64, zeroed by the caller.
+ *   d_n_records : optional device counter (e.g. d_counters + RFRT_CTR_RECORDS); when non-NULL only
+ *                 min(*d_n_records, n_records) records are read, so no host round trip is needed.
  *   deterministic != 0 : records must be sorted by (rx, ray id); each receiver's records are then
  *                        summed by one thread in ray-id order — the reference's own order — so the
  *                        result is bit-reproducible and independent of the GPU count.
  *   deterministic == 0 : shared-memory privatised histogram per receiver tile, flushed with atomics.
  * ------------------------------------------------------------------------------------------- */
 RFRT_API int rfrt_bin_ir(const int32_t *d_rec_rx, const int64_t *d_rec_bin, const double *d_rec_amp, int64_t n_records,
-                int64_t n_receivers, int64_t n_bins, int32_t deterministic, double *d_ir, void *stream);
+                const uint64_t *d_n_records, int64_t n_receivers, int64_t n_bins, int32_t deterministic,
+                double *d_ir, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * RX power of main.py:39,46-55 / coverage.py:45-55 for each receiver, from its SPARSE arrivals

@@ -4,7 +4,8 @@ TEST INFRASTRUCTURE ONLY.  dtype semantics are written out explicitly and follow
 promotion rules of the reference's era (python float (+) np.float32 scalar -> float64), so the
 result does not depend on the NumPy version installed:
   * segment vectors, their lengths, the dot product and the arccos are fp32 (tracer.py:107-110);
-    the 3-term sums are evaluated left to right without FMA: (x*x + y*y) + z*z
+    the 3-term sums are evaluated left to right without FMA: (x*x + y*y) + z*z; the fp32 arccos is the
+    correctly rounded one (fp64 acos rounded to fp32)
   * the Fresnel chain is fp64 `math` (tracer.py:34-61), fed with the fp32 angle
   * distance accumulates fp32 lengths in fp64 (tracer.py:104,112-113)
 The debug prints (tracer.py:36,41,46,56,59) are omitted.
@@ -66,7 +67,12 @@ def path_amplitude_delay(path, tx_power, tx_num_rays, light_speed_mps, sample_ra
         seg1_len = _norm32(seg1)
         with np.errstate(invalid="ignore", divide="ignore"):
             q = _f32(_dot32(seg1, seg2) / _f32(seg1_len * _norm32(seg2)))
-            angle_between = np.arccos(q)  # fp32; NaN if q > 1, q < -1 or 0/0
+        # np.arccos on a float32 scalar (tracer.py:110): NaN if q > 1, q < -1 or 0/0.  NumPy's fp32 arccos is
+        # SIMD-dispatch dependent (up to a few ulp), so the oracle pins it to the correctly rounded fp32 value.
+        if np.isnan(q) or q > 1 or q < -1:
+            angle_between = _f32(np.nan)
+        else:
+            angle_between = _f32(math.acos(float(q)))
         amplitude *= bounce_amplitude(angle_between)
         distance += float(seg1_len)
     distance += float(_norm32((path[-2] - path[-1]).astype(np.float32)))

@@ -166,8 +166,16 @@ static inline int sign_bit(float x)
     return (int)(u >> 31);
 }
 
-static int woop(const float p[3], const float dir[3], const float a[3], const float b[3], const float c[3],
-                float *t_out)
+/* The per-ray part of the test (dominant axis, shear constants) is hoisted out of the per-triangle
+ * part — the arithmetic and its order are exactly those of intersect_ray_tri_woop, evaluated once per
+ * query instead of once per triangle (what an optimising compiler does after inlining). */
+typedef struct {
+    int kx, ky, kz;
+    float Sx, Sy, Sz;
+    float p[3];
+} WoopRay;
+
+static inline void woop_setup(const float p[3], const float dir[3], WoopRay *r)
 {
     float ax = fabsf(dir[0]), ay = fabsf(dir[1]), az = fabsf(dir[2]);
     int kz;
@@ -177,10 +185,18 @@ static int woop(const float p[3], const float dir[3], const float a[3], const fl
     int kx = kz + 1; if (kx == 3) kx = 0;
     int ky = kx + 1; if (ky == 3) ky = 0;
     if (dir[kz] < 0.0f) { int tmp = kx; kx = ky; ky = tmp; }
+    r->kx = kx; r->ky = ky; r->kz = kz;
+    r->Sx = dir[kx] / dir[kz];
+    r->Sy = dir[ky] / dir[kz];
+    r->Sz = 1.0f / dir[kz];
+    r->p[0] = p[0]; r->p[1] = p[1]; r->p[2] = p[2];
+}
 
-    float Sx = dir[kx] / dir[kz];
-    float Sy = dir[ky] / dir[kz];
-    float Sz = 1.0f / dir[kz];
+static inline int woop_tri(const WoopRay *r, const float a[3], const float b[3], const float c[3], float *t_out)
+{
+    const int kx = r->kx, ky = r->ky, kz = r->kz;
+    const float Sx = r->Sx, Sy = r->Sy, Sz = r->Sz;
+    const float *p = r->p;
 
     float A[3] = {a[0] - p[0], a[1] - p[1], a[2] - p[2]};
     float B[3] = {b[0] - p[0], b[1] - p[1], b[2] - p[2]};
@@ -234,6 +250,14 @@ static int woop(const float p[3], const float dir[3], const float a[3], const fl
     return 1;
 }
 
+static inline int woop(const float p[3], const float dir[3], const float a[3], const float b[3], const float c[3],
+                       float *t_out)
+{
+    WoopRay r;
+    woop_setup(p, dir, &r);
+    return woop_tri(&r, a, b, c, t_out);
+}
+
 /* mesh_query_ray [restated]: closest accepted hit with 0 <= t < max_t.  Brute force in
  * index order with strict '<'  ==>  equal-t ties go to the lowest triangle index. */
 static int query_closest(const float *tris, int64_t ntris, const float p[3], const float dir[3], float max_t,
@@ -241,10 +265,12 @@ static int query_closest(const float *tris, int64_t ntris, const float p[3], con
 {
     float min_t = max_t;
     int min_face = -1;
+    WoopRay wr;
+    woop_setup(p, dir, &wr);
     for (int64_t i = 0; i < ntris; ++i) {
         const float *a = tris + 9 * i;
         float t;
-        if (woop(p, dir, a, a + 3, a + 6, &t)) {
+        if (woop_tri(&wr, a, a + 3, a + 6, &t)) {
             if (t < min_t && t >= 0.0f) {
                 min_t = t;
                 min_face = (int)i;
@@ -394,7 +420,15 @@ static int obvh_query(const OBvh *b, const float p[3], const float dir[3], float
         }
         if (m * 1.0e-5f > pad) pad = m * 1.0e-5f;
     }
-    float inv[3] = {1.0f / dir[0], 1.0f / dir[1], 1.0f / dir[2]};
+    /* zero direction components are tilted by 1e-18 so the slab arithmetic stays NaN free (pruning only) */
+    float inv[3];
+    for (int k = 0; k < 3; ++k) {
+        float d = dir[k];
+        if (fabsf(d) < 1.0e-18f) d = copysignf(1.0e-18f, d);
+        inv[k] = 1.0f / d;
+    }
+    WoopRay wr;
+    woop_setup(p, dir, &wr);
     float min_t = max_t;
     int min_face = -1;
     int stack[128];
@@ -406,17 +440,17 @@ static int obvh_query(const OBvh *b, const float p[3], const float dir[3], float
         for (int k = 0; k < 3; ++k) {
             float t0 = ((n->lo[k] - pad) - p[k]) * inv[k];
             float t1 = ((n->hi[k] + pad) - p[k]) * inv[k];
-            float tn = fminf(t0, t1), tf = fmaxf(t0, t1); /* NaN (0*inf) is ignored */
-            tmin = fmaxf(tmin, tn);
-            tmax = fminf(tmax, tf);
+            float tn = t0 < t1 ? t0 : t1, tf = t0 < t1 ? t1 : t0;
+            tmin = tn > tmin ? tn : tmin;
+            tmax = tf < tmax ? tf : tmax;
         }
-        if (!(tmax >= tmin) || !(tmin <= min_t)) continue;
+        if (!(tmax * 1.0000004f >= tmin) || !(tmin <= min_t)) continue;
         if (n->right < 0) {
             for (int i = n->left; i < n->left - n->right; ++i) {
                 int f = b->prim[i];
                 const float *a = b->tris + 9 * (int64_t)f;
                 float t;
-                if (woop(p, dir, a, a + 3, a + 6, &t)) {
+                if (woop_tri(&wr, a, a + 3, a + 6, &t)) {
                     if (t >= 0.0f && (t < min_t || (t == min_t && min_face >= 0 && f < min_face))) {
                         min_t = t;
                         min_face = f;
@@ -450,6 +484,7 @@ static inline int query(const float *tris, int64_t ntris, const OBvh *bvh, const
  * 2 = rx hit.
  * ---------------------------------------------------------------------------------------- */
 static void trace_one(const float *env, int64_t nenv, const OBvh *env_bvh, const float *rx, int64_t nrx,
+                      const OBvh *rx_bvh,
                       const float tx[3], int max_bounces, uint32_t tid, float *traced, float *received,
                       uint32_t *mask, int32_t *hit_tri, float *hit_t, int8_t *event)
 {
@@ -462,7 +497,7 @@ static void trace_one(const float *env, int64_t nenv, const OBvh *env_bvh, const
         /* kernel.py:58 — ray_finished is reset every iteration, so nothing ever stops early */
         float t_rx = 0.0f, t_env = 0.0f;
         int f_rx = 0, f_env = 0;
-        int maybe_hit_rx = nrx > 0 ? query_closest(rx, nrx, pos, dir, 1.0e6f, &t_rx, &f_rx) : 0; /* :71 */
+        int maybe_hit_rx = nrx > 0 ? query(rx, nrx, rx_bvh, pos, dir, 1.0e6f, &t_rx, &f_rx) : 0; /* :71 */
         int maybe_hit_env = query(env, nenv, env_bvh, pos, dir, 1.0e6f, &t_env, &f_env);       /* :82 */
         int hit_recv = maybe_hit_rx && (!maybe_hit_env || (maybe_hit_env && t_env > t_rx));    /* :85 */
         if (hit_recv) {
@@ -503,6 +538,8 @@ ORACLE_API void oracle_trace_paths(const float *env, int64_t nenv, void *env_bvh
                                    int nthreads)
 {
     const int64_t row = 3 * (int64_t)(max_bounces + 1);
+    /* with an environment BVH the receiver mesh gets one too (Warp traverses a BVH for both meshes) */
+    OBvh *rx_bvh = (env_bvh && nrx > 0) ? (OBvh *)oracle_bvh_create(rx, nrx) : NULL;
 #ifdef _OPENMP
     if (nthreads <= 0) nthreads = omp_get_max_threads();
 #pragma omp parallel for schedule(dynamic, 4096) num_threads(nthreads)
@@ -511,10 +548,11 @@ ORACLE_API void oracle_trace_paths(const float *env, int64_t nenv, void *env_bvh
         float *tr = traced + i * row, *rc = received + i * row;
         for (int64_t k = 0; k < row; ++k) { tr[k] = NAN; rc[k] = NAN; }
         mask[i] = 0u;
-        trace_one(env, nenv, (const OBvh *)env_bvh, rx, nrx, tx, max_bounces, (uint32_t)(tid_begin + i), tr, rc,
+        trace_one(env, nenv, (const OBvh *)env_bvh, rx, nrx, rx_bvh, tx, max_bounces, (uint32_t)(tid_begin + i), tr, rc,
                   mask + i, hit_tri ? hit_tri + i * max_bounces : NULL, hit_t ? hit_t + i * max_bounces : NULL,
                   event ? event + i * max_bounces : NULL);
     }
+    oracle_bvh_destroy(rx_bvh);
 }
 
 /* Sparse variant for big N: same loop, but only received rows are kept.
@@ -533,6 +571,7 @@ ORACLE_API int64_t oracle_trace_received(const float *env, int64_t nenv, void *e
 #endif
     uint8_t *flag = (uint8_t *)malloc((size_t)chunk);
     float *rows = (float *)malloc(sizeof(float) * (size_t)(chunk * row));
+    OBvh *rx_bvh = (env_bvh && nrx > 0) ? (OBvh *)oracle_bvh_create(rx, nrx) : NULL;
     for (int64_t c0 = 0; c0 < n; c0 += chunk) {
         int64_t m = n - c0 < chunk ? n - c0 : chunk;
 #ifdef _OPENMP
@@ -543,7 +582,7 @@ ORACLE_API int64_t oracle_trace_received(const float *env, int64_t nenv, void *e
             float *rc = rows + i * row;
             uint32_t msk = 0;
             for (int64_t k = 0; k < row; ++k) { tr[k] = NAN; rc[k] = NAN; }
-            trace_one(env, nenv, (const OBvh *)env_bvh, rx, nrx, tx, max_bounces, (uint32_t)(tid_begin + c0 + i),
+            trace_one(env, nenv, (const OBvh *)env_bvh, rx, nrx, rx_bvh, tx, max_bounces, (uint32_t)(tid_begin + c0 + i),
                       tr, rc, &msk, NULL, NULL, NULL);
             flag[i] = (uint8_t)msk;
         }
@@ -558,6 +597,7 @@ ORACLE_API int64_t oracle_trace_received(const float *env, int64_t nenv, void *e
     }
     free(flag);
     free(rows);
+    oracle_bvh_destroy(rx_bvh);
     return count;
 }
 

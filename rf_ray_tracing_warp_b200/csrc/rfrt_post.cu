@@ -12,8 +12,10 @@ namespace {
 
 // order-free: one fp64 atomic per record
 __global__ void k_bin_atomic(const int32_t *__restrict__ rx, const int64_t *__restrict__ bin,
-                             const double *__restrict__ amp, int64_t n, int64_t n_rx, int64_t n_bins, double *ir)
+                             const double *__restrict__ amp, int64_t n, const unsigned long long *d_n, int64_t n_rx,
+                             int64_t n_bins, double *ir)
 {
+    if (d_n && (int64_t)*d_n < n) n = (int64_t)*d_n;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t b = bin[i];
         int64_t k = rx[i];
@@ -25,10 +27,11 @@ __global__ void k_bin_atomic(const int32_t *__restrict__ rx, const int64_t *__re
 // accumulates the bins that fall into its shared-memory window with shared atomics and flushes the
 // non-zero bins with one global atomic each.  Used when one receiver's histogram fits in shared memory.
 __global__ void k_bin_privatised(const int32_t *__restrict__ rx, const int64_t *__restrict__ bin,
-                                 const double *__restrict__ amp, int64_t n, int64_t n_rx, int64_t n_bins, double *ir,
-                                 int64_t per_block)
+                                 const double *__restrict__ amp, int64_t n, const unsigned long long *d_n, int64_t n_rx,
+                                 int64_t n_bins, double *ir, int64_t per_block)
 {
     extern __shared__ double s_hist[];
+    if (d_n && (int64_t)*d_n < n) n = (int64_t)*d_n;
     const int64_t begin = blockIdx.x * per_block;
     const int64_t end = begin + per_block < n ? begin + per_block : n;
     for (int64_t k = 0; k < n_rx; ++k) {
@@ -49,10 +52,12 @@ __global__ void k_bin_privatised(const int32_t *__restrict__ rx, const int64_t *
 
 // deterministic: records sorted by (rx, ray id); receiver k's records are added by one thread in order
 __global__ void k_bin_ordered(const int32_t *__restrict__ rx, const int64_t *__restrict__ bin,
-                              const double *__restrict__ amp, int64_t n, int64_t n_rx, int64_t n_bins, double *ir)
+                              const double *__restrict__ amp, int64_t n, const unsigned long long *d_n, int64_t n_rx,
+                              int64_t n_bins, double *ir)
 {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= n_rx) return;
+    if (d_n && (int64_t)*d_n < n) n = (int64_t)*d_n;
     int64_t lo = 0, hi = n; // lower_bound of k
     while (lo < hi) {
         int64_t mid = (lo + hi) >> 1;
@@ -117,9 +122,10 @@ k_rx_power(const int64_t *__restrict__ offsets, const int32_t *__restrict__ abin
 using namespace rfrt;
 
 extern "C" int rfrt_bin_ir(const int32_t *d_rec_rx, const int64_t *d_rec_bin, const double *d_rec_amp,
-                           int64_t n_records, int64_t n_receivers, int64_t n_bins, int32_t deterministic,
-                           double *d_ir, void *stream_)
+                           int64_t n_records, const uint64_t *d_n_records, int64_t n_receivers, int64_t n_bins,
+                           int32_t deterministic, double *d_ir, void *stream_)
 {
+    const unsigned long long *d_n = (const unsigned long long *)d_n_records;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_records < 0 || n_receivers <= 0 || n_bins < 0 || !d_ir ||
         (n_records > 0 && (!d_rec_rx || !d_rec_bin || !d_rec_amp))) {
@@ -129,7 +135,7 @@ extern "C" int rfrt_bin_ir(const int32_t *d_rec_rx, const int64_t *d_rec_bin, co
     if (n_records == 0 || n_bins == 0) return RFRT_OK;
     if (deterministic) {
         k_bin_ordered<<<(unsigned)((n_receivers + 127) / 128), 128, 0, stream>>>(d_rec_rx, d_rec_bin, d_rec_amp,
-                                                                                 n_records, n_receivers, n_bins, d_ir);
+                                                                                 n_records, d_n, n_receivers, n_bins, d_ir);
     } else {
         const size_t smem = sizeof(double) * (size_t)n_bins;
         if (n_receivers <= 4 && smem <= 200 * 1024 && n_records >= (1 << 16)) {
@@ -138,12 +144,12 @@ extern "C" int rfrt_bin_ir(const int32_t *d_rec_rx, const int64_t *d_rec_bin, co
             RFRT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
             RFRT_CUDA(cudaFuncSetAttribute((const void *)k_bin_privatised, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int64_t per_block = (n_records + sms - 1) / sms;
-            k_bin_privatised<<<sms, 512, smem, stream>>>(d_rec_rx, d_rec_bin, d_rec_amp, n_records, n_receivers,
+            k_bin_privatised<<<sms, 512, smem, stream>>>(d_rec_rx, d_rec_bin, d_rec_amp, n_records, d_n, n_receivers,
                                                         n_bins, d_ir, per_block);
         } else {
             int64_t nb = (n_records + 255) / 256;
             if (nb > 4096) nb = 4096;
-            k_bin_atomic<<<(unsigned)nb, 256, 0, stream>>>(d_rec_rx, d_rec_bin, d_rec_amp, n_records, n_receivers,
+            k_bin_atomic<<<(unsigned)nb, 256, 0, stream>>>(d_rec_rx, d_rec_bin, d_rec_amp, n_records, d_n, n_receivers,
                                                            n_bins, d_ir);
         }
     }

@@ -467,8 +467,8 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
                           int64_t chunk_rays, uint64_t *d_counters, uint32_t *d_candidates, int64_t cand_capacity,
                           int32_t *d_hit_tri, float *d_hit_t, void *stream_)
 {
-    (void)flags;
     cudaStream_t stream = (cudaStream_t)stream_;
+    const bool dirs_ready = (flags & RFRT_FLAG_DIRS_READY) != 0;
     Mesh *m = get_mesh(env_mesh);
     if (!m) { set_error("rfrt_trace: unknown environment mesh handle"); return RFRT_ERR_HANDLE; }
     RxSet *r = nullptr;
@@ -485,6 +485,7 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     if (n == 0 || max_bounces == 0) return RFRT_OK;
     if (!d_dir_scratch) { set_error("rfrt_trace: d_dir_scratch required"); return RFRT_ERR_INVALID; }
     if (chunk_rays <= 0) chunk_rays = 1ll << 24;
+    if (dirs_ready) chunk_rays = n; // the caller generated all directions with rfrt_ray_directions
 
     TraceParams P;
     P.nodes = m->bvh.nodes; P.tris = m->tris; P.n_tris = m->bvh.n_prims;
@@ -509,7 +510,7 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
 
     for (int64_t c0 = ray_begin; c0 < ray_end; c0 += chunk_rays) {
         int64_t cn = ray_end - c0 < chunk_rays ? ray_end - c0 : chunk_rays;
-        k_gen_dirs<<<(unsigned)((cn + 255) / 256), 256, 0, stream>>>(c0, cn, (float4 *)d_dir_scratch);
+        if (!dirs_ready) k_gen_dirs<<<(unsigned)((cn + 255) / 256), 256, 0, stream>>>(c0, cn, (float4 *)d_dir_scratch);
         RFRT_CUDA(cudaMemsetAsync(d_counters + RFRT_CTR_NEXT_RAY, 0, sizeof(uint64_t), stream));
         P.chunk_begin = c0; P.chunk_n = cn;
         int g = grid;

@@ -141,49 +141,30 @@ class Tracer:
             out.update(hit_tri=hit_tri, hit_t=hit_t)
         return out
 
+    def make_job(self, rx_positions, rx_radius, want_paths=False, cand_capacity=None, rec_capacity=None):
+        """Allocates the device work lists for one batch of receivers and returns a reusable :class:`TraceJob`
+        (receiver set + buffers stay resident across steps)."""
+        return TraceJob(self, rx_positions, rx_radius, want_paths, cand_capacity or self.max_candidates,
+                        rec_capacity or self.max_records)
+
     def _trace_records(self, tx_pos, tx_power, centers, rx_radius, want_paths):
         """trace + literal replay for this process's ray range -> unsorted device record arrays."""
-        begin, end = self.ray_range
-        n, B = end - begin, self.max_bounces
-        dev = self.device
-        rxset = self._make_rxset(centers, rx_radius)
-        try:
-            cand_cap, rec_cap = self.max_candidates, self.max_records
-            while True:
-                counters = torch.zeros(_lib.CTR_COUNT, dtype=torch.int64, device=dev)
-                cands = torch.empty(cand_cap * 4, dtype=torch.int32, device=dev)
-                rec = dict(ray=torch.empty(rec_cap, dtype=torch.int32, device=dev),
-                           rx=torch.empty(rec_cap, dtype=torch.int32, device=dev),
-                           nverts=torch.empty(rec_cap, dtype=torch.int32, device=dev),
-                           bin=torch.empty(rec_cap, dtype=torch.int64, device=dev),
-                           amp=torch.empty(rec_cap, dtype=torch.float64, device=dev),
-                           dist=torch.empty(rec_cap, dtype=torch.float64, device=dev),
-                           paths=torch.empty((rec_cap, B + 1, 3), dtype=torch.float32, device=dev) if want_paths else None)
-                tx = float3(tx_pos)
-                check(self._lib.rfrt_trace(self._env, rxset, tx, B, begin, end, 0, _ptr(self._scratch(n)),
-                                           self.chunk_rays, _ptr(counters), _ptr(cands), cand_cap, None, None,
-                                           _stream_ptr()), "rfrt_trace")
-                amp0 = tx_power / self.tx_num_rays if self.tx_num_rays else 0.0  # tracer.py:103
-                check(self._lib.rfrt_trace_receive(self._env, rxset, tx, B, _ptr(cands), cand_cap, _ptr(counters),
-                                                   float(amp0), float(self.light_speed_mps), float(self.sample_rate_hz),
-                                                   _ptr(rec["ray"]), _ptr(rec["rx"]), _ptr(rec["nverts"]),
-                                                   _ptr(rec["bin"]), _ptr(rec["amp"]), _ptr(rec["dist"]),
-                                                   _ptr(rec["paths"]), rec_cap, _stream_ptr()), "rfrt_trace_receive")
-                c = counters.cpu().numpy()  # synchronises
-                n_cand, n_rec = int(c[_lib.CTR_CANDIDATES]), int(c[_lib.CTR_RECORDS])
-                if n_cand <= cand_cap and n_rec <= rec_cap:
-                    break
-                cand_cap = max(cand_cap, int(n_cand * 1.25) + 1)  # overflow is reported, never silent: retry
-                rec_cap = max(rec_cap, int(n_cand * 1.25) + 1)
-            self.max_candidates, self.max_records = cand_cap, rec_cap
-        finally:
-            self._lib.rfrt_rxset_destroy(rxset)
-        for k in rec:
-            if rec[k] is not None:
-                rec[k] = rec[k][:n_rec]
-        stats = dict(segments=int(c[_lib.CTR_SEGMENTS]), env_hits=int(c[_lib.CTR_ENV_HITS]), candidates=n_cand,
-                     records=n_rec)
-        return rec, stats
+        cand_cap, rec_cap = self.max_candidates, self.max_records
+        while True:
+            job = TraceJob(self, centers, rx_radius, want_paths, cand_cap, rec_cap)
+            try:
+                job.enqueue(tx_pos, tx_power)
+                c = job.counters()  # synchronises
+            finally:
+                job.close()
+            n_cand, n_rec = c["candidates"], c["records"]
+            if n_cand <= cand_cap and n_rec <= rec_cap:
+                break
+            cand_cap = max(cand_cap, int(n_cand * 1.25) + 1)  # overflow is reported, never silent: retry
+            rec_cap = max(rec_cap, int(n_cand * 1.25) + 1)
+        self.max_candidates, self.max_records = cand_cap, rec_cap
+        rec = {k: (v[:n_rec] if v is not None else None) for k, v in job.rec.items()}
+        return rec, c
 
     def _gather_records(self, rec, stats):
         """Multi-GPU exchange step: every rank ends up with ALL received records (they are sparse), so the
@@ -220,9 +201,8 @@ class Tracer:
         return {k: (v[order].contiguous() if v is not None else None) for k, v in rec.items()}
 
     def _records(self, tx_pos, tx_power, rx_positions, rx_radius, want_paths):
-        centers = torch.as_tensor(np.ascontiguousarray(np.asarray(rx_positions, dtype=np.float64).reshape(-1, 3)))
+        centers = np.ascontiguousarray(np.asarray(rx_positions, dtype=np.float64).reshape(-1, 3))
         with torch.cuda.device(self.device):
-            centers = centers.to(self.device)
             rec, stats = self._trace_records(tx_pos, tx_power, centers, rx_radius, want_paths)
             rec, stats = self._gather_records(rec, stats)
             rec = self._sort_records(rec)
@@ -234,8 +214,8 @@ class Tracer:
         ir = torch.zeros((n_rx, L), dtype=torch.float64, device=self.device)
         n = rec["ray"].shape[0]
         if n and L:
-            check(self._lib.rfrt_bin_ir(_ptr(rec["rx"]), _ptr(rec["bin"]), _ptr(rec["amp"]), n, n_rx, L, 1, _ptr(ir),
-                                        _stream_ptr()), "rfrt_bin_ir")
+            check(self._lib.rfrt_bin_ir(_ptr(rec["rx"]), _ptr(rec["bin"]), _ptr(rec["amp"]), n, None, n_rx, L, 1,
+                                        _ptr(ir), _stream_ptr()), "rfrt_bin_ir")
         return ir
 
     # ------------------------------------------------------------------------------------------
@@ -336,8 +316,89 @@ class Tracer:
                                                _stream_ptr()), "rfrt_query_closest")
         return t, f
 
-    def ray_directions(self, begin, end):
+    def ray_directions(self, begin, end, out=None):
         with torch.cuda.device(self.device):
-            d = torch.empty((end - begin, 4), dtype=torch.float32, device=self.device)
+            d = torch.empty((end - begin, 4), dtype=torch.float32, device=self.device) if out is None else out
             check(self._lib.rfrt_ray_directions(begin, end, _ptr(d), _stream_ptr()), "rfrt_ray_directions")
-        return d[:, :3]
+        return d if out is not None else d[:, :3]
+
+
+class TraceJob:
+    """Device-resident state of one receiver batch: receiver set (tracer.py:26-30), candidate / record work lists
+    and counters.  ``enqueue`` launches the whole hot path on the current stream without any host
+    synchronisation: [directions ->] environment trace -> literal replay of the candidates -> (optional)
+    impulse-response binning."""
+
+    def __init__(self, tracer, rx_positions, rx_radius, want_paths, cand_capacity, rec_capacity):
+        self.t = tracer
+        dev = tracer.device
+        B = tracer.max_bounces
+        with torch.cuda.device(dev):
+            if torch.is_tensor(rx_positions):
+                centers = rx_positions.to(device=dev, dtype=torch.float64).reshape(-1, 3).contiguous()
+            else:
+                centers = torch.as_tensor(np.ascontiguousarray(np.asarray(rx_positions, dtype=np.float64).reshape(-1, 3))).to(dev)
+            self.centers = centers
+            self.n_rx = centers.shape[0]
+            self.rxset = tracer._make_rxset(centers, rx_radius)
+            self.cand_capacity, self.rec_capacity = int(cand_capacity), int(rec_capacity)
+            self.counters_t = torch.zeros(_lib.CTR_COUNT, dtype=torch.int64, device=dev)
+            self.cands = torch.empty(self.cand_capacity * 4, dtype=torch.int32, device=dev)
+            rc = self.rec_capacity
+            self.rec = dict(ray=torch.empty(rc, dtype=torch.int32, device=dev),
+                            rx=torch.empty(rc, dtype=torch.int32, device=dev),
+                            nverts=torch.empty(rc, dtype=torch.int32, device=dev),
+                            bin=torch.empty(rc, dtype=torch.int64, device=dev),
+                            amp=torch.empty(rc, dtype=torch.float64, device=dev),
+                            dist=torch.empty(rc, dtype=torch.float64, device=dev),
+                            paths=torch.empty((rc, B + 1, 3), dtype=torch.float32, device=dev) if want_paths else None)
+        self.kernel_launches = 0
+
+    def enqueue(self, tx_pos, tx_power, ray_range=None, dirs=None, ir=None):
+        """dirs: optional (n,4) float32 tensor already filled by ``Tracer.ray_directions`` (one wave, no chunking).
+        ir: optional (R,L) float64 tensor, zeroed here and filled with the order-free (atomic) binning."""
+        t, lib = self.t, self.t._lib
+        begin, end = ray_range if ray_range is not None else t.ray_range
+        n, B = end - begin, t.max_bounces
+        tx = float3(tx_pos)
+        with torch.cuda.device(t.device):
+            self.counters_t.zero_()
+            if dirs is None:
+                check(lib.rfrt_trace(t._env, self.rxset, tx, B, begin, end, 0, _ptr(t._scratch(n)), t.chunk_rays,
+                                     _ptr(self.counters_t), _ptr(self.cands), self.cand_capacity, None, None,
+                                     _stream_ptr()), "rfrt_trace")
+                self.kernel_launches += 2 * max(1, -(-n // t.chunk_rays))
+            else:
+                check(lib.rfrt_trace(t._env, self.rxset, tx, B, begin, end, 1, _ptr(dirs), n, _ptr(self.counters_t),
+                                     _ptr(self.cands), self.cand_capacity, None, None, _stream_ptr()), "rfrt_trace")
+                self.kernel_launches += 1
+            amp0 = tx_power / t.tx_num_rays if t.tx_num_rays else 0.0  # tracer.py:103
+            r = self.rec
+            check(lib.rfrt_trace_receive(t._env, self.rxset, tx, B, _ptr(self.cands), self.cand_capacity,
+                                         _ptr(self.counters_t), float(amp0), float(t.light_speed_mps),
+                                         float(t.sample_rate_hz), _ptr(r["ray"]), _ptr(r["rx"]), _ptr(r["nverts"]),
+                                         _ptr(r["bin"]), _ptr(r["amp"]), _ptr(r["dist"]), _ptr(r["paths"]),
+                                         self.rec_capacity, _stream_ptr()), "rfrt_trace_receive")
+            self.kernel_launches += 1
+            if ir is not None:
+                ir.zero_()
+                check(lib.rfrt_bin_ir(_ptr(r["rx"]), _ptr(r["bin"]), _ptr(r["amp"]), self.rec_capacity,
+                                      self.counters_t.data_ptr() + 8 * _lib.CTR_RECORDS, self.n_rx, ir.shape[1], 0,
+                                      _ptr(ir), _stream_ptr()), "rfrt_bin_ir")
+                self.kernel_launches += 1
+
+    def counters(self):
+        c = self.counters_t.cpu().numpy()  # synchronises the stream
+        return dict(segments=int(c[_lib.CTR_SEGMENTS]), env_hits=int(c[_lib.CTR_ENV_HITS]),
+                    candidates=int(c[_lib.CTR_CANDIDATES]), records=int(c[_lib.CTR_RECORDS]))
+
+    def close(self):
+        if self.rxset:
+            self.t._lib.rfrt_rxset_destroy(self.rxset)
+            self.rxset = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -113,7 +113,7 @@ def test_compute_cir_matches_oracle(torch_cuda, room_stl, B):
         assert a.dtype == np.float32 and np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert ir.dtype == np.float64 and ir.shape == o_ir.shape
     assert np.array_equal(ir != 0, o_ir != 0)
-    np.testing.assert_allclose(ir, o_ir, rtol=1e-5, atol=0)
+    np.testing.assert_allclose(ir, o_ir, rtol=1e-5, atol=1e-12 / n)
 
 
 def test_multi_receiver_equals_separate_runs(torch_cuda, room_stl):
@@ -137,7 +137,7 @@ def test_multi_receiver_equals_separate_runs(torch_cuda, room_stl):
         for row, nv, op in zip(rec["paths"][sel], rec["nverts"][sel], o_paths):
             assert np.array_equal(row[:nv].view(np.uint32), op.view(np.uint32))
         assert np.array_equal(ir[k] != 0, o_ir != 0)
-        np.testing.assert_allclose(ir[k], o_ir, rtol=1e-5, atol=0)
+        np.testing.assert_allclose(ir[k], o_ir, rtol=1e-5, atol=1e-12 / n)
         total += len(o_paths)
     assert total > 100 and total == rec["ray"].shape[0]
 
