@@ -131,8 +131,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
             if ((int64_t)base + cnt >= P.chunk_n) exhausted = true;
         }
         if (!__any_sync(FULL, has_ray)) break;
-        if (!has_ray) continue;
-
+        if (has_ray) {
         // ---- one bounce iteration (kernel.py:57-98, environment branch) -----------------------
         WoopRay wr = woop_setup(pos, dir);
         SlabRay sr = slab_setup(pos, dir);
@@ -152,7 +151,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
                 // enumerate every receiver whose box overlaps the segment [0, t_limit]
                 int sp = 0;
                 int node = 0;
-                for (;;) {
+                while (node >= 0) {
                     const float4 *np = reinterpret_cast<const float4 *>(P.rx_nodes + node);
                     float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
                     int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
@@ -169,9 +168,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
                         if (c1 < 0) rx_test_and_emit(P, __ldg(P.rx_order + (~c1)), pos, dir, wr, hit_env, h.t, t_limit, gid, bounce);
                         else { stack[sp * TRACE_THREADS] = c1; ++sp; }
                     }
-                    if (sp == 0) break;
-                    --sp;
-                    node = stack[sp * TRACE_THREADS];
+                    node = -1;
+                    if (sp > 0) { --sp; node = stack[sp * TRACE_THREADS]; }
                 }
             }
         }
@@ -193,6 +191,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
         } else {
             has_ray = false; // a miss repeats forever in the reference (kernel.py:97-98): nothing more to do
         }
+        } // has_ray
     }
 
     // warp-reduced counters

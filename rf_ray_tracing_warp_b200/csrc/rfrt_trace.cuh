@@ -63,55 +63,53 @@ __device__ __forceinline__ void closest_hit(const BvhNode *__restrict__ nodes, c
                                             int64_t n_prims, const WoopRay &wr, const SlabRay &sr, int *stack,
                                             float *stack_t, int stride, Hit &h)
 {
-    if (n_prims <= 0) return;
+    // One loop, ONE back-edge: every lane still traversing comes back to the same loop head each trip, so the
+    // warp stays converged (independent thread scheduling only re-converges at compiler-placed barriers;
+    // several `continue` back-edges let sub-groups of lanes run the loop separately — measured 6/32 active).
     int sp = 0;
-    int node = 0;
-    for (;;) {
+    int node = n_prims > 0 ? 0 : -1; // -1 = done
+    while (node >= 0) {
         const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
         float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
         int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
         float tn0, tn1;
         bool h0 = slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, h.t, tn0);
         bool h1 = slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, h.t, tn1);
-        int c0 = q3.x, c1 = q3.y;
-        if (h0 && c0 < 0) {
+        const int c0 = q3.x, c1 = q3.y;
+        if (c1 == c0) h1 = false; // single-primitive tree
+        // leaves: at most two triangle tests per trip, done in ONE converged region
+        int leaf = -1, leaf2 = -1;
+        if (h0 && c0 < 0) { leaf = ~c0; h0 = false; }
+        if (h1 && c1 < 0) { if (leaf < 0) leaf = ~c1; else leaf2 = ~c1; h1 = false; }
+        while (leaf >= 0) {
             float3 a, b, c; int idx; float t;
-            tri_vertices(tris, ~c0, a, b, c, idx);
+            tri_vertices(tris, leaf, a, b, c, idx);
             if (woop_hit(wr, a, b, c, t) && t >= 0.0f && (t < h.t || (t == h.t && h.face >= 0 && idx < h.face))) {
-                h.t = t; h.face = idx; h.slot = ~c0;
+                h.t = t; h.face = idx; h.slot = leaf;
             }
-            h0 = false;
+            leaf = leaf2;
+            leaf2 = -1;
         }
-        if (h1 && c1 < 0 && c1 != c0) {
-            float3 a, b, c; int idx; float t;
-            tri_vertices(tris, ~c1, a, b, c, idx);
-            if (woop_hit(wr, a, b, c, t) && t >= 0.0f && (t < h.t || (t == h.t && h.face >= 0 && idx < h.face))) {
-                h.t = t; h.face = idx; h.slot = ~c1;
-            }
-            h1 = false;
-        }
-        if (c1 < 0) h1 = false;
+        int next = -1;
         if (h0 && h1) {
             // descend into the nearer child first, defer the other with its entry distance
-            bool swap = tn1 < tn0;
-            int near_c = swap ? c1 : c0, far_c = swap ? c0 : c1;
-            float far_t = swap ? tn0 : tn1;
-            stack[sp * stride] = far_c;
-            stack_t[sp * stride] = far_t;
+            const bool swap = tn1 < tn0;
+            next = swap ? c1 : c0;
+            stack[sp * stride] = swap ? c0 : c1;
+            stack_t[sp * stride] = swap ? tn0 : tn1;
             ++sp;
-            node = near_c;
-            continue;
+        } else if (h0) {
+            next = c0;
+        } else if (h1) {
+            next = c1;
+        } else {
+            // pop, skipping entries that the current best already rules out
+            while (sp > 0) {
+                --sp;
+                if (stack_t[sp * stride] <= h.t) { next = stack[sp * stride]; break; }
+            }
         }
-        if (h0) { node = c0; continue; }
-        if (h1) { node = c1; continue; }
-        // pop, skipping entries that the current best already rules out
-        bool found = false;
-        while (sp > 0) {
-            --sp;
-            float tn = stack_t[sp * stride];
-            if (tn <= h.t) { node = stack[sp * stride]; found = true; break; }
-        }
-        if (!found) break;
+        node = next;
     }
 }
 
