@@ -17,7 +17,7 @@ import time
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, sharding
 from ._lib import RfrtError, c_f, c_i32, c_i64, c_u64, check, float3
 from .mesh_io import unit_icosphere
 
@@ -70,8 +70,7 @@ class Tracer:
         if self.shard and torch.distributed.is_available() and torch.distributed.is_initialized():
             self._world, self._rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
         if ray_range is None:
-            n = self.tx_num_rays
-            ray_range = (self._rank * n // self._world, (self._rank + 1) * n // self._world)
+            ray_range = sharding.ray_range(self.tx_num_rays, self._rank, self._world)
         self.ray_range = (int(ray_range[0]), int(ray_range[1]))
 
         # tracer.py:22-23: vertices -> vec3 float32, faces.flatten() -> int32
@@ -171,41 +170,14 @@ class Tracer:
         ordered binning below gives bit-identical results for any GPU count."""
         if self._world == 1:
             return rec, stats
-        dist = torch.distributed
-        n_local = torch.tensor([rec["ray"].shape[0]], dtype=torch.int64, device=self.device)
-        counts = [torch.zeros_like(n_local) for _ in range(self._world)]
-        dist.all_gather(counts, n_local)
-        counts = [int(x.item()) for x in counts]
-        m = max(max(counts), 1)
-        out = {}
-        for k, t in rec.items():
-            if t is None:
-                out[k] = None
-                continue
-            pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
-            pad[: t.shape[0]] = t
-            parts = [torch.empty_like(pad) for _ in range(self._world)]
-            dist.all_gather(parts, pad)
-            out[k] = torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
-        tot = torch.tensor([stats["segments"], stats["env_hits"], stats["candidates"], stats["records"]],
-                           dtype=torch.int64, device=self.device)
-        dist.all_reduce(tot)
-        tot = tot.cpu().tolist()
-        return out, dict(segments=tot[0], env_hits=tot[1], candidates=tot[2], records=tot[3])
-
-    @staticmethod
-    def _sort_records(rec):
-        """(rx, ray id) order == the reference's accumulation order per receiver (tracer.py:87,102)."""
-        key = (rec["rx"].to(torch.int64) << 32) | (rec["ray"].to(torch.int64) & 0xFFFFFFFF)
-        order = torch.argsort(key)
-        return {k: (v[order].contiguous() if v is not None else None) for k, v in rec.items()}
+        return sharding.gather_records(rec), sharding.sum_stats(stats, self.device)
 
     def _records(self, tx_pos, tx_power, rx_positions, rx_radius, want_paths):
         centers = np.ascontiguousarray(np.asarray(rx_positions, dtype=np.float64).reshape(-1, 3))
         with torch.cuda.device(self.device):
             rec, stats = self._trace_records(tx_pos, tx_power, centers, rx_radius, want_paths)
             rec, stats = self._gather_records(rec, stats)
-            rec = self._sort_records(rec)
+            rec = sharding.sort_records(rec)
         self.last_stats = stats
         return rec, centers.shape[0]
 
