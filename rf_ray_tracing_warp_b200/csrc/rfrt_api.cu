@@ -4,6 +4,7 @@
 #include <memory>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "rfrt_internal.h"
 
@@ -245,6 +246,30 @@ extern "C" int rfrt_rxset_create(const double *d_centers_xyz, int64_t n_receiver
     int rc = build_lbvh(lo, hi, n_receivers, stream, &r->bvh);
     cudaFree(d_unit); cudaFree(lo); cudaFree(hi);
     if (rc) { cudaFree(r->centers); cudaFree(r->verts); return rc; }
+    {
+        // BVH over the unit icosphere's faces, used (after mapping the ray into unit space) to prune the exact
+        // per-receiver triangle tests.  Boxes are inflated: the mapping (o - c) / r is only approximate in fp32.
+        std::vector<float4> ulo(n_faces), uhi(n_faces);
+        for (int f = 0; f < n_faces; ++f) {
+            float l[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, h[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            for (int c = 0; c < 3; ++c)
+                for (int a = 0; a < 3; ++a) {
+                    float x = (float)h_unit_vertices[3 * h_faces[3 * f + c] + a];
+                    l[a] = fminf(l[a], x); h[a] = fmaxf(h[a], x);
+                }
+            const float infl = 4.0e-3f;
+            ulo[f] = make_float4(l[0] - infl, l[1] - infl, l[2] - infl, 0.f);
+            uhi[f] = make_float4(h[0] + infl, h[1] + infl, h[2] + infl, 0.f);
+        }
+        float4 *dlo = nullptr, *dhi = nullptr;
+        RFRT_CUDA(cudaMalloc(&dlo, sizeof(float4) * n_faces));
+        RFRT_CUDA(cudaMalloc(&dhi, sizeof(float4) * n_faces));
+        RFRT_CUDA(cudaMemcpyAsync(dlo, ulo.data(), sizeof(float4) * n_faces, cudaMemcpyHostToDevice, stream));
+        RFRT_CUDA(cudaMemcpyAsync(dhi, uhi.data(), sizeof(float4) * n_faces, cudaMemcpyHostToDevice, stream));
+        rc = build_lbvh(dlo, dhi, n_faces, stream, &r->unit_bvh); // synchronises the stream
+        cudaFree(dlo); cudaFree(dhi);
+        if (rc) { cudaFree(r->centers); cudaFree(r->verts); free_bvh(&r->bvh); return rc; }
+    }
     std::lock_guard<std::mutex> lock(g_mutex);
     rfrt_handle h = g_next_handle++;
     g_rxsets[h] = r.release();
@@ -263,6 +288,7 @@ extern "C" int rfrt_rxset_destroy(rfrt_handle rxset)
         g_rxsets.erase(it);
     }
     free_bvh(&r->bvh);
+    free_bvh(&r->unit_bvh);
     if (r->verts) cudaFree(r->verts);
     if (r->centers) cudaFree(r->centers);
     delete r;

@@ -46,6 +46,7 @@ struct Mesh {
 
 struct RxSet {
     Bvh bvh;                  // over receiver bounding boxes
+    Bvh unit_bvh;             // over the UNIT icosphere's triangles (shared by all receivers: translate + scale)
     float *verts = nullptr;   // [R * n_unit * 3] fp32
     int64_t n_receivers = 0;
     int32_t n_unit = 0;

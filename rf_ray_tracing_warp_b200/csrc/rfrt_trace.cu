@@ -79,17 +79,15 @@ __device__ __forceinline__ bool rx_sphere_filter(float3 p, float3 d, float cx, f
     return tc - half <= t_limit * 1.0001f + 1.0e-6f;
 }
 
-// Exact receiver test for one segment (kernel.py:71,85) behind a conservative sphere filter; appends the
-// candidate (ray id, receiver, bounce).  Rarely taken, so kept out of line to spare the hot loop's registers.
-__device__ __noinline__ void rx_test_and_emit(const TraceParams &P, int k, float3 pos, float3 dir, const WoopRay &wr,
-                                              bool hit_env, float t_env, float t_limit, uint32_t gid, int bounce)
+// Receiver candidates for one segment (kernel.py:71,85): a conservative bounding-sphere filter only.  The exact
+// 80-triangle test is NOT done here — the literal replay (k_trace_receive) performs it anyway and drops the
+// candidates whose first receiver hit is not at this bounce (false positives are ~10 % of the candidates).
+__device__ __forceinline__ void rx_filter_and_emit(const TraceParams &P, int k, float3 pos, float3 dir, float t_limit,
+                                                   uint32_t gid, int bounce)
 {
     float cx = (float)__ldg(P.rx_centers + 3 * k), cy = (float)__ldg(P.rx_centers + 3 * k + 1),
           cz = (float)__ldg(P.rx_centers + 3 * k + 2);
     if (!rx_sphere_filter(pos, dir, cx, cy, cz, P.rx_radius, t_limit)) return;
-    float t_rx;
-    if (!rx_query(P.rx_verts + (int64_t)k * P.n_unit * 3, c_rx_faces, P.n_faces, wr, 1.0e6f, t_rx)) return;
-    if (hit_env && !(t_env > t_rx)) return;
     unsigned long long slot = atomicAdd(&P.counters[RFRT_CTR_CANDIDATES], 1ull);
     if ((int64_t)slot < P.cand_capacity) P.candidates[slot] = make_uint4(gid, (uint32_t)k, (uint32_t)bounce, 0u);
 }
@@ -146,7 +144,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
             const float t_limit = hit_env ? h.t : 1.0e6f;
             const uint32_t gid = (uint32_t)(P.chunk_begin + ray);
             if (P.n_rx == 1) {
-                rx_test_and_emit(P, 0, pos, dir, wr, hit_env, h.t, t_limit, gid, bounce);
+                rx_filter_and_emit(P, 0, pos, dir, t_limit, gid, bounce);
             } else {
                 // enumerate every receiver whose box overlaps the segment [0, t_limit]
                 int sp = 0;
@@ -161,11 +159,11 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
                     int c0 = q3.x, c1 = q3.y;
                     if (c1 == c0) h1 = false;
                     if (h0) {
-                        if (c0 < 0) rx_test_and_emit(P, __ldg(P.rx_order + (~c0)), pos, dir, wr, hit_env, h.t, t_limit, gid, bounce);
+                        if (c0 < 0) rx_filter_and_emit(P, __ldg(P.rx_order + (~c0)), pos, dir, t_limit, gid, bounce);
                         else { stack[sp * TRACE_THREADS] = c0; ++sp; }
                     }
                     if (h1) {
-                        if (c1 < 0) rx_test_and_emit(P, __ldg(P.rx_order + (~c1)), pos, dir, wr, hit_env, h.t, t_limit, gid, bounce);
+                        if (c1 < 0) rx_filter_and_emit(P, __ldg(P.rx_order + (~c1)), pos, dir, t_limit, gid, bounce);
                         else { stack[sp * TRACE_THREADS] = c1; ++sp; }
                     }
                     node = -1;
@@ -214,9 +212,9 @@ struct LiteralEnv {
 
 // kernel.py:38-98 for one ray and one receiver.  Sink receives the vertex writes and RX-hit events.
 template <class Sink>
-__device__ __forceinline__ void literal_trace(const LiteralEnv &E, const float *__restrict__ rx_verts, int n_faces,
-                                              float3 tx, int max_bounces, uint32_t tid, int *stack, float *stack_t,
-                                              int stride, Sink &sink)
+__device__ __forceinline__ void literal_trace(const LiteralEnv &E, const RxView *rx, int n_faces, float3 tx,
+                                              int max_bounces, uint32_t tid, int *stack, float *stack_t, int stride,
+                                              Sink &sink)
 {
     float3 dir = ray_direction(tid); // kernel.py:51-52
     float3 pos = tx;                 // :53
@@ -225,7 +223,7 @@ __device__ __forceinline__ void literal_trace(const LiteralEnv &E, const float *
         WoopRay wr = woop_setup(pos, dir);
         SlabRay sr = slab_setup(pos, dir);
         float t_rx = 0.0f;
-        bool maybe_hit_rx = rx_verts ? rx_query(rx_verts, c_rx_faces, n_faces, wr, 1.0e6f, t_rx) : false; // :71
+        bool maybe_hit_rx = rx ? rx_query(*rx, c_rx_faces, n_faces, wr, pos, dir, 1.0e6f, stack, stack_t, stride, t_rx) : false; // :71
         Hit h;
         h.t = 1.0e6f; h.face = -1; h.slot = -1;
         closest_hit(E.nodes, E.tris, E.n_tris, wr, sr, stack, stack_t, stride, h);                          // :82
@@ -241,6 +239,8 @@ __device__ __forceinline__ void literal_trace(const LiteralEnv &E, const float *
             float3 a, b, c; int idx;
             tri_vertices(E.tris, h.slot, a, b, c, idx);
             dir = reflect(dir, tri_normal(a, b, c)); // :96
+        } else {
+            break; // :97-98: nothing changes, so every later iteration repeats the same two misses
         }
     }
 }
@@ -261,8 +261,8 @@ struct CompatSink {
 };
 
 __global__ void __launch_bounds__(TRACE_THREADS)
-k_trace_compat(LiteralEnv E, const float *__restrict__ rx_verts, int n_faces, float3 tx, int max_bounces,
-               int64_t ray_begin, int64_t n_rays, float *traced, float *received, uint32_t *mask, int stack_depth)
+k_trace_compat(LiteralEnv E, RxView rx, int has_rx, int n_faces, float3 tx, int max_bounces, int64_t ray_begin, int64_t n_rays,
+               float *traced, float *received, uint32_t *mask, int stack_depth)
 {
     extern __shared__ int s_stack_raw[];
     int *stack = s_stack_raw + threadIdx.x;
@@ -270,7 +270,7 @@ k_trace_compat(LiteralEnv E, const float *__restrict__ rx_verts, int n_faces, fl
     const int64_t row = 3 * (int64_t)(max_bounces + 1);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_rays; i += (int64_t)gridDim.x * blockDim.x) {
         CompatSink sink{traced + i * row, received + i * row, mask + i};
-        literal_trace(E, rx_verts, n_faces, tx, max_bounces, (uint32_t)(ray_begin + i), stack, stack_t,
+        literal_trace(E, has_rx ? &rx : nullptr, n_faces, tx, max_bounces, (uint32_t)(ray_begin + i), stack, stack_t,
                       TRACE_THREADS, sink);
     }
 }
@@ -315,6 +315,10 @@ __device__ __forceinline__ double bounce_amplitude(double angle_between)
 struct ReceiveParams {
     LiteralEnv env;
     const float *rx_verts;
+    const double *rx_centers;
+    const BvhNode *unit_nodes;
+    const int32_t *unit_order;
+    float inv_r;
     int32_t n_unit;
     int32_t n_faces;
     float3 tx;
@@ -347,8 +351,12 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_receive(const ReceivePa
         RecordSink sink;
         sink.last_rx_bounce = -1;
         sink.first_rx_bounce = -1;
-        literal_trace(P.env, P.rx_verts + (int64_t)cand.y * P.n_unit * 3, P.n_faces, P.tx, P.max_bounces, cand.x,
-                      stack, stack_t, TRACE_THREADS, sink);
+        RxView rx;
+        rx.verts = P.rx_verts + (int64_t)cand.y * P.n_unit * 3;
+        rx.unit_nodes = P.unit_nodes; rx.unit_order = P.unit_order;
+        rx.cx = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y); rx.cy = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y + 1);
+        rx.cz = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y + 2); rx.inv_r = P.inv_r;
+        literal_trace(P.env, &rx, P.n_faces, P.tx, P.max_bounces, cand.x, stack, stack_t, TRACE_THREADS, sink);
         // a candidate raised at a later bounce than the replay's first receiver hit is a duplicate
         if (sink.last_rx_bounce < 0 || sink.first_rx_bounce != (int)cand.z) continue;
         int nverts = sink.last_rx_bounce + 2;
@@ -420,6 +428,7 @@ int stack_depth_for(const Mesh *m, const RxSet *r)
 {
     int d = m->bvh.max_depth;
     if (r && r->bvh.max_depth > d) d = r->bvh.max_depth;
+    if (r && r->unit_bvh.max_depth > d) d = r->unit_bvh.max_depth;
     d += 2;
     if (d < 8) d = 8;
     return d;
@@ -545,6 +554,8 @@ extern "C" int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const
     ReceiveParams P;
     P.env.nodes = m->bvh.nodes; P.env.tris = m->tris; P.env.n_tris = m->bvh.n_prims;
     P.rx_verts = r->verts; P.n_unit = r->n_unit; P.n_faces = r->n_faces;
+    P.rx_centers = r->centers; P.unit_nodes = r->unit_bvh.nodes; P.unit_order = r->unit_bvh.prim_order;
+    P.inv_r = (float)(1.0 / r->radius);
     P.tx = make_float3(h_tx_pos[0], h_tx_pos[1], h_tx_pos[2]);
     P.max_bounces = max_bounces;
     P.candidates = (const uint4 *)d_candidates; P.cand_capacity = cand_capacity;
@@ -552,7 +563,7 @@ extern "C" int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const
     P.amp0 = amp0; P.light_speed = light_speed_mps; P.sample_rate = sample_rate_hz;
     P.rec_ray = d_rec_ray; P.rec_rx = d_rec_rx; P.rec_nverts = d_rec_nverts; P.rec_bin = d_rec_bin;
     P.rec_amp = d_rec_amp; P.rec_dist = d_rec_dist; P.rec_paths = d_rec_paths; P.rec_capacity = rec_capacity;
-    P.stack_depth = stack_depth_for(m, nullptr);
+    P.stack_depth = stack_depth_for(m, r);
     const size_t smem = stack_bytes(P.stack_depth);
     int grid = 0;
     int rc = grid_for((const void *)k_trace_receive, smem, &grid);
@@ -585,18 +596,26 @@ extern "C" int rfrt_trace_paths_compat(rfrt_handle env_mesh, const float *h_tx_p
     }
     if (n_rays == 0) return RFRT_OK;
     LiteralEnv E{m->bvh.nodes, m->tris, m->bvh.n_prims};
-    int depth = stack_depth_for(m, nullptr);
+    int depth = stack_depth_for(m, r);
     const size_t smem = stack_bytes(depth);
     int grid = 0;
     int rc = grid_for((const void *)k_trace_compat, smem, &grid);
+    RxView rxv{};
+    if (r) {
+        double c[3];
+        RFRT_CUDA(cudaMemcpyAsync(c, r->centers + 3 * rx_index, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream));
+        RFRT_CUDA(cudaStreamSynchronize(stream));
+        rxv.verts = r->verts + rx_index * r->n_unit * 3;
+        rxv.unit_nodes = r->unit_bvh.nodes; rxv.unit_order = r->unit_bvh.prim_order;
+        rxv.cx = (float)c[0]; rxv.cy = (float)c[1]; rxv.cz = (float)c[2]; rxv.inv_r = (float)(1.0 / r->radius);
+    }
     if (rc) return rc;
     int64_t need = (n_rays + TRACE_THREADS - 1) / TRACE_THREADS;
     if (need < grid) grid = (int)need;
     if (r) { rc = upload_faces(r, stream); if (rc) return rc; }
     k_trace_compat<<<grid, TRACE_THREADS, smem, stream>>>(
-        E, r ? r->verts + rx_index * r->n_unit * 3 : nullptr, r ? r->n_faces : 0,
-        make_float3(h_tx_pos[0], h_tx_pos[1], h_tx_pos[2]), max_bounces, ray_begin, n_rays, d_traced_paths,
-        d_received_paths, d_row_mask, depth);
+        E, rxv, r ? 1 : 0, r ? r->n_faces : 0, make_float3(h_tx_pos[0], h_tx_pos[1], h_tx_pos[2]), max_bounces, ray_begin, n_rays,
+        d_traced_paths, d_received_paths, d_row_mask, depth);
     RFRT_CUDA(cudaGetLastError());
     return RFRT_OK;
 }

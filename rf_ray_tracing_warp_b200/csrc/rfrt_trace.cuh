@@ -57,79 +57,130 @@ struct Hit {
     int slot;  // sorted slot of that triangle
 };
 
+// Traversal state codes: node >= 0 internal node, node < 0 leaf (~slot), TRAV_DONE = walk finished.
+constexpr int TRAV_DONE = (int)0x80000000;
+
+// pop the next stack entry that the current best does not already rule out (TRAV_DONE if none)
+__device__ __forceinline__ int stack_pop(int *stack, float *stack_t, int stride, int &sp, float best_t)
+{
+    int next = TRAV_DONE;
+    while (sp > 0) {
+        --sp;
+        if (stack_t[sp * stride] <= best_t) { next = stack[sp * stride]; break; }
+    }
+    return next;
+}
+
+// visit one internal node: slab-test both child boxes (4 x 128-bit loads), go to the nearer hit child and
+// defer the other (with its entry distance) on the stack.  Returns the next state code.
+__device__ __forceinline__ int node_step(const BvhNode *__restrict__ nodes, int node, const SlabRay &sr, float best_t,
+                                         int *stack, float *stack_t, int stride, int &sp)
+{
+    const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
+    float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+    int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
+    float tn0, tn1;
+    bool h0 = slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, best_t, tn0);
+    bool h1 = slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, best_t, tn1);
+    const int c0 = q3.x, c1 = q3.y;
+    if (c1 == c0) h1 = false; // single-primitive tree
+    int next;
+    if (h0 && h1) {
+        const bool swap = tn1 < tn0;
+        next = swap ? c1 : c0;
+        stack[sp * stride] = swap ? c0 : c1;
+        stack_t[sp * stride] = swap ? tn0 : tn1;
+        ++sp;
+    } else if (h0) {
+        next = c0;
+    } else if (h1) {
+        next = c1;
+    } else {
+        next = stack_pop(stack, stack_t, stride, sp, best_t);
+    }
+    return next;
+}
+
+// test the triangle of one leaf (closest t, 0 <= t < best; equal t -> lowest triangle index), then pop
+__device__ __forceinline__ int leaf_step(const BvhTri *__restrict__ tris, int node, const WoopRay &wr, Hit &h,
+                                         int *stack, float *stack_t, int stride, int &sp)
+{
+    const int slot = ~node;
+    float3 a, b, c; int idx; float t;
+    tri_vertices(tris, slot, a, b, c, idx);
+    if (woop_hit(wr, a, b, c, t) && t >= 0.0f && (t < h.t || (t == h.t && h.face >= 0 && idx < h.face))) {
+        h.t = t; h.face = idx; h.slot = slot;
+    }
+    return stack_pop(stack, stack_t, stride, sp, h.t);
+}
+
 // mesh_query_ray (kernel.py:71,82): closest accepted hit, 0 <= t < max_t; equal t -> lowest index.
 // `stack` / `stack_t` point at this thread's column of the shared-memory stack (stride = blockDim.x).
+// "while-while" (Aila & Laine): the inner loop walks internal nodes until THIS lane holds a leaf, then the
+// lanes holding one test their triangles together.  Each loop has ONE back-edge so the warp re-converges on
+// every trip (several `continue` back-edges let sub-groups of lanes run the loop separately: measured 6/32
+// lanes active; testing leaves inside the node loop: 3/32 active in the triangle test).
 __device__ __forceinline__ void closest_hit(const BvhNode *__restrict__ nodes, const BvhTri *__restrict__ tris,
                                             int64_t n_prims, const WoopRay &wr, const SlabRay &sr, int *stack,
                                             float *stack_t, int stride, Hit &h)
 {
-    // "while-while" traversal (Aila & Laine): an inner loop walks internal nodes until THIS lane holds a leaf,
-    // then all lanes of the warp that hold one test their triangle together.  Each loop has ONE back-edge so
-    // the warp re-converges every trip (several `continue` back-edges let sub-groups of lanes run the loop
-    // separately: measured 6/32 lanes active; testing leaves inside the node loop: 3/32 in the triangle test).
-    // Stack entries are child codes: >= 0 internal node, < 0 leaf (~slot); DONE ends the walk.
-    const int DONE = (int)0x80000000;
     int sp = 0;
-    int node = n_prims > 0 ? 0 : DONE;
-    while (node != DONE) {
-        while (node >= 0) {
-            const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
-            float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-            int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
-            float tn0, tn1;
-            bool h0 = slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, h.t, tn0);
-            bool h1 = slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, h.t, tn1);
-            const int c0 = q3.x, c1 = q3.y;
-            if (c1 == c0) h1 = false; // single-primitive tree
-            int next = DONE;
-            if (h0 && h1) {
-                // nearer child first; the other waits on the stack with its entry distance
-                const bool swap = tn1 < tn0;
-                next = swap ? c1 : c0;
-                stack[sp * stride] = swap ? c0 : c1;
-                stack_t[sp * stride] = swap ? tn0 : tn1;
-                ++sp;
-            } else if (h0) {
-                next = c0;
-            } else if (h1) {
-                next = c1;
-            } else {
-                while (sp > 0) { // pop, skipping entries the current best already rules out
-                    --sp;
-                    if (stack_t[sp * stride] <= h.t) { next = stack[sp * stride]; break; }
-                }
-            }
-            node = next;
-        }
-        if (node != DONE) {
-            const int slot = ~node;
-            float3 a, b, c; int idx; float t;
-            tri_vertices(tris, slot, a, b, c, idx);
-            if (woop_hit(wr, a, b, c, t) && t >= 0.0f && (t < h.t || (t == h.t && h.face >= 0 && idx < h.face))) {
-                h.t = t; h.face = idx; h.slot = slot;
-            }
-            node = DONE;
-            while (sp > 0) {
-                --sp;
-                if (stack_t[sp * stride] <= h.t) { node = stack[sp * stride]; break; }
-            }
-        }
+    int node = n_prims > 0 ? 0 : TRAV_DONE;
+    while (node != TRAV_DONE) {
+        while (node >= 0) node = node_step(nodes, node, sr, h.t, stack, stack_t, stride, sp);
+        if (node != TRAV_DONE) node = leaf_step(tris, node, wr, h, stack, stack_t, stride, sp);
     }
 }
 
-// Brute-force exact receiver query (kernel.py:71 against the 80-triangle icosphere of receiver k):
-// returns true and the closest t in [0, max_t).
-__device__ __forceinline__ bool rx_query(const float *__restrict__ rx_verts, const uint8_t *faces, int n_faces,
-                                         const WoopRay &wr, float max_t, float &t_out)
+// One receiver as seen by the kernels: its fp32 world-space vertices plus the shared unit-icosphere BVH.
+struct RxView {
+    const float *verts;          // [n_unit*3] world-space vertices of THIS receiver
+    const BvhNode *unit_nodes;   // BVH over the unit icosphere's faces (shared by all receivers)
+    const int32_t *unit_order;   // sorted slot -> face index
+    float cx, cy, cz, inv_r;     // centre and 1/radius: world -> unit space (approximate, pruning only)
+};
+
+// Exact receiver query (kernel.py:71 against the 80-triangle icosphere of one receiver): closest t in
+// [0, max_t) over ALL faces.  The faces actually tested are pruned with the unit-space BVH (boxes inflated by
+// 4e-3 of the radius; t is the same parameter in both spaces); every triangle test itself is the exact
+// world-space Woop test, so the result equals the brute-force minimum.
+__device__ __forceinline__ bool rx_query(const RxView &rx, const uint8_t *faces, int n_faces, const WoopRay &wr,
+                                         float3 pos, float3 dir, float max_t, int *stack, float *stack_t, int stride,
+                                         float &t_out)
 {
+    const float3 ou = make_float3((pos.x - rx.cx) * rx.inv_r, (pos.y - rx.cy) * rx.inv_r, (pos.z - rx.cz) * rx.inv_r);
+    const float3 du = make_float3(dir.x * rx.inv_r, dir.y * rx.inv_r, dir.z * rx.inv_r);
+    const SlabRay su = slab_setup(ou, du);
     float best = max_t;
-    for (int f = 0; f < n_faces; ++f) {
-        int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
-        float3 a = make_float3(__ldg(rx_verts + 3 * i0), __ldg(rx_verts + 3 * i0 + 1), __ldg(rx_verts + 3 * i0 + 2));
-        float3 b = make_float3(__ldg(rx_verts + 3 * i1), __ldg(rx_verts + 3 * i1 + 1), __ldg(rx_verts + 3 * i1 + 2));
-        float3 c = make_float3(__ldg(rx_verts + 3 * i2), __ldg(rx_verts + 3 * i2 + 1), __ldg(rx_verts + 3 * i2 + 2));
-        float t;
-        if (woop_hit(wr, a, b, c, t) && t < best && t >= 0.0f) best = t;
+    int sp = 0;
+    int node = 0;
+    if (fmaxf(fmaxf(fabsf(ou.x), fabsf(ou.y)), fabsf(ou.z)) > 8192.0f) {
+        // origin farther than 8192 radii: fp32 unit-space coordinates get too coarse for the 4e-3 box inflation,
+        // so test every face (n_faces == number of unit-BVH leaves)
+        node = TRAV_DONE;
+        for (int f = 0; f < n_faces; ++f) {
+            const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+            const float *v = rx.verts;
+            float3 a = make_float3(__ldg(v + 3 * i0), __ldg(v + 3 * i0 + 1), __ldg(v + 3 * i0 + 2));
+            float3 b = make_float3(__ldg(v + 3 * i1), __ldg(v + 3 * i1 + 1), __ldg(v + 3 * i1 + 2));
+            float3 c = make_float3(__ldg(v + 3 * i2), __ldg(v + 3 * i2 + 1), __ldg(v + 3 * i2 + 2));
+            float t;
+            if (woop_hit(wr, a, b, c, t) && t < best && t >= 0.0f) best = t;
+        }
+    }
+    while (node != TRAV_DONE) {
+        while (node >= 0) node = node_step(rx.unit_nodes, node, su, best, stack, stack_t, stride, sp);
+        if (node != TRAV_DONE) {
+            const int f = __ldg(rx.unit_order + (~node));
+            const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+            const float *v = rx.verts;
+            float3 a = make_float3(__ldg(v + 3 * i0), __ldg(v + 3 * i0 + 1), __ldg(v + 3 * i0 + 2));
+            float3 b = make_float3(__ldg(v + 3 * i1), __ldg(v + 3 * i1 + 1), __ldg(v + 3 * i1 + 2));
+            float3 c = make_float3(__ldg(v + 3 * i2), __ldg(v + 3 * i2 + 1), __ldg(v + 3 * i2 + 2));
+            float t;
+            if (woop_hit(wr, a, b, c, t) && t < best && t >= 0.0f) best = t;
+            node = stack_pop(stack, stack_t, stride, sp, best);
+        }
     }
     t_out = best;
     return best < max_t;
