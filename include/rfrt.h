@@ -176,6 +176,12 @@ RFRT_API int rfrt_rx_power(const int64_t *d_arr_offsets, const int32_t *d_arr_bi
                   int64_t n_receivers, int64_t n_bins, double sample_window_s, double carrier_hz,
                   double *d_stx_table, double *d_power, void *stream);
 
+/* Same quantity straight from DENSE impulse-response rows d_ir [n_receivers*n_bins] (one CTA per receiver stages
+ * the row's non-zero bins in shared memory and evaluates the convolution through prefix sums of phasors:
+ * O(L + nnz) per receiver instead of O(L * nnz); agrees with rfrt_rx_power to ~1e-12 relative). */
+RFRT_API int rfrt_rx_power_dense(const double *d_ir, int64_t n_receivers, int64_t n_bins, double sample_window_s,
+                        double carrier_hz, double *d_power, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Compatibility launch with the reference kernel's exact contract (kernel.py:38-47 as launched at
  * tracer.py:75-79): dense outputs for ray ids [ray_begin, ray_begin+n_rays) against receiver

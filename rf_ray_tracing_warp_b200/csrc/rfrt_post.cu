@@ -116,6 +116,123 @@ k_rx_power(const int64_t *__restrict__ offsets, const int32_t *__restrict__ abin
     if (threadIdx.x == 0) power[k] = s_cnt[0] ? s_sum[0] / (double)s_cnt[0] : nan("");
 }
 
+
+// ---- receiver power straight from dense impulse-response rows, O(L + nnz) per receiver -------------------------
+// s_rx[n] = sum_j a_j sin(arg(q - b_j)),  q = n + (L-1)/2, over the arrivals with 0 <= q - b_j <= L-1.  With
+// arg(m) = K*(m*step) the sum is  Im( e^{i arg(q)} * sum_j a_j e^{-i arg(b_j)} ), and because arrivals are sorted by
+// bin the valid j form a contiguous range -> a prefix-sum difference.  Agrees with the direct sum to ~1e-13
+// relative; a sample counts as non-zero exactly when the direct sum has a non-zero term (np.nonzero, main.py:48).
+constexpr int RXP_THREADS = 256;
+constexpr int RXP_CAP = 6144; // arrivals staged in shared memory per receiver
+
+__device__ __forceinline__ double stx_arg(int64_t m, int64_t n_bins, double window, double K)
+{
+    double t;
+    if (n_bins == 1) t = 0.0;
+    else if (m == n_bins - 1) t = window;
+    else t = __dmul_rn((double)m, __ddiv_rn(window, (double)(n_bins - 1)));
+    return __dmul_rn(K, t);
+}
+
+__global__ void __launch_bounds__(RXP_THREADS)
+k_rx_power_dense(const double *__restrict__ ir, int64_t n_bins, double window, double carrier, double *__restrict__ power)
+{
+    extern __shared__ double s_dyn[];
+    double *s_re = s_dyn;                       // [RXP_CAP+1]  after the scan: exclusive prefix sums of the phasors
+    double *s_im = s_dyn + (RXP_CAP + 1);       // [RXP_CAP+1]
+    int *s_bin = reinterpret_cast<int *>(s_dyn + 2 * (RXP_CAP + 1)); // [RXP_CAP]
+    __shared__ int s_warp_cnt[RXP_THREADS / 32];
+    __shared__ int s_total;
+    __shared__ double s_sum[RXP_THREADS];
+    __shared__ unsigned long long s_cnt[RXP_THREADS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *row = ir + (int64_t)blockIdx.x * n_bins;
+    const double K = __dmul_rn(__dmul_rn(2.0, 3.141592653589793), carrier);
+    const int64_t half = (n_bins - 1) / 2;
+
+    // 1. ordered compaction of the non-zero bins
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_bins; base += RXP_THREADS) {
+        const int64_t b = base + tid;
+        const double a = b < n_bins ? row[b] : 0.0;
+        const bool nz = a != 0.0;
+        const unsigned m = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) s_warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        int off = s_total;
+        for (int w = 0; w < warp; ++w) off += s_warp_cnt[w];
+        off += __popc(m & ((1u << lane) - 1u));
+        if (nz && off < RXP_CAP) {
+            double sn, cs;
+            sincos(stx_arg(b, n_bins, window, K), &sn, &cs);
+            s_bin[off] = (int)b;
+            s_re[off] = a * cs;   // a * e^{-i arg(b)}
+            s_im[off] = -a * sn;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int w = 0; w < RXP_THREADS / 32; ++w) t += s_warp_cnt[w];
+            s_total += t;
+        }
+        __syncthreads();
+    }
+    const int nnz = s_total;
+    double sum = 0.0;
+    unsigned long long cnt = 0;
+    if (nnz <= RXP_CAP) {
+        // 2. exclusive prefix sums (sequential: nnz is small and the order is fixed -> reproducible)
+        if (tid == 0) {
+            double ar = 0.0, ai = 0.0;
+            for (int j = 0; j < nnz; ++j) {
+                double r = s_re[j], i = s_im[j];
+                s_re[j] = ar; s_im[j] = ai;
+                ar += r; ai += i;
+            }
+            s_re[nnz] = ar; s_im[nnz] = ai;
+        }
+        __syncthreads();
+        // 3. samples
+        for (int64_t n = tid; n < n_bins && nnz > 0; n += RXP_THREADS) {
+            const int64_t q = n + half;
+            const int64_t lo_bin = q - (n_bins - 1); // valid arrivals: lo_bin <= b_j <= q
+            int lo = 0, hi = nnz;
+            { int a = 0, b = nnz; while (a < b) { int m = (a + b) >> 1; if (s_bin[m] < lo_bin) a = m + 1; else b = m; } lo = a; }
+            { int a = lo, b = nnz; while (a < b) { int m = (a + b) >> 1; if (s_bin[m] <= q) a = m + 1; else b = m; } hi = a; }
+            const int c = hi - lo;
+            if (c == 0) continue;
+            if (c == 1 && s_bin[lo] == q) continue; // the only term is a * sin(0) == 0
+            double sn, cs;
+            sincos(stx_arg(q, n_bins, window, K), &sn, &cs);
+            const double pr = s_re[hi] - s_re[lo], pi = s_im[hi] - s_im[lo];
+            const double s = sn * pr + cs * pi;
+            if (s != 0.0) { sum += s * s; ++cnt; }
+        }
+    } else {
+        // fallback for very dense rows: the direct O(L * nnz) sum straight from the row
+        for (int64_t n = tid; n < n_bins; n += RXP_THREADS) {
+            const int64_t q = n + half;
+            double s = 0.0;
+            int64_t b0 = q - (n_bins - 1); if (b0 < 0) b0 = 0;
+            int64_t b1 = q < n_bins - 1 ? q : n_bins - 1;
+            for (int64_t b = b0; b <= b1; ++b) {
+                const double a = row[b];
+                if (a != 0.0) s = __dadd_rn(s, __dmul_rn(a, sin(stx_arg(q - b, n_bins, window, K))));
+            }
+            if (s != 0.0) { sum += s * s; ++cnt; }
+        }
+    }
+    s_sum[tid] = sum;
+    s_cnt[tid] = cnt;
+    __syncthreads();
+    for (int o = RXP_THREADS / 2; o > 0; o >>= 1) {
+        if (tid < o) { s_sum[tid] += s_sum[tid + o]; s_cnt[tid] += s_cnt[tid + o]; }
+        __syncthreads();
+    }
+    if (tid == 0) power[blockIdx.x] = s_cnt[0] ? s_sum[0] / (double)s_cnt[0] : nan("");
+}
+
 } // namespace
 } // namespace rfrt
 
@@ -169,6 +286,21 @@ extern "C" int rfrt_rx_power(const int64_t *d_arr_offsets, const int32_t *d_arr_
     k_stx_table<<<(unsigned)((n_bins + 255) / 256), 256, 0, stream>>>(n_bins, sample_window_s, carrier_hz, d_stx_table);
     k_rx_power<<<(unsigned)n_receivers, 256, 0, stream>>>(d_arr_offsets, d_arr_bin, d_arr_amp, n_bins, d_stx_table,
                                                           d_power);
+    RFRT_CUDA(cudaGetLastError());
+    return RFRT_OK;
+}
+
+extern "C" int rfrt_rx_power_dense(const double *d_ir, int64_t n_receivers, int64_t n_bins, double sample_window_s,
+                                   double carrier_hz, double *d_power, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_ir || n_receivers <= 0 || n_bins <= 0 || n_bins >= (1ll << 31) || !d_power) {
+        set_error("rfrt_rx_power_dense: bad arguments");
+        return RFRT_ERR_INVALID;
+    }
+    const size_t smem = sizeof(double) * 2 * (RXP_CAP + 1) + sizeof(int) * RXP_CAP;
+    RFRT_CUDA(cudaFuncSetAttribute((const void *)k_rx_power_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_rx_power_dense<<<(unsigned)n_receivers, RXP_THREADS, smem, stream>>>(d_ir, n_bins, sample_window_s, carrier_hz, d_power);
     RFRT_CUDA(cudaGetLastError());
     return RFRT_OK;
 }

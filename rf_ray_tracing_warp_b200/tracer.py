@@ -244,13 +244,67 @@ class Tracer:
                                           _stream_ptr()), "rfrt_rx_power")
         return power
 
-    def coverage(self, tx_pos, tx_power, rx_positions, rx_radius, carrier_hz=2.4e9):
+    def rx_power_dense(self, ir, carrier_hz=2.4e9):
+        """main.py:39,46-55 for every row of a dense (R, L) float64 impulse-response tensor -> (R,) tensor."""
+        with torch.cuda.device(self.device):
+            power = torch.empty(ir.shape[0], dtype=torch.float64, device=self.device)
+            check(self._lib.rfrt_rx_power_dense(_ptr(ir), ir.shape[0], ir.shape[1], float(self.sample_window_s),
+                                                float(carrier_hz), _ptr(power), _stream_ptr()), "rfrt_rx_power_dense")
+        return power
+
+    def coverage(self, tx_pos, tx_power, rx_positions, rx_radius, carrier_hz=2.4e9, dense_budget_bytes=96 << 30,
+                 ray_chunk=None):
         """coverage.py:38-57 without the per-receiver re-trace: one trace, every receiver tested per segment.
+
+        Dense mode (default when the (R, L) float64 impulse responses fit `dense_budget_bytes`): rays are traced
+        in chunks sized to the device work lists, every chunk's records are binned into the resident impulse
+        responses (atomics), ranks combine them with ONE all-reduce, and the power kernel reads the rows once.
+        Otherwise the sparse record path (sort + CSR) is used.
         Returns dict(power (R,) linear, dbm (R,), stats)."""
-        rec, n_rx = self._records(tx_pos, tx_power, rx_positions, rx_radius, False)
-        power = self.rx_power(rec, n_rx, carrier_hz)
-        p = power.cpu().numpy()
-        return dict(power=p, dbm=to_dbm(p), stats=dict(self.last_stats), records=rec)
+        centers = np.ascontiguousarray(np.asarray(rx_positions, dtype=np.float64).reshape(-1, 3))
+        n_rx = centers.shape[0]
+        L = int(self.sample_window_s * self.sample_rate_hz)
+        if n_rx * L * 8 > dense_budget_bytes or L == 0:
+            rec, n_rx = self._records(tx_pos, tx_power, centers, rx_radius, False)
+            power = self.rx_power(rec, n_rx, carrier_hz)
+            p = power.cpu().numpy()
+            return dict(power=p, dbm=to_dbm(p), stats=dict(self.last_stats), records=rec)
+        begin, end = self.ray_range
+        with torch.cuda.device(self.device):
+            ir = torch.zeros((n_rx, L), dtype=torch.float64, device=self.device)
+            job = TraceJob(self, centers, rx_radius, False, self.max_candidates, self.max_records)
+            stats = dict(segments=0, env_hits=0, candidates=0, records=0)
+            chunk = int(ray_chunk or min(max(end - begin, 1), 1 << 22))
+            try:
+                pos = begin
+                while pos < end:
+                    hi = min(end, pos + chunk)
+                    job.enqueue(tx_pos, tx_power, ray_range=(pos, hi))
+                    c = job.counters()  # one host round trip per chunk: overflow is detected BEFORE binning
+                    if c["candidates"] > job.cand_capacity or c["records"] > job.rec_capacity:
+                        if hi - pos <= 1024:
+                            job.close()
+                            job = TraceJob(self, centers, rx_radius, False, max(2 * job.cand_capacity, c["candidates"] + 1),
+                                           max(2 * job.rec_capacity, c["candidates"] + 1))
+                        else:
+                            chunk = max(1024, (hi - pos) // 2)
+                        continue
+                    job.bin_into(ir)
+                    for k in stats:
+                        stats[k] += c[k]
+                    pos = hi
+                    # grow / shrink the chunk so the work lists run ~60 % full
+                    fill = max(c["candidates"] / job.cand_capacity, c["records"] / job.rec_capacity, 1e-9)
+                    chunk = int(min(max(1024, chunk * 0.6 / fill), 1 << 26))
+            finally:
+                job.close()
+            if self._world > 1:
+                torch.distributed.all_reduce(ir)  # the one exchange step: sum of per-GPU impulse responses (NCCL)
+                stats = sharding.sum_stats(stats, self.device)
+            power = self.rx_power_dense(ir, carrier_hz)
+            p = power.cpu().numpy()
+        self.last_stats = stats
+        return dict(power=p, dbm=to_dbm(p), stats=dict(stats), impulse_response=ir)
 
     # ------------------------------------------------------------------------------------------
     def trace_paths_kernel(self, tx_pos, rx_pos, rx_radius, ray_range=None):
@@ -358,6 +412,16 @@ class TraceJob:
                                       self.counters_t.data_ptr() + 8 * _lib.CTR_RECORDS, self.n_rx, ir.shape[1], 0,
                                       _ptr(ir), _stream_ptr()), "rfrt_bin_ir")
                 self.kernel_launches += 1
+
+    def bin_into(self, ir):
+        """tracer.py:116-117 for the records of the last enqueue, ACCUMULATED into ir (R, L) with fp64 atomics
+        (shared-memory privatised when one receiver's histogram fits and there are many records)."""
+        r = self.rec
+        with torch.cuda.device(self.t.device):
+            check(self.t._lib.rfrt_bin_ir(_ptr(r["rx"]), _ptr(r["bin"]), _ptr(r["amp"]), self.rec_capacity,
+                                          self.counters_t.data_ptr() + 8 * _lib.CTR_RECORDS, self.n_rx, ir.shape[1], 0,
+                                          _ptr(ir), _stream_ptr()), "rfrt_bin_ir")
+        self.kernel_launches += 1
 
     def counters(self):
         c = self.counters_t.cpu().numpy()  # synchronises the stream

@@ -142,13 +142,18 @@ def test_multi_receiver_equals_separate_runs(torch_cuda, room_stl):
     assert total > 100 and total == rec["ray"].shape[0]
 
 
-def test_rx_power_matches_oracle(torch_cuda, room_stl):
+@pytest.mark.parametrize("mode", ["dense", "dense_chunked", "sparse"])
+def test_rx_power_matches_oracle(torch_cuda, room_stl, mode):
+    """coverage.py:45-55 per receiver: dense path (chunked trace + atomic binning + prefix-sum power kernel) and
+    sparse path (sorted records + CSR + direct-sum power kernel) against np.convolve on the oracle's IR."""
     from oracle import cpu, geometry, post
     from rf_ray_tracing_warp_b200 import Tracer, load_mesh
     n, B, tx, r = 1 << 17, 3, [10, 0, 5], 0.6
     rxs = np.array([[3.0, 6.0, 5.0], [-8.0, 8.0, 3.0], [12.0, -12.0, 14.0], [0.0, -5.0, 50.0]])
-    tr = Tracer(load_mesh(room_stl), C, 100e9, 100e-9, B, n)
-    cov = tr.coverage(tx, 1, rxs, r)
+    tr = Tracer(load_mesh(room_stl), C, 100e9, 100e-9, B, n, max_candidates=4096 if mode == "dense_chunked" else 1 << 20)
+    cov = tr.coverage(tx, 1, rxs, r, dense_budget_bytes=0 if mode == "sparse" else 1 << 34,
+                      ray_chunk=30000 if mode == "dense_chunked" else None)
+    assert cov["stats"]["records"] > 300
     soup = geometry.load_stl_soup(room_stl)
     for k, c in enumerate(rxs):
         o = cpu.trace_paths(soup, geometry.rx_soup(c, r), tx, B, 0, n, instrument=False)
