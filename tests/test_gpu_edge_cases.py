@@ -1,0 +1,138 @@
+"""GPU edge cases: empty / tiny inputs, ragged sizes, overflow handling, random meshes (BVH == brute force)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+C = 2.998e8
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device — no CPU fallback exists")
+    torch.cuda.set_device(0)
+    return torch
+
+
+def _mesh(tris):
+    from rf_ray_tracing_warp_b200 import mesh_from_triangles
+    return mesh_from_triangles(np.asarray(tris, dtype=np.float32))
+
+
+def test_empty_mesh_and_zero_rays(torch_cuda, room_stl):
+    from rf_ray_tracing_warp_b200 import Mesh, Tracer, load_mesh
+    empty = Mesh(vertices=np.zeros((0, 3)), faces=np.zeros((0, 3), dtype=np.int64))
+    tr = Tracer(empty, C, 100e9, 200e-9, 3, 1000)
+    out = tr.trace_segments([0, 0, 0], dump=True)
+    assert out["segments"] == 1000 and out["env_hits"] == 0          # every ray: one segment, then dead
+    assert (out["hit_tri"].cpu().numpy() == -1).all()
+    # a receiver in empty space still captures line-of-sight rays (kernel.py:85: `not maybe_hit_env`)
+    paths, ir = tr.compute_cir([0, 0, 0], 1, [1.0, 0, 0], 0.5)
+    assert len(paths) > 10 and all(2 <= len(p) <= 4 for p in paths)
+    # zero rays / zero bounces
+    tr0 = Tracer(load_mesh(room_stl), C, 100e9, 200e-9, 3, 0)
+    paths, ir = tr0.compute_cir([10, 0, 5], 1, [-10, 0, 5], 0.1)
+    assert paths == [] and ir.shape == (20000,) and not ir.any()
+    trb = Tracer(load_mesh(room_stl), C, 100e9, 200e-9, 0, 1000)
+    paths, ir = trb.compute_cir([10, 0, 5], 1, [-10, 0, 5], 0.1)
+    assert paths == [] and not ir.any()
+
+
+@pytest.mark.parametrize("ntri", [1, 2, 3, 5])
+def test_tiny_meshes_match_oracle(torch_cuda, ntri):
+    from oracle import cpu
+    rng = np.random.default_rng(ntri)
+    tris = rng.uniform(-2, 2, size=(ntri, 3, 3)).astype(np.float32)
+    from rf_ray_tracing_warp_b200 import Tracer
+    n, B = 50000, 4
+    tr = Tracer(_mesh(tris), C, 100e9, 200e-9, B, n)
+    out = tr.trace_segments([0.1, 0.2, 0.3], dump=True)
+    seg, tri, t = cpu.trace_env(tris, [0.1, 0.2, 0.3], B, 0, n)
+    assert out["segments"] == seg and (tri >= 0).sum() > 100
+    assert np.array_equal(out["hit_tri"].cpu().numpy(), tri)
+    assert np.array_equal(out["hit_t"].cpu().numpy().view(np.uint32), t.view(np.uint32))
+
+
+def test_random_soups_bvh_equals_brute_force(torch_cuda):
+    """Property test over random triangle soups incl. degenerate and duplicated triangles (ties -> lowest index)."""
+    from oracle import cpu
+    from rf_ray_tracing_warp_b200 import Tracer
+    rng = np.random.default_rng(99)
+    for trial in range(6):
+        ntri = int(rng.integers(8, 400))
+        tris = rng.uniform(-5, 5, size=(ntri, 3, 3)).astype(np.float32)
+        tris[: ntri // 8] = tris[ntri // 8: 2 * (ntri // 8)]          # exact duplicates: equal-t ties
+        tris[-1, 2] = tris[-1, 1]                                      # a degenerate (zero-area) triangle
+        tris[-2] = np.round(tris[-2])                                  # axis-snapped vertices
+        n, B = 20000, 5
+        tr = Tracer(_mesh(tris), C, 100e9, 200e-9, B, n)
+        out = tr.trace_segments([0.0, 0.0, 0.0], dump=True)
+        seg, tri, t = cpu.trace_env(tris, [0.0, 0.0, 0.0], B, 0, n)
+        assert out["segments"] == seg
+        assert np.array_equal(out["hit_tri"].cpu().numpy(), tri), trial
+        assert np.array_equal(out["hit_t"].cpu().numpy().view(np.uint32), t.view(np.uint32)), trial
+
+
+def test_ragged_ray_ranges_and_chunks(torch_cuda, room_stl):
+    """Results are independent of how ray ids are split into ranges / chunks (the multi-GPU invariant)."""
+    from rf_ray_tracing_warp_b200 import Tracer, load_mesh
+    mesh = load_mesh(room_stl)
+    n, B, tx, rx, r = 100003, 4, [10, 0, 5], [3.0, 6.0, 5.0], 0.7
+    whole = Tracer(mesh, C, 100e9, 200e-9, B, n)
+    paths, ir = whole.compute_cir(tx, 1, rx, r)
+    seg = whole.last_stats["segments"]
+    parts, seg_parts, ir_sum = [], 0, np.zeros_like(ir)
+    for begin, end in [(0, 1), (1, 33333), (33333, 33334), (33334, 100003)]:
+        t = Tracer(mesh, C, 100e9, 200e-9, B, n, ray_range=(begin, end), chunk_rays=7777)
+        p, i = t.compute_cir(tx, 1, rx, r)
+        parts += p
+        seg_parts += t.last_stats["segments"]
+        ir_sum += i
+    assert seg_parts == seg and len(parts) == len(paths) > 50
+    assert all(np.array_equal(a, b) for a, b in zip(parts, paths))
+    np.testing.assert_allclose(ir_sum, ir, rtol=1e-12, atol=0)
+
+
+def test_work_list_overflow_is_retried(torch_cuda, room_stl):
+    from rf_ray_tracing_warp_b200 import Tracer, load_mesh
+    mesh = load_mesh(room_stl)
+    n, B, tx, rx, r = 1 << 16, 3, [10, 0, 5], [3.0, 6.0, 5.0], 1.5
+    big = Tracer(mesh, C, 100e9, 200e-9, B, n)
+    small = Tracer(mesh, C, 100e9, 200e-9, B, n, max_candidates=16, max_records=16)
+    p1, ir1 = big.compute_cir(tx, 1, rx, r)
+    p2, ir2 = small.compute_cir(tx, 1, rx, r)
+    assert len(p1) == len(p2) > 100 and small.max_records >= len(p2)
+    assert all(np.array_equal(a, b) for a, b in zip(p1, p2)) and np.array_equal(ir1, ir2)
+
+
+def test_bad_arguments_are_rejected(torch_cuda, room_stl):
+    from rf_ray_tracing_warp_b200 import Mesh, RfrtError, Tracer, load_mesh
+    bad = Mesh(vertices=np.zeros((3, 3)), faces=np.array([[0, 1, 7]]))
+    with pytest.raises(RfrtError):
+        Tracer(bad, C, 100e9, 200e-9, 3, 10)
+    tr = Tracer(load_mesh(room_stl), C, 100e9, 200e-9, 40, 10)   # replay path supports <= 32 bounces
+    with pytest.raises(RfrtError):
+        tr.compute_cir([10, 0, 5], 1, [-10, 0, 5], 0.1)
+    with pytest.raises(RfrtError):
+        Tracer(load_mesh(room_stl), C, 100e9, 200e-9, 3, 10).compute_cir([10, 0, 5], 1, [-10, 0, 5], -1.0)
+
+
+def test_far_receiver_uses_exact_fallback(torch_cuda, almost_empty_stl):
+    """A receiver > 8192 radii away takes the all-faces branch of the receiver query.  Hits are ~1e-9 per ray, so
+    the oracle first finds the ray ids that hit the receiver's bounding sphere and replays only those."""
+    from oracle import cpu, geometry, post
+    from rf_ray_tracing_warp_b200 import Tracer, load_mesh
+    n, B, tx, rx, r = 1 << 29, 2, [0, 0, 1.0], [0, 0, 101.0], 0.012
+    tr = Tracer(load_mesh(almost_empty_stl), C, 100e9, 200e-9, B, n)
+    out = tr.compute_cir_multi(tx, 1, [rx], r, return_paths=True, dense=False)
+    rec = {k: v.cpu().numpy() for k, v in out["records"].items()}
+    soup, rxs = geometry.load_stl_soup(almost_empty_stl), geometry.rx_soup(rx, r)
+    expect = {}
+    for tid in cpu.sphere_hits(0, n, tx, rx, r * 1.0001):
+        o = cpu.trace_paths(soup, rxs, tx, B, int(tid), 1, instrument=False)
+        if o["mask"][0]:
+            expect[int(tid)] = post.clean_paths(o["received"], o["mask"])[0]
+    assert sorted(expect) == sorted(int(t) & 0xFFFFFFFF for t in rec["ray"])
+    for t, row, nv in zip(rec["ray"], rec["paths"], rec["nverts"]):
+        assert np.array_equal(row[:nv], expect[int(t) & 0xFFFFFFFF])
