@@ -53,6 +53,7 @@ enum rfrt_status {
 
 /* rfrt_trace flags */
 #define RFRT_FLAG_NONE 0u
+#define RFRT_FLAG_FORCE_BVH 2u  /* always walk the BVH (default: scenes of <= 64 triangles use the lockstep sweep) */
 #define RFRT_FLAG_DIRS_READY 1u /* d_dir_scratch already holds rfrt_ray_directions(ray_begin, ray_end): one wave */
 
 /* layout of the u64 counter block written by rfrt_trace / rfrt_trace_receive */

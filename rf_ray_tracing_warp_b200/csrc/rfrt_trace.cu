@@ -25,6 +25,7 @@ constexpr int MAX_RECV_BOUNCES = 32;
 struct TraceParams {
     const BvhNode *nodes;
     const BvhTri *tris;
+    const float *soup; // [n_tris*9] original order
     int64_t n_tris;
     // receivers
     const BvhNode *rx_nodes;
@@ -92,7 +93,7 @@ __device__ __forceinline__ void rx_filter_and_emit(const TraceParams &P, int k, 
     if ((int64_t)slot < P.cand_capacity) P.candidates[slot] = make_uint4(gid, (uint32_t)k, (uint32_t)bounce, 0u);
 }
 
-template <bool DUMP>
+template <bool DUMP, bool SMALL>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P)
 {
     extern __shared__ int s_stack_raw[];
@@ -100,6 +101,12 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
     float *stack_t = reinterpret_cast<float *>(s_stack_raw + P.stack_depth * TRACE_THREADS) + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
+    // SMALL: the whole scene (<= 64 triangles, original order) lives in shared memory behind the stacks
+    float *s_tris = reinterpret_cast<float *>(s_stack_raw + 2 * P.stack_depth * TRACE_THREADS);
+    if (SMALL) {
+        for (int i = threadIdx.x; i < 9 * (int)P.n_tris; i += TRACE_THREADS) s_tris[i] = __ldg(P.soup + i);
+        __syncthreads();
+    }
 
     bool has_ray = false;
     bool exhausted = false; // warp-uniform
@@ -135,7 +142,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
         SlabRay sr = slab_setup(pos, dir);
         Hit h;
         h.t = 1.0e6f; h.face = -1; h.slot = -1;
-        closest_hit(P.nodes, P.tris, P.n_tris, wr, sr, stack, stack_t, TRACE_THREADS, h);
+        if (SMALL) closest_hit_small(s_tris, (int)P.n_tris, wr, h);
+        else closest_hit(P.nodes, P.tris, P.n_tris, wr, sr, stack, stack_t, TRACE_THREADS, h);
         const bool hit_env = h.face >= 0;
         ++n_seg;
 
@@ -182,7 +190,12 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
             ++n_hit;
             pos = advance(pos, dir, h.t);                 // kernel.py:94
             float3 a, b, c; int idx;
-            tri_vertices(P.tris, h.slot, a, b, c, idx);
+            if (SMALL) {
+                const float *v = s_tris + 9 * h.face;
+                a = make_float3(v[0], v[1], v[2]); b = make_float3(v[3], v[4], v[5]); c = make_float3(v[6], v[7], v[8]);
+            } else {
+                tri_vertices(P.tris, h.slot, a, b, c, idx);
+            }
             dir = reflect(dir, tri_normal(a, b, c));      // kernel.py:96
             ++bounce;
             if (bounce >= P.max_bounces) has_ray = false;
@@ -426,7 +439,7 @@ k_query(LiteralEnv E, const float *__restrict__ origins, const float *__restrict
 
 int stack_depth_for(const Mesh *m, const RxSet *r)
 {
-    int d = m->bvh.max_depth;
+    int d = m ? m->bvh.max_depth : 0;
     if (r && r->bvh.max_depth > d) d = r->bvh.max_depth;
     if (r && r->unit_bvh.max_depth > d) d = r->unit_bvh.max_depth;
     d += 2;
@@ -496,7 +509,7 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     if (dirs_ready) chunk_rays = n; // the caller generated all directions with rfrt_ray_directions
 
     TraceParams P;
-    P.nodes = m->bvh.nodes; P.tris = m->tris; P.n_tris = m->bvh.n_prims;
+    P.nodes = m->bvh.nodes; P.tris = m->tris; P.soup = m->soup; P.n_tris = m->bvh.n_prims;
     P.rx_nodes = r ? r->bvh.nodes : nullptr; P.rx_order = r ? r->bvh.prim_order : nullptr;
     P.rx_verts = r ? r->verts : nullptr; P.rx_centers = r ? r->centers : nullptr;
     P.n_rx = r ? r->n_receivers : 0; P.n_unit = r ? r->n_unit : 0; P.n_faces = r ? r->n_faces : 0;
@@ -509,8 +522,12 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     P.hit_tri = d_hit_tri; P.hit_t = d_hit_t; P.dump_begin = ray_begin;
     P.stack_depth = stack_depth_for(m, r);
     const bool dump = d_hit_tri || d_hit_t;
-    const size_t smem = stack_bytes(P.stack_depth);
-    const void *kern = dump ? (const void *)k_trace_env<true> : (const void *)k_trace_env<false>;
+    // scenes of <= 64 triangles: lockstep sweep over the triangles staged in shared memory (see closest_hit_small)
+    const bool small = P.n_tris > 0 && P.n_tris <= 64 && !(flags & RFRT_FLAG_FORCE_BVH);
+    if (small) P.stack_depth = r ? stack_depth_for(nullptr, r) : 1;
+    const size_t smem = stack_bytes(P.stack_depth) + (small ? sizeof(float) * 9 * (size_t)P.n_tris : 0);
+    const void *kern = small ? (dump ? (const void *)k_trace_env<true, true> : (const void *)k_trace_env<false, true>)
+                             : (dump ? (const void *)k_trace_env<true, false> : (const void *)k_trace_env<false, false>);
     int grid = 0;
     int rc = grid_for(kern, smem, &grid);
     if (rc) return rc;
@@ -524,8 +541,13 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
         int g = grid;
         int64_t need = (cn + TRACE_THREADS - 1) / TRACE_THREADS;
         if (need < g) g = (int)need;
-        if (dump) k_trace_env<true><<<g, TRACE_THREADS, smem, stream>>>(P);
-        else k_trace_env<false><<<g, TRACE_THREADS, smem, stream>>>(P);
+        if (small) {
+            if (dump) k_trace_env<true, true><<<g, TRACE_THREADS, smem, stream>>>(P);
+            else k_trace_env<false, true><<<g, TRACE_THREADS, smem, stream>>>(P);
+        } else {
+            if (dump) k_trace_env<true, false><<<g, TRACE_THREADS, smem, stream>>>(P);
+            else k_trace_env<false, false><<<g, TRACE_THREADS, smem, stream>>>(P);
+        }
     }
     RFRT_CUDA(cudaGetLastError());
     return RFRT_OK;

@@ -47,11 +47,12 @@ class Tracer:
       chunk_rays    rays generated per wave
       max_candidates / max_records   initial capacities of the device work lists (grown on overflow)
       verbose       print the reference's progress line (tracer.py:119)
+      force_bvh     walk the BVH even for scenes of <= 64 triangles (default: lockstep sweep for those)
     """
 
     def __init__(self, environment_trimesh, light_speed_mps, sample_rate_hz, sample_window_s, max_bounces,
                  tx_num_rays, *, device=None, ray_range=None, shard=False, chunk_rays=1 << 24,
-                 max_candidates=1 << 20, max_records=1 << 20, verbose=False):
+                 max_candidates=1 << 20, max_records=1 << 20, verbose=False, force_bvh=False):
         if not torch.cuda.is_available():
             raise RfrtError("rf_ray_tracing_warp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self._lib = _lib.load()
@@ -65,6 +66,7 @@ class Tracer:
         self.max_candidates = int(max_candidates)
         self.max_records = int(max_records)
         self.verbose = verbose
+        self.trace_flags = 2 if force_bvh else 0  # RFRT_FLAG_FORCE_BVH
         self.shard = bool(shard)
         self._world, self._rank = 1, 0
         if self.shard and torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -131,7 +133,7 @@ class Tracer:
             counters = torch.zeros(_lib.CTR_COUNT, dtype=torch.int64, device=self.device)
             hit_tri = torch.full((n, B), -1, dtype=torch.int32, device=self.device) if dump else None
             hit_t = torch.zeros((n, B), dtype=torch.float32, device=self.device) if dump else None
-            check(self._lib.rfrt_trace(self._env, 0, float3(tx_pos), B, begin, end, 0, _ptr(self._scratch(n)),
+            check(self._lib.rfrt_trace(self._env, 0, float3(tx_pos), B, begin, end, self.trace_flags, _ptr(self._scratch(n)),
                                        self.chunk_rays, _ptr(counters), None, 0, _ptr(hit_tri), _ptr(hit_t),
                                        _stream_ptr()), "rfrt_trace")
             c = counters.cpu().numpy()
@@ -390,12 +392,12 @@ class TraceJob:
         with torch.cuda.device(t.device):
             self.counters_t.zero_()
             if dirs is None:
-                check(lib.rfrt_trace(t._env, self.rxset, tx, B, begin, end, 0, _ptr(t._scratch(n)), t.chunk_rays,
+                check(lib.rfrt_trace(t._env, self.rxset, tx, B, begin, end, t.trace_flags, _ptr(t._scratch(n)), t.chunk_rays,
                                      _ptr(self.counters_t), _ptr(self.cands), self.cand_capacity, None, None,
                                      _stream_ptr()), "rfrt_trace")
                 self.kernel_launches += 2 * max(1, -(-n // t.chunk_rays))
             else:
-                check(lib.rfrt_trace(t._env, self.rxset, tx, B, begin, end, 1, _ptr(dirs), n, _ptr(self.counters_t),
+                check(lib.rfrt_trace(t._env, self.rxset, tx, B, begin, end, 1 | t.trace_flags, _ptr(dirs), n, _ptr(self.counters_t),
                                      _ptr(self.cands), self.cand_capacity, None, None, _stream_ptr()), "rfrt_trace")
                 self.kernel_launches += 1
             amp0 = tx_power / t.tx_num_rays if t.tx_num_rays else 0.0  # tracer.py:103

@@ -69,13 +69,17 @@ def test_bvh_query_equals_brute_force(torch_cuda, room_stl, almost_empty_stl, sc
             assert f[i] == -1
 
 
+@pytest.mark.parametrize("force_bvh", [False, True])
 @pytest.mark.parametrize("scene,B,n,tx", [("room", 3, 1 << 18, [10, 0, 5]), ("room", 8, 1 << 16, [10, 0, 5]),
-                                           ("almost_empty", 4, 1 << 18, [1, 0, 1])])
-def test_env_trajectory_bit_exact(torch_cuda, room_stl, almost_empty_stl, scene, B, n, tx):
+                                           ("almost_empty", 4, 1 << 18, [1, 0, 1]), ("room", 3, 1 << 17, [0, 0, 0]),
+                                           ("room", 4, 1 << 16, [15, 15, 0])])
+def test_env_trajectory_bit_exact(torch_cuda, room_stl, almost_empty_stl, scene, B, n, tx, force_bvh):
+    """Hit triangle and distance per (ray, bounce) and the segment count, for both closest-hit strategies (BVH walk /
+    lockstep sweep of small scenes), incl. a transmitter ON the geometry (t == 0 hits, edge/vertex hits)."""
     from oracle import cpu, geometry
     from rf_ray_tracing_warp_b200 import load_mesh
     path = room_stl if scene == "room" else almost_empty_stl
-    tr = _tracer(load_mesh(path), B, n, chunk_rays=100_000)
+    tr = _tracer(load_mesh(path), B, n, chunk_rays=100_000, force_bvh=force_bvh)
     out = tr.trace_segments(tx, dump=True)
     seg, tri, t = cpu.trace_env(geometry.load_stl_soup(path), tx, B, 0, n)
     assert out["segments"] == seg
@@ -98,12 +102,12 @@ def test_compat_kernel_matches_reference_contract(torch_cuda, room_stl):
     assert np.array_equal(received.cpu().numpy().view(np.uint32), o["received"].view(np.uint32))
 
 
-@pytest.mark.parametrize("B", [1, 3, 6])
-def test_compute_cir_matches_oracle(torch_cuda, room_stl, B):
+@pytest.mark.parametrize("B,force_bvh", [(1, False), (3, False), (6, False), (3, True)])
+def test_compute_cir_matches_oracle(torch_cuda, room_stl, B, force_bvh):
     from oracle import cpu, geometry, post
     from rf_ray_tracing_warp_b200 import load_mesh
     n, tx, rx, r = 1 << 18, [10, 0, 5], [3.0, 6.0, 5.0], 0.5
-    tr = _tracer(load_mesh(room_stl), B, n, chunk_rays=70_000)
+    tr = _tracer(load_mesh(room_stl), B, n, chunk_rays=70_000, force_bvh=force_bvh)
     paths, ir = tr.compute_cir(tx, 1, rx, r)
     o = cpu.trace_paths(geometry.load_stl_soup(room_stl), geometry.rx_soup(rx, r), tx, B, 0, n, instrument=False)
     o_paths = post.clean_paths(o["received"], o["mask"])
