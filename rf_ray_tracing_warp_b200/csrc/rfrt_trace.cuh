@@ -143,40 +143,102 @@ __device__ __forceinline__ void closest_hit(const BvhNode *__restrict__ nodes, c
 //   phase 2 (per lane, 1-4 candidates): the full woop_hit on the candidates in ascending index order; strict
 //            `t < best` then yields the lowest index among equal t — the same rule as the BVH path.
 // ---------------------------------------------------------------------------------------------------------
+// U, V, W of one shared-memory triangle (offset o = 9*f) with the permuted components fetched through the
+// per-lane base pointers tkx/tky/tkz — the same fp32 operations, in the same order, as woop_hit.
+struct WoopUVW {
+    float U, V, W, Akz, Bkz, Ckz;
+};
+__device__ __forceinline__ WoopUVW woop_uvw_smem(const float *tkx, const float *tky, const float *tkz, int o, float pkx,
+                                                 float pky, float pkz, float Sx, float Sy)
+{
+    WoopUVW r;
+    const float Akx = __fsub_rn(tkx[o], pkx), Aky = __fsub_rn(tky[o], pky);
+    r.Akz = __fsub_rn(tkz[o], pkz);
+    const float Bkx = __fsub_rn(tkx[o + 3], pkx), Bky = __fsub_rn(tky[o + 3], pky);
+    r.Bkz = __fsub_rn(tkz[o + 3], pkz);
+    const float Ckx = __fsub_rn(tkx[o + 6], pkx), Cky = __fsub_rn(tky[o + 6], pky);
+    r.Ckz = __fsub_rn(tkz[o + 6], pkz);
+    const float Ax = __fsub_rn(Akx, __fmul_rn(Sx, r.Akz));
+    const float Ay = __fsub_rn(Aky, __fmul_rn(Sy, r.Akz));
+    const float Bx = __fsub_rn(Bkx, __fmul_rn(Sx, r.Bkz));
+    const float By = __fsub_rn(Bky, __fmul_rn(Sy, r.Bkz));
+    const float Cx = __fsub_rn(Ckx, __fmul_rn(Sx, r.Ckz));
+    const float Cy = __fsub_rn(Cky, __fmul_rn(Sy, r.Ckz));
+    r.U = diff_product(Cx, By, Cy, Bx);
+    r.V = diff_product(Ax, Cy, Ay, Cx);
+    r.W = diff_product(Bx, Ay, By, Ax);
+    if (r.U == 0.0f || r.V == 0.0f || r.W == 0.0f) {
+        // fp64 fallback of intersect_ray_tri_woop (rare: edge / vertex hits)
+        r.U = __double2float_rn(__dsub_rn(__dmul_rn((double)Cx, (double)By), __dmul_rn((double)Cy, (double)Bx)));
+        r.V = __double2float_rn(__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx)));
+        r.W = __double2float_rn(__dsub_rn(__dmul_rn((double)Bx, (double)Ay), __dmul_rn((double)By, (double)Ax)));
+    }
+    return r;
+}
+
+// sign bit set  <=>  U, V, W have mixed signs (for non-zero, non-NaN values)
+__device__ __forceinline__ bool uvw_candidate(float U, float V, float W)
+{
+    const unsigned u = __float_as_uint(U), v = __float_as_uint(V), w = __float_as_uint(W);
+    const unsigned mixed = (u | v | w) & ~(u & v & w);                                  // one LOP3
+    const bool all_nonzero = fminf(fminf(fabsf(U), fabsf(V)), fabsf(W)) > 0.0f;         // false for 0 and NaN
+    return !all_nonzero || (int)mixed >= 0;
+}
+
 __device__ __forceinline__ void closest_hit_small(const float *s_tris, int n_tris, const WoopRay &wr, Hit &h)
 {
     const float *tkx = s_tris + wr.kx, *tky = s_tris + wr.ky, *tkz = s_tris + wr.kz;
     const float pkx = sel3(wr.px, wr.py, wr.pz, wr.kx), pky = sel3(wr.px, wr.py, wr.pz, wr.ky),
                 pkz = sel3(wr.px, wr.py, wr.pz, wr.kz);
-    unsigned long long cand = 0ull;
+    // ---- phase 1: lockstep sweep, candidates collected in two 32-bit masks with a walking bit --------------
+    unsigned cand_lo = 0u, cand_hi = 0u;
+    {
+        const int n_lo = n_tris < 32 ? n_tris : 32;
+        unsigned bit = 1u;
 #pragma unroll 4
-    for (int f = 0; f < n_tris; ++f) {
-        const int o = 9 * f;
-        const float Akx = __fsub_rn(tkx[o], pkx), Aky = __fsub_rn(tky[o], pky), Akz = __fsub_rn(tkz[o], pkz);
-        const float Bkx = __fsub_rn(tkx[o + 3], pkx), Bky = __fsub_rn(tky[o + 3], pky), Bkz = __fsub_rn(tkz[o + 3], pkz);
-        const float Ckx = __fsub_rn(tkx[o + 6], pkx), Cky = __fsub_rn(tky[o + 6], pky), Ckz = __fsub_rn(tkz[o + 6], pkz);
-        const float Ax = __fsub_rn(Akx, __fmul_rn(wr.Sx, Akz));
-        const float Ay = __fsub_rn(Aky, __fmul_rn(wr.Sy, Akz));
-        const float Bx = __fsub_rn(Bkx, __fmul_rn(wr.Sx, Bkz));
-        const float By = __fsub_rn(Bky, __fmul_rn(wr.Sy, Bkz));
-        const float Cx = __fsub_rn(Ckx, __fmul_rn(wr.Sx, Ckz));
-        const float Cy = __fsub_rn(Cky, __fmul_rn(wr.Sy, Ckz));
-        const float U = diff_product(Cx, By, Cy, Bx);
-        const float V = diff_product(Ax, Cy, Ay, Cx);
-        const float W = diff_product(Bx, Ay, By, Ax);
-        const bool all_nonzero = fabsf(U) > 0.0f && fabsf(V) > 0.0f && fabsf(W) > 0.0f; // false for 0 and NaN
-        const bool mixed = fminf(fminf(U, V), W) < 0.0f && fmaxf(fmaxf(U, V), W) > 0.0f;
-        if (!all_nonzero || !mixed) cand |= 1ull << f;
-    }
-    while (cand) {
-        const int f = __ffsll((long long)cand) - 1;
-        cand &= cand - 1ull;
-        const float *v = s_tris + 9 * f;
-        float t;
-        if (woop_hit(wr, make_float3(v[0], v[1], v[2]), make_float3(v[3], v[4], v[5]), make_float3(v[6], v[7], v[8]), t) &&
-            t >= 0.0f && t < h.t) {
-            h.t = t; h.face = f; h.slot = f;
+        for (int f = 0; f < n_lo; ++f) {
+            const int o = 9 * f;
+            const float Akx = __fsub_rn(tkx[o], pkx), Aky = __fsub_rn(tky[o], pky), Akz = __fsub_rn(tkz[o], pkz);
+            const float Bkx = __fsub_rn(tkx[o + 3], pkx), Bky = __fsub_rn(tky[o + 3], pky), Bkz = __fsub_rn(tkz[o + 3], pkz);
+            const float Ckx = __fsub_rn(tkx[o + 6], pkx), Cky = __fsub_rn(tky[o + 6], pky), Ckz = __fsub_rn(tkz[o + 6], pkz);
+            const float Ax = __fsub_rn(Akx, __fmul_rn(wr.Sx, Akz)), Ay = __fsub_rn(Aky, __fmul_rn(wr.Sy, Akz));
+            const float Bx = __fsub_rn(Bkx, __fmul_rn(wr.Sx, Bkz)), By = __fsub_rn(Bky, __fmul_rn(wr.Sy, Bkz));
+            const float Cx = __fsub_rn(Ckx, __fmul_rn(wr.Sx, Ckz)), Cy = __fsub_rn(Cky, __fmul_rn(wr.Sy, Ckz));
+            if (uvw_candidate(diff_product(Cx, By, Cy, Bx), diff_product(Ax, Cy, Ay, Cx), diff_product(Bx, Ay, By, Ax)))
+                cand_lo |= bit;
+            bit <<= 1;
         }
+        bit = 1u;
+#pragma unroll 4
+        for (int f = 32; f < n_tris; ++f) {
+            const int o = 9 * f;
+            const float Akx = __fsub_rn(tkx[o], pkx), Aky = __fsub_rn(tky[o], pky), Akz = __fsub_rn(tkz[o], pkz);
+            const float Bkx = __fsub_rn(tkx[o + 3], pkx), Bky = __fsub_rn(tky[o + 3], pky), Bkz = __fsub_rn(tkz[o + 3], pkz);
+            const float Ckx = __fsub_rn(tkx[o + 6], pkx), Cky = __fsub_rn(tky[o + 6], pky), Ckz = __fsub_rn(tkz[o + 6], pkz);
+            const float Ax = __fsub_rn(Akx, __fmul_rn(wr.Sx, Akz)), Ay = __fsub_rn(Aky, __fmul_rn(wr.Sy, Akz));
+            const float Bx = __fsub_rn(Bkx, __fmul_rn(wr.Sx, Bkz)), By = __fsub_rn(Bky, __fmul_rn(wr.Sy, Bkz));
+            const float Cx = __fsub_rn(Ckx, __fmul_rn(wr.Sx, Ckz)), Cy = __fsub_rn(Cky, __fmul_rn(wr.Sy, Ckz));
+            if (uvw_candidate(diff_product(Cx, By, Cy, Bx), diff_product(Ax, Cy, Ay, Cx), diff_product(Bx, Ay, By, Ax)))
+                cand_hi |= bit;
+            bit <<= 1;
+        }
+    }
+    // ---- phase 2: the full test on this lane's candidates, ascending index ----------------------------------
+    while (cand_lo | cand_hi) {
+        int f;
+        if (cand_lo) { f = __ffs((int)cand_lo) - 1; cand_lo &= cand_lo - 1u; }
+        else { f = 32 + __ffs((int)cand_hi) - 1; cand_hi &= cand_hi - 1u; }
+        const WoopUVW q = woop_uvw_smem(tkx, tky, tkz, 9 * f, pkx, pky, pkz, wr.Sx, wr.Sy);
+        const float U = q.U, V = q.V, W = q.W;
+        if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) continue;
+        const float det = __fadd_rn(__fadd_rn(U, V), W);
+        if (det == 0.0f) continue;
+        const float Az = __fmul_rn(wr.Sz, q.Akz), Bz = __fmul_rn(wr.Sz, q.Bkz), Cz = __fmul_rn(wr.Sz, q.Ckz);
+        const float T = __fadd_rn(__fadd_rn(__fmul_rn(U, Az), __fmul_rn(V, Bz)), __fmul_rn(W, Cz));
+        const float x = __uint_as_float(__float_as_uint(T) ^ (__float_as_uint(det) & 0x80000000u));
+        if (x < 0.0f) continue;
+        const float t = __fmul_rn(T, __fdiv_rn(1.0f, det));
+        if (t >= 0.0f && t < h.t) { h.t = t; h.face = f; h.slot = f; }
     }
 }
 
