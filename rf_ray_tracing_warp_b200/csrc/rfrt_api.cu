@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "rfrt_internal.h"
+#include "rfrt_math.cuh"
 
 namespace rfrt {
 
@@ -46,13 +47,18 @@ __global__ void k_tri_boxes(const float *__restrict__ verts, int64_t n_verts, co
     hi[i] = make_float4(fmaxf(fmaxf(v[0], v[3]), v[6]), fmaxf(fmaxf(v[1], v[4]), v[7]), fmaxf(fmaxf(v[2], v[5]), v[8]), 0.f);
 }
 
+// Also precomputes each triangle's reflection normal (kernel.py:82,96: the normal mesh_query_ray returns) with the
+// very same operation sequence the trace would use — it does not depend on the ray, so it is hoisted to build time.
 __global__ void k_pack_tris(const float *__restrict__ soup, const int32_t *__restrict__ order, int64_t n,
-                            BvhTri *__restrict__ tris)
+                            BvhTri *__restrict__ tris, float4 *__restrict__ normals, float *__restrict__ face_normals)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= n) return;
     int32_t f = order[s];
     const float *v = soup + 9 * (int64_t)f;
+    float3 nrm = tri_normal(make_float3(v[0], v[1], v[2]), make_float3(v[3], v[4], v[5]), make_float3(v[6], v[7], v[8]));
+    normals[s] = make_float4(nrm.x, nrm.y, nrm.z, 0.f);
+    face_normals[3 * (int64_t)f] = nrm.x; face_normals[3 * (int64_t)f + 1] = nrm.y; face_normals[3 * (int64_t)f + 2] = nrm.z;
     BvhTri t;
     t.v0 = make_float4(v[0], v[1], v[2], v[3]);
     t.v1 = make_float4(v[4], v[5], v[6], v[7]);
@@ -156,7 +162,9 @@ extern "C" int rfrt_mesh_create(const float *d_vertices_xyz, int64_t n_vertices,
         int rc = build_lbvh(lo, hi, n_triangles, stream, &m->bvh);
         if (rc) { cudaFree(lo); cudaFree(hi); cudaFree(bad); cudaFree(m->soup); return rc; }
         RFRT_CUDA(cudaMalloc(&m->tris, sizeof(BvhTri) * n_triangles));
-        k_pack_tris<<<nb, T, 0, stream>>>(m->soup, m->bvh.prim_order, n_triangles, m->tris);
+        RFRT_CUDA(cudaMalloc(&m->normals, sizeof(float4) * n_triangles));
+        RFRT_CUDA(cudaMalloc(&m->face_normals, sizeof(float) * 3 * n_triangles));
+        k_pack_tris<<<nb, T, 0, stream>>>(m->soup, m->bvh.prim_order, n_triangles, m->tris, m->normals, m->face_normals);
         RFRT_CUDA(cudaGetLastError());
         RFRT_CUDA(cudaEventRecord(e1, stream));
         RFRT_CUDA(cudaStreamSynchronize(stream));
@@ -185,6 +193,8 @@ extern "C" int rfrt_mesh_destroy(rfrt_handle mesh)
     free_bvh(&m->bvh);
     if (m->tris) cudaFree(m->tris);
     if (m->soup) cudaFree(m->soup);
+    if (m->normals) cudaFree(m->normals);
+    if (m->face_normals) cudaFree(m->face_normals);
     delete m;
     return RFRT_OK;
 }

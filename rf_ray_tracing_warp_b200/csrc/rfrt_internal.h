@@ -40,7 +40,9 @@ struct Bvh {
 struct Mesh {
     Bvh bvh;
     BvhTri *tris = nullptr;      // sorted order, for traversal
-    float *soup = nullptr;       // [n*9] original order (a,b,c) for normals / literal replay
+    float *soup = nullptr;       // [n*9] original order (a,b,c)
+    float4 *normals = nullptr;   // [n] sorted order: normalize(cross(b-a, c-a)) precomputed with the trace's own ops
+    float *face_normals = nullptr; // [n*3] original order
     float build_ms = 0.0f;
 };
 

@@ -25,7 +25,9 @@ constexpr int MAX_RECV_BOUNCES = 32;
 struct TraceParams {
     const BvhNode *nodes;
     const BvhTri *tris;
-    const float *soup; // [n_tris*9] original order
+    const float4 *normals;      // [n_tris] sorted order
+    const float *soup;          // [n_tris*9] original order
+    const float *face_normals;  // [n_tris*3] original order
     int64_t n_tris;
     // receivers
     const BvhNode *rx_nodes;
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
     float *s_tris = reinterpret_cast<float *>(s_stack_raw + 2 * P.stack_depth * TRACE_THREADS);
     if (SMALL) {
         for (int i = threadIdx.x; i < 9 * (int)P.n_tris; i += TRACE_THREADS) s_tris[i] = __ldg(P.soup + i);
+        for (int i = threadIdx.x; i < 3 * (int)P.n_tris; i += TRACE_THREADS) s_tris[9 * (int)P.n_tris + i] = __ldg(P.face_normals + i);
         __syncthreads();
     }
 
@@ -189,14 +192,15 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
         if (hit_env) {
             ++n_hit;
             pos = advance(pos, dir, h.t);                 // kernel.py:94
-            float3 a, b, c; int idx;
+            float3 nrm; // normalize(cross(b-a, c-a)) of the hit triangle, precomputed at build time
             if (SMALL) {
-                const float *v = s_tris + 9 * h.face;
-                a = make_float3(v[0], v[1], v[2]); b = make_float3(v[3], v[4], v[5]); c = make_float3(v[6], v[7], v[8]);
+                const float *v = s_tris + 9 * (int)P.n_tris + 3 * h.face;
+                nrm = make_float3(v[0], v[1], v[2]);
             } else {
-                tri_vertices(P.tris, h.slot, a, b, c, idx);
+                float4 n4 = __ldg(P.normals + h.slot);
+                nrm = make_float3(n4.x, n4.y, n4.z);
             }
-            dir = reflect(dir, tri_normal(a, b, c));      // kernel.py:96
+            dir = reflect(dir, nrm);                      // kernel.py:96
             ++bounce;
             if (bounce >= P.max_bounces) has_ray = false;
         } else {
@@ -510,6 +514,7 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
 
     TraceParams P;
     P.nodes = m->bvh.nodes; P.tris = m->tris; P.soup = m->soup; P.n_tris = m->bvh.n_prims;
+    P.normals = m->normals; P.face_normals = m->face_normals;
     P.rx_nodes = r ? r->bvh.nodes : nullptr; P.rx_order = r ? r->bvh.prim_order : nullptr;
     P.rx_verts = r ? r->verts : nullptr; P.rx_centers = r ? r->centers : nullptr;
     P.n_rx = r ? r->n_receivers : 0; P.n_unit = r ? r->n_unit : 0; P.n_faces = r ? r->n_faces : 0;
@@ -525,7 +530,7 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     // scenes of <= 64 triangles: lockstep sweep over the triangles staged in shared memory (see closest_hit_small)
     const bool small = P.n_tris > 0 && P.n_tris <= 64 && !(flags & RFRT_FLAG_FORCE_BVH);
     if (small) P.stack_depth = r ? stack_depth_for(nullptr, r) : 1;
-    const size_t smem = stack_bytes(P.stack_depth) + (small ? sizeof(float) * 9 * (size_t)P.n_tris : 0);
+    const size_t smem = stack_bytes(P.stack_depth) + (small ? sizeof(float) * 12 * (size_t)P.n_tris : 0);
     const void *kern = small ? (dump ? (const void *)k_trace_env<true, true> : (const void *)k_trace_env<false, true>)
                              : (dump ? (const void *)k_trace_env<true, false> : (const void *)k_trace_env<false, false>);
     int grid = 0;
