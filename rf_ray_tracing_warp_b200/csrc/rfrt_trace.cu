@@ -95,12 +95,17 @@ __device__ __forceinline__ void rx_filter_and_emit(const TraceParams &P, int k, 
     if ((int64_t)slot < P.cand_capacity) P.candidates[slot] = make_uint4(gid, (uint32_t)k, (uint32_t)bounce, 0u);
 }
 
-template <bool DUMP, bool SMALL>
+// LSTACK: deep trees (big meshes) keep the traversal stack in per-thread local memory (L1-cached) instead of
+// shared memory, whose depth x 1 KiB per CTA would otherwise cap the occupancy of this latency-bound case.
+template <bool DUMP, bool SMALL, bool LSTACK>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P)
 {
     extern __shared__ int s_stack_raw[];
-    int *stack = s_stack_raw + threadIdx.x;
-    float *stack_t = reinterpret_cast<float *>(s_stack_raw + P.stack_depth * TRACE_THREADS) + threadIdx.x;
+    int l_stack[LSTACK ? 64 : 1];
+    float l_stack_t[LSTACK ? 64 : 1];
+    int *stack = LSTACK ? l_stack : s_stack_raw + threadIdx.x;
+    float *stack_t = LSTACK ? l_stack_t : reinterpret_cast<float *>(s_stack_raw + P.stack_depth * TRACE_THREADS) + threadIdx.x;
+    constexpr int STRIDE = LSTACK ? 1 : TRACE_THREADS;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     // SMALL: the whole scene (<= 64 triangles, original order) lives in shared memory behind the stacks
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
         Hit h;
         h.t = 1.0e6f; h.face = -1; h.slot = -1;
         if (SMALL) closest_hit_small(s_tris, (int)P.n_tris, wr, h);
-        else closest_hit(P.nodes, P.tris, P.n_tris, wr, sr, stack, stack_t, TRACE_THREADS, h);
+        else closest_hit(P.nodes, P.tris, P.n_tris, wr, sr, stack, stack_t, STRIDE, h);
         const bool hit_env = h.face >= 0;
         ++n_seg;
 
@@ -171,14 +176,14 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
                     if (c1 == c0) h1 = false;
                     if (h0) {
                         if (c0 < 0) rx_filter_and_emit(P, __ldg(P.rx_order + (~c0)), pos, dir, t_limit, gid, bounce);
-                        else { stack[sp * TRACE_THREADS] = c0; ++sp; }
+                        else { stack[sp * STRIDE] = c0; ++sp; }
                     }
                     if (h1) {
                         if (c1 < 0) rx_filter_and_emit(P, __ldg(P.rx_order + (~c1)), pos, dir, t_limit, gid, bounce);
-                        else { stack[sp * TRACE_THREADS] = c1; ++sp; }
+                        else { stack[sp * STRIDE] = c1; ++sp; }
                     }
                     node = -1;
-                    if (sp > 0) { --sp; node = stack[sp * TRACE_THREADS]; }
+                    if (sp > 0) { --sp; node = stack[sp * STRIDE]; }
                 }
             }
         }
@@ -530,9 +535,13 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     // scenes of <= 64 triangles: lockstep sweep over the triangles staged in shared memory (see closest_hit_small)
     const bool small = P.n_tris > 0 && P.n_tris <= 64 && !(flags & RFRT_FLAG_FORCE_BVH);
     if (small) P.stack_depth = r ? stack_depth_for(nullptr, r) : 1;
+    const bool lstack = !small && P.stack_depth > 16; // deep tree: local-memory stack (<= 64 entries by construction)
+    if (lstack && P.stack_depth > 64) { set_error("rfrt_trace: BVH deeper than 64 levels"); return RFRT_ERR_INVALID; }
+    if (lstack) P.stack_depth = 0;
     const size_t smem = stack_bytes(P.stack_depth) + (small ? sizeof(float) * 12 * (size_t)P.n_tris : 0);
-    const void *kern = small ? (dump ? (const void *)k_trace_env<true, true> : (const void *)k_trace_env<false, true>)
-                             : (dump ? (const void *)k_trace_env<true, false> : (const void *)k_trace_env<false, false>);
+    const void *kern = small    ? (dump ? (const void *)k_trace_env<true, true, false> : (const void *)k_trace_env<false, true, false>)
+                       : lstack ? (dump ? (const void *)k_trace_env<true, false, true> : (const void *)k_trace_env<false, false, true>)
+                                : (dump ? (const void *)k_trace_env<true, false, false> : (const void *)k_trace_env<false, false, false>);
     int grid = 0;
     int rc = grid_for(kern, smem, &grid);
     if (rc) return rc;
@@ -547,11 +556,14 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
         int64_t need = (cn + TRACE_THREADS - 1) / TRACE_THREADS;
         if (need < g) g = (int)need;
         if (small) {
-            if (dump) k_trace_env<true, true><<<g, TRACE_THREADS, smem, stream>>>(P);
-            else k_trace_env<false, true><<<g, TRACE_THREADS, smem, stream>>>(P);
+            if (dump) k_trace_env<true, true, false><<<g, TRACE_THREADS, smem, stream>>>(P);
+            else k_trace_env<false, true, false><<<g, TRACE_THREADS, smem, stream>>>(P);
+        } else if (lstack) {
+            if (dump) k_trace_env<true, false, true><<<g, TRACE_THREADS, smem, stream>>>(P);
+            else k_trace_env<false, false, true><<<g, TRACE_THREADS, smem, stream>>>(P);
         } else {
-            if (dump) k_trace_env<true, false><<<g, TRACE_THREADS, smem, stream>>>(P);
-            else k_trace_env<false, false><<<g, TRACE_THREADS, smem, stream>>>(P);
+            if (dump) k_trace_env<true, false, false><<<g, TRACE_THREADS, smem, stream>>>(P);
+            else k_trace_env<false, false, false><<<g, TRACE_THREADS, smem, stream>>>(P);
         }
     }
     RFRT_CUDA(cudaGetLastError());

@@ -88,6 +88,31 @@ def test_env_trajectory_bit_exact(torch_cuda, room_stl, almost_empty_stl, scene,
     assert out["env_hits"] == int((tri >= 0).sum())
 
 
+def test_terrain_trajectory_bit_exact(torch_cuda):
+    """Deep-tree path (local-memory stack) on the synthetic terrain that stands in for the missing apollo STL:
+    hit triangle / distance per (ray, bounce) == oracle (the oracle's own BVH == its brute force, tested on CPU)."""
+    from oracle import cpu
+    from rf_ray_tracing_warp_b200 import synthetic_terrain
+    mesh = synthetic_terrain(96, 20.0, 17)
+    soup = mesh.triangles.astype(np.float32)
+    n, B, tx = 1 << 17, 6, [10, 0, 4.5]
+    tr = _tracer(mesh, B, n)
+    assert tr.mesh_info()["max_depth"] > 16
+    out = tr.trace_segments(tx, dump=True)
+    seg, tri, t = cpu.trace_env(soup, tx, B, 0, n, bvh=cpu.Bvh(soup))
+    assert out["segments"] == seg and (tri[:, 1] >= 0).sum() > 100
+    assert np.array_equal(out["hit_tri"].cpu().numpy(), tri)
+    assert np.array_equal(out["hit_t"].cpu().numpy().view(np.uint32), t.view(np.uint32))
+    # and with receivers over the terrain (replay kernel on a deep tree)
+    from oracle import geometry, post
+    rx, r = [0.0, 0.0, 3.0], 1.0
+    paths, ir = tr.compute_cir(tx, 1, rx, r)
+    o = cpu.trace_paths(soup, geometry.rx_soup(rx, r), tx, B, 0, n, instrument=False, bvh=cpu.Bvh(soup))
+    o_paths = post.clean_paths(o["received"], o["mask"])
+    assert len(paths) == len(o_paths) > 50
+    assert all(np.array_equal(a, b) for a, b in zip(paths, o_paths))
+
+
 def test_compat_kernel_matches_reference_contract(torch_cuda, room_stl):
     """The dense 7-argument launch (tracer.py:75-79): traced/received/row_mask identical to the oracle."""
     from oracle import cpu, geometry
