@@ -360,11 +360,15 @@ struct ReceiveParams {
     int32_t stack_depth;
 };
 
+template <bool LSTACK>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_receive(const ReceiveParams P)
 {
     extern __shared__ int s_stack_raw[];
-    int *stack = s_stack_raw + threadIdx.x;
-    float *stack_t = reinterpret_cast<float *>(s_stack_raw + P.stack_depth * TRACE_THREADS) + threadIdx.x;
+    int l_stack[LSTACK ? 64 : 1];
+    float l_stack_t[LSTACK ? 64 : 1];
+    int *stack = LSTACK ? l_stack : s_stack_raw + threadIdx.x;
+    float *stack_t = LSTACK ? l_stack_t : reinterpret_cast<float *>(s_stack_raw + P.stack_depth * TRACE_THREADS) + threadIdx.x;
+    constexpr int STRIDE = LSTACK ? 1 : TRACE_THREADS;
     int64_t n_cand = (int64_t)P.counters[RFRT_CTR_CANDIDATES];
     if (n_cand > P.cand_capacity) n_cand = P.cand_capacity;
     const int row = 3 * (P.max_bounces + 1);
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_receive(const ReceivePa
         rx.unit_nodes = P.unit_nodes; rx.unit_order = P.unit_order;
         rx.cx = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y); rx.cy = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y + 1);
         rx.cz = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y + 2); rx.inv_r = P.inv_r;
-        literal_trace(P.env, &rx, P.n_faces, P.tx, P.max_bounces, cand.x, stack, stack_t, TRACE_THREADS, sink);
+        literal_trace(P.env, &rx, P.n_faces, P.tx, P.max_bounces, cand.x, stack, stack_t, STRIDE, sink);
         // a candidate raised at a later bounce than the replay's first receiver hit is a duplicate
         if (sink.last_rx_bounce < 0 || sink.first_rx_bounce != (int)cand.z) continue;
         int nverts = sink.last_rx_bounce + 2;
@@ -603,13 +607,17 @@ extern "C" int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const
     P.rec_ray = d_rec_ray; P.rec_rx = d_rec_rx; P.rec_nverts = d_rec_nverts; P.rec_bin = d_rec_bin;
     P.rec_amp = d_rec_amp; P.rec_dist = d_rec_dist; P.rec_paths = d_rec_paths; P.rec_capacity = rec_capacity;
     P.stack_depth = stack_depth_for(m, r);
+    const bool lstack = P.stack_depth > 16;
+    if (lstack && P.stack_depth > 64) { set_error("rfrt_trace_receive: BVH deeper than 64 levels"); return RFRT_ERR_INVALID; }
+    if (lstack) P.stack_depth = 0;
     const size_t smem = stack_bytes(P.stack_depth);
     int grid = 0;
-    int rc = grid_for((const void *)k_trace_receive, smem, &grid);
+    int rc = grid_for(lstack ? (const void *)k_trace_receive<true> : (const void *)k_trace_receive<false>, smem, &grid);
     if (rc) return rc;
     rc = upload_faces(r, stream);
     if (rc) return rc;
-    k_trace_receive<<<grid, TRACE_THREADS, smem, stream>>>(P);
+    if (lstack) k_trace_receive<true><<<grid, TRACE_THREADS, smem, stream>>>(P);
+    else k_trace_receive<false><<<grid, TRACE_THREADS, smem, stream>>>(P);
     RFRT_CUDA(cudaGetLastError());
     return RFRT_OK;
 }

@@ -179,8 +179,9 @@ __device__ __forceinline__ WoopUVW woop_uvw_smem(const float *tkx, const float *
 // sign bit set  <=>  U, V, W have mixed signs (for non-zero, non-NaN values)
 __device__ __forceinline__ bool uvw_candidate(float U, float V, float W)
 {
-    const unsigned u = __float_as_uint(U), v = __float_as_uint(V), w = __float_as_uint(W);
-    const unsigned mixed = (u | v | w) & ~(u & v & w);                                  // one LOP3
+    unsigned mixed;
+    asm("lop3.b32 %0, %1, %2, %3, 0x7e;" // (u|v|w) & ~(u&v&w) in one instruction
+        : "=r"(mixed) : "r"(__float_as_uint(U)), "r"(__float_as_uint(V)), "r"(__float_as_uint(W)));
     const bool all_nonzero = fminf(fminf(fabsf(U), fabsf(V)), fabsf(W)) > 0.0f;         // false for 0 and NaN
     return !all_nonzero || (int)mixed >= 0;
 }
@@ -191,10 +192,10 @@ __device__ __forceinline__ void closest_hit_small(const float *s_tris, int n_tri
     const float pkx = sel3(wr.px, wr.py, wr.pz, wr.kx), pky = sel3(wr.px, wr.py, wr.pz, wr.ky),
                 pkz = sel3(wr.px, wr.py, wr.pz, wr.kz);
     // ---- phase 1: lockstep sweep, candidates collected in two 32-bit masks with a walking bit --------------
+    // (bits are shifted in, so triangle f of a group of n sits at bit n-1-f: phase 2 walks from the top bit down)
     unsigned cand_lo = 0u, cand_hi = 0u;
+    const int n_lo = n_tris < 32 ? n_tris : 32, n_hi = n_tris - n_lo;
     {
-        const int n_lo = n_tris < 32 ? n_tris : 32;
-        unsigned bit = 1u;
 #pragma unroll 4
         for (int f = 0; f < n_lo; ++f) {
             const int o = 9 * f;
@@ -204,11 +205,9 @@ __device__ __forceinline__ void closest_hit_small(const float *s_tris, int n_tri
             const float Ax = __fsub_rn(Akx, __fmul_rn(wr.Sx, Akz)), Ay = __fsub_rn(Aky, __fmul_rn(wr.Sy, Akz));
             const float Bx = __fsub_rn(Bkx, __fmul_rn(wr.Sx, Bkz)), By = __fsub_rn(Bky, __fmul_rn(wr.Sy, Bkz));
             const float Cx = __fsub_rn(Ckx, __fmul_rn(wr.Sx, Ckz)), Cy = __fsub_rn(Cky, __fmul_rn(wr.Sy, Ckz));
-            if (uvw_candidate(diff_product(Cx, By, Cy, Bx), diff_product(Ax, Cy, Ay, Cx), diff_product(Bx, Ay, By, Ax)))
-                cand_lo |= bit;
-            bit <<= 1;
+            cand_lo = cand_lo + cand_lo +
+                      (uvw_candidate(diff_product(Cx, By, Cy, Bx), diff_product(Ax, Cy, Ay, Cx), diff_product(Bx, Ay, By, Ax)) ? 1u : 0u);
         }
-        bit = 1u;
 #pragma unroll 4
         for (int f = 32; f < n_tris; ++f) {
             const int o = 9 * f;
@@ -218,16 +217,15 @@ __device__ __forceinline__ void closest_hit_small(const float *s_tris, int n_tri
             const float Ax = __fsub_rn(Akx, __fmul_rn(wr.Sx, Akz)), Ay = __fsub_rn(Aky, __fmul_rn(wr.Sy, Akz));
             const float Bx = __fsub_rn(Bkx, __fmul_rn(wr.Sx, Bkz)), By = __fsub_rn(Bky, __fmul_rn(wr.Sy, Bkz));
             const float Cx = __fsub_rn(Ckx, __fmul_rn(wr.Sx, Ckz)), Cy = __fsub_rn(Cky, __fmul_rn(wr.Sy, Ckz));
-            if (uvw_candidate(diff_product(Cx, By, Cy, Bx), diff_product(Ax, Cy, Ay, Cx), diff_product(Bx, Ay, By, Ax)))
-                cand_hi |= bit;
-            bit <<= 1;
+            cand_hi = cand_hi + cand_hi +
+                      (uvw_candidate(diff_product(Cx, By, Cy, Bx), diff_product(Ax, Cy, Ay, Cx), diff_product(Bx, Ay, By, Ax)) ? 1u : 0u);
         }
     }
     // ---- phase 2: the full test on this lane's candidates, ascending index ----------------------------------
     while (cand_lo | cand_hi) {
         int f;
-        if (cand_lo) { f = __ffs((int)cand_lo) - 1; cand_lo &= cand_lo - 1u; }
-        else { f = 32 + __ffs((int)cand_hi) - 1; cand_hi &= cand_hi - 1u; }
+        if (cand_lo) { const int b = 31 - __clz((int)cand_lo); cand_lo ^= 1u << b; f = n_lo - 1 - b; }
+        else { const int b = 31 - __clz((int)cand_hi); cand_hi ^= 1u << b; f = 32 + n_hi - 1 - b; }
         const WoopUVW q = woop_uvw_smem(tkx, tky, tkz, 9 * f, pkx, pky, pkz, wr.Sx, wr.Sy);
         const float U = q.U, V = q.V, W = q.W;
         if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) continue;
