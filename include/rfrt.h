@@ -55,6 +55,9 @@ enum rfrt_status {
 #define RFRT_FLAG_NONE 0u
 #define RFRT_FLAG_FORCE_BVH 2u  /* always walk the BVH (default: scenes of <= 64 triangles use the lockstep sweep) */
 #define RFRT_FLAG_DIRS_READY 1u /* d_dir_scratch already holds rfrt_ray_directions(ray_begin, ray_end): one wave */
+#define RFRT_FLAG_CHECKSUM 8u   /* also accumulate RFRT_CTR_CHECKSUM (costs a few instructions per segment) */
+
+#define RFRT_SMALL_MAX_TRIS 64  /* scenes that fit this many filter slots take the lockstep sweep instead of the BVH walk */
 
 /* layout of the u64 counter block written by rfrt_trace / rfrt_trace_receive */
 #define RFRT_CTR_SEGMENTS 0    /* traced ray segments (alive bounce iterations), SURVEY.md 8d */
@@ -63,6 +66,8 @@ enum rfrt_status {
 #define RFRT_CTR_ENV_HITS 3    /* environment hits among the segments */
 #define RFRT_CTR_NEXT_RAY 4    /* internal: persistent-kernel ray fetch cursor */
 #define RFRT_CTR_NEXT_CAND 5   /* internal: candidate fetch cursor */
+#define RFRT_CTR_CHECKSUM 6    /* with RFRT_FLAG_CHECKSUM: sum over segments of hash(ray id, bounce, hit triangle, bits of t)
+                                  (mod 2^64; order-independent, so it compares whole runs of different kernels / GPU counts) */
 #define RFRT_CTR_COUNT 8
 
 RFRT_API int rfrt_version(void);
@@ -88,6 +93,15 @@ RFRT_API int rfrt_mesh_info(rfrt_handle mesh, int64_t *n_triangles, int64_t *n_n
  *   d_nodes      : [n_nodes*16] float32 (64-byte nodes)  or NULL
  *   d_tri_order  : [n_triangles] int32 — triangle index stored at each sorted slot  or NULL */
 RFRT_API int rfrt_mesh_export(rfrt_handle mesh, float *d_nodes, int32_t *d_tri_order, void *stream);
+
+/* Host-only helper (no device work): the candidate-filter tables rfrt_mesh_create builds for a small scene,
+ * exposed so that the filter's "superset of the exact test" property can be checked on the CPU.
+ *   h_soup [n*9] (a, b, c per triangle); outputs h_recs [64*14] (28 floats per pair of coplanar triangles:
+ *   plane (n.xyz, d) + 2 x 3 edge functions (m.xyz, c)), h_slot_tri [64] (slot -> triangle), *n_pairs,
+ *   *extent (max |coordinate|).  RFRT_ERR_INVALID when the scene needs more than 64 slots (it then takes the BVH
+ *   path).  Layout and tolerance: csrc/rfrt_small.cu. */
+RFRT_API int rfrt_small_scene_tables(const float *h_soup, int32_t n_triangles, float *h_recs, int32_t *h_slot_tri,
+                            int32_t *n_pairs, float *extent);
 
 /* ---------------------------------------------------------------------------------------------
  * Receiver set.  Replaces Tracer._generate_rx_mesh (tracer.py:26-30), batched over R receivers:

@@ -18,7 +18,9 @@ c_u64 = ctypes.c_uint64
 c_f = ctypes.c_float
 c_d = ctypes.c_double
 
-CTR_SEGMENTS, CTR_CANDIDATES, CTR_RECORDS, CTR_ENV_HITS, CTR_NEXT_RAY, CTR_NEXT_CAND, CTR_COUNT = 0, 1, 2, 3, 4, 5, 8
+CTR_SEGMENTS, CTR_CANDIDATES, CTR_RECORDS, CTR_ENV_HITS, CTR_NEXT_RAY, CTR_NEXT_CAND, CTR_CHECKSUM, CTR_COUNT = 0, 1, 2, 3, 4, 5, 6, 8
+FLAG_DIRS_READY, FLAG_FORCE_BVH, FLAG_CHECKSUM = 1, 2, 8
+SMALL_MAX_TRIS = 64
 
 # name -> (restype, argtypes); mirrors include/rfrt.h one to one
 SIGNATURES = {
@@ -30,6 +32,8 @@ SIGNATURES = {
     "rfrt_mesh_info": (ctypes.c_int, [c_u64, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_f),
                                       ctypes.POINTER(c_i32), ctypes.POINTER(c_f)]),
     "rfrt_mesh_export": (ctypes.c_int, [c_u64, c_void_p, c_void_p, c_void_p]),
+    "rfrt_small_scene_tables": (ctypes.c_int, [c_void_p, c_i32, c_void_p, c_void_p, ctypes.POINTER(c_i32),
+                                               ctypes.POINTER(c_f)]),
     "rfrt_rxset_create": (ctypes.c_int, [c_void_p, c_i64, c_d, ctypes.POINTER(c_d), c_i32, ctypes.POINTER(c_i32),
                                          c_i32, c_void_p, ctypes.POINTER(c_u64)]),
     "rfrt_rxset_destroy": (ctypes.c_int, [c_u64]),

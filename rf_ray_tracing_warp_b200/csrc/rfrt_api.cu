@@ -1,6 +1,7 @@
 // rfrt_api.cu — handle registry, error reporting, mesh / receiver-set construction (C ABI).
 #include <cfloat>
 #include <cstdio>
+#include <cstring>
 #include <memory>
 #include <mutex>
 #include <unordered_map>
@@ -170,6 +171,26 @@ extern "C" int rfrt_mesh_create(const float *d_vertices_xyz, int64_t n_vertices,
         RFRT_CUDA(cudaStreamSynchronize(stream));
         RFRT_CUDA(cudaEventElapsedTime(&m->build_ms, e0, e1));
         cudaFree(lo); cudaFree(hi); cudaFree(bad);
+        if (n_triangles <= RFRT_SMALL_MAX_TRIS) {
+            // small scene: the shared-memory image of the lockstep sweep (candidate-filter tables + exact-test data)
+            const int n = (int)n_triangles;
+            std::vector<float> soup(9 * n), fnorm(3 * n), recs(28 * (RFRT_SMALL_MAX_TRIS / 2));
+            std::vector<int32_t> slot_tri(RFRT_SMALL_MAX_TRIS);
+            RFRT_CUDA(cudaMemcpy(soup.data(), m->soup, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost));
+            RFRT_CUDA(cudaMemcpy(fnorm.data(), m->face_normals, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+            int32_t n_pairs = 0;
+            if (small_scene_tables(soup.data(), n, recs.data(), slot_tri.data(), &n_pairs, &m->small_extent) == RFRT_OK) {
+                m->small_pairs = n_pairs;
+                std::vector<float> image(small_image_floats(n_pairs, n));
+                float *w = image.data();
+                memcpy(w, recs.data(), sizeof(float) * 28 * n_pairs); w += 28 * n_pairs;
+                memcpy(w, slot_tri.data(), sizeof(int32_t) * 2 * n_pairs); w += 2 * n_pairs;
+                memcpy(w, soup.data(), sizeof(float) * 9 * n); w += 9 * n;
+                memcpy(w, fnorm.data(), sizeof(float) * 3 * n);
+                RFRT_CUDA(cudaMalloc(&m->small, sizeof(float) * image.size()));
+                RFRT_CUDA(cudaMemcpy(m->small, image.data(), sizeof(float) * image.size(), cudaMemcpyHostToDevice));
+            } // else: too many distinct planes for 64 slots -> BVH path
+        }
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
@@ -195,6 +216,7 @@ extern "C" int rfrt_mesh_destroy(rfrt_handle mesh)
     if (m->soup) cudaFree(m->soup);
     if (m->normals) cudaFree(m->normals);
     if (m->face_normals) cudaFree(m->face_normals);
+    if (m->small) cudaFree(m->small);
     delete m;
     return RFRT_OK;
 }

@@ -43,6 +43,11 @@ struct Mesh {
     float *soup = nullptr;       // [n*9] original order (a,b,c)
     float4 *normals = nullptr;   // [n] sorted order: normalize(cross(b-a, c-a)) precomputed with the trace's own ops
     float *face_normals = nullptr; // [n*3] original order
+    // small scenes: shared-memory image of the lockstep sweep (rfrt_small.cu), NULL when the scene does not fit:
+    // recs[28*pairs] | slot_tri[2*pairs] | soup[9*n] | face_normals[3*n]
+    float *small = nullptr;
+    int32_t small_pairs = 0;
+    float small_extent = 0.0f;
     float build_ms = 0.0f;
 };
 
@@ -71,6 +76,9 @@ int cuda_fail(cudaError_t e, const char *what);
 // Allocates bvh.nodes / bvh.prim_order.  Synchronises the stream.
 int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t stream, Bvh *out);
 void free_bvh(Bvh *b);
+
+int small_scene_tables(const float *soup, int n_tris, float *recs, int32_t *slot_tri, int32_t *n_pairs, float *extent);
+inline size_t small_image_floats(int n_pairs, int n_tris) { return 30 * (size_t)n_pairs + 12 * (size_t)n_tris; }
 
 Mesh *get_mesh(rfrt_handle h);
 RxSet *get_rxset(rfrt_handle h);

@@ -26,8 +26,9 @@ struct TraceParams {
     const BvhNode *nodes;
     const BvhTri *tris;
     const float4 *normals;      // [n_tris] sorted order
-    const float *soup;          // [n_tris*9] original order
-    const float *face_normals;  // [n_tris*3] original order
+    const float *small;         // small scenes: shared-memory image (rfrt_internal.h), else NULL
+    int32_t small_pairs;
+    float small_extent;
     int64_t n_tris;
     // receivers
     const BvhNode *rx_nodes;
@@ -97,10 +98,21 @@ __device__ __forceinline__ void rx_filter_and_emit(const TraceParams &P, int k, 
 
 // LSTACK: deep trees (big meshes) keep the traversal stack in per-thread local memory (L1-cached) instead of
 // shared memory, whose depth x 1 KiB per CTA would otherwise cap the occupancy of this latency-bound case.
-template <bool DUMP, bool SMALL, bool LSTACK>
+__device__ __forceinline__ unsigned long long segment_hash(uint32_t gid, int bounce, int face, float t)
+{
+    // splitmix64 finaliser of (ray id, bounce | triangle, bits of t): RFRT_CTR_CHECKSUM sums it over all segments
+    unsigned long long z = (((unsigned long long)gid << 8) | (unsigned)bounce) * 0x9E3779B97F4A7C15ull +
+                           (((unsigned long long)(uint32_t)face << 32) | __float_as_uint(t));
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// SMALL: 0 = BVH walk, 1 = lockstep sweep of <= 16 triangle pairs, 2 = of <= 32 pairs
+template <bool DUMP, int SMALL, bool LSTACK>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P)
 {
-    extern __shared__ int s_stack_raw[];
+    extern __shared__ __align__(16) int s_stack_raw[];
     int l_stack[LSTACK ? 64 : 1];
     float l_stack_t[LSTACK ? 64 : 1];
     int *stack = LSTACK ? l_stack : s_stack_raw + threadIdx.x;
@@ -108,12 +120,18 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
     constexpr int STRIDE = LSTACK ? 1 : TRACE_THREADS;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    // SMALL: the whole scene (<= 64 triangles, original order) lives in shared memory behind the stacks
-    float *s_tris = reinterpret_cast<float *>(s_stack_raw + 2 * P.stack_depth * TRACE_THREADS);
+    // SMALL: the whole scene (filter tables + exact-test data) lives in shared memory behind the stacks
+    SmallScene S;
     if (SMALL) {
-        for (int i = threadIdx.x; i < 9 * (int)P.n_tris; i += TRACE_THREADS) s_tris[i] = __ldg(P.soup + i);
-        for (int i = threadIdx.x; i < 3 * (int)P.n_tris; i += TRACE_THREADS) s_tris[9 * (int)P.n_tris + i] = __ldg(P.face_normals + i);
+        float *img = reinterpret_cast<float *>(s_stack_raw + 2 * P.stack_depth * TRACE_THREADS);
+        const int n = (int)P.n_tris, np = P.small_pairs;
+        for (int i = threadIdx.x; i < 30 * np + 12 * n; i += TRACE_THREADS) img[i] = __ldg(P.small + i);
         __syncthreads();
+        S.recs = reinterpret_cast<const float4 *>(img);
+        S.slot_tri = reinterpret_cast<const int *>(img + 28 * np);
+        S.soup = img + 30 * np;
+        S.normals = img + 30 * np + 9 * n;
+        S.n_pairs = np; S.extent = P.small_extent;
     }
 
     bool has_ray = false;
@@ -122,6 +140,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
     int bounce = 0;
     int64_t ray = 0;
     unsigned int n_seg = 0, n_hit = 0;
+    unsigned long long csum = 0ull;
 
     for (;;) {
         unsigned idle = __ballot_sync(FULL, !has_ray);
@@ -150,7 +169,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
         SlabRay sr = slab_setup(pos, dir);
         Hit h;
         h.t = 1.0e6f; h.face = -1; h.slot = -1;
-        if (SMALL) closest_hit_small(s_tris, (int)P.n_tris, wr, h);
+        if (SMALL) closest_hit_small<SMALL == 2>(S, pos, dir, wr, h);
         else closest_hit(P.nodes, P.tris, P.n_tris, wr, sr, stack, stack_t, STRIDE, h);
         const bool hit_env = h.face >= 0;
         ++n_seg;
@@ -192,6 +211,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
             int64_t row = (P.chunk_begin + ray - P.dump_begin) * P.max_bounces + bounce;
             if (P.hit_tri) P.hit_tri[row] = hit_env ? h.face : -1;
             if (P.hit_t) P.hit_t[row] = hit_env ? h.t : 0.0f;
+            csum += segment_hash((uint32_t)(P.chunk_begin + ray), bounce, hit_env ? h.face : -1, hit_env ? h.t : 0.0f);
         }
 
         if (hit_env) {
@@ -199,7 +219,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
             pos = advance(pos, dir, h.t);                 // kernel.py:94
             float3 nrm; // normalize(cross(b-a, c-a)) of the hit triangle, precomputed at build time
             if (SMALL) {
-                const float *v = s_tris + 9 * (int)P.n_tris + 3 * h.face;
+                const float *v = S.normals + 3 * h.face;
                 nrm = make_float3(v[0], v[1], v[2]);
             } else {
                 float4 n4 = __ldg(P.normals + h.slot);
@@ -222,6 +242,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
     if (lane == 0) {
         atomicAdd(&P.counters[RFRT_CTR_SEGMENTS], (unsigned long long)n_seg);
         atomicAdd(&P.counters[RFRT_CTR_ENV_HITS], (unsigned long long)n_hit);
+    }
+    if (DUMP) {
+        for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(FULL, csum, o);
+        if (lane == 0) atomicAdd(&P.counters[RFRT_CTR_CHECKSUM], csum);
     }
 }
 
@@ -522,8 +546,9 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     if (dirs_ready) chunk_rays = n; // the caller generated all directions with rfrt_ray_directions
 
     TraceParams P;
-    P.nodes = m->bvh.nodes; P.tris = m->tris; P.soup = m->soup; P.n_tris = m->bvh.n_prims;
-    P.normals = m->normals; P.face_normals = m->face_normals;
+    P.nodes = m->bvh.nodes; P.tris = m->tris; P.n_tris = m->bvh.n_prims;
+    P.normals = m->normals;
+    P.small = m->small; P.small_pairs = m->small_pairs; P.small_extent = m->small_extent;
     P.rx_nodes = r ? r->bvh.nodes : nullptr; P.rx_order = r ? r->bvh.prim_order : nullptr;
     P.rx_verts = r ? r->verts : nullptr; P.rx_centers = r ? r->centers : nullptr;
     P.n_rx = r ? r->n_receivers : 0; P.n_unit = r ? r->n_unit : 0; P.n_faces = r ? r->n_faces : 0;
@@ -535,19 +560,27 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     P.candidates = (uint4 *)d_candidates; P.cand_capacity = r ? cand_capacity : 0;
     P.hit_tri = d_hit_tri; P.hit_t = d_hit_t; P.dump_begin = ray_begin;
     P.stack_depth = stack_depth_for(m, r);
-    const bool dump = d_hit_tri || d_hit_t;
-    // scenes of <= 64 triangles: lockstep sweep over the triangles staged in shared memory (see closest_hit_small)
-    const bool small = P.n_tris > 0 && P.n_tris <= 64 && !(flags & RFRT_FLAG_FORCE_BVH);
+    // DUMP instantiations also accumulate the checksum
+    const bool dump = d_hit_tri || d_hit_t || (flags & RFRT_FLAG_CHECKSUM);
+    // small scenes: lockstep sweep over the scene staged in shared memory (see closest_hit_small)
+    const bool small = m->small && P.n_tris > 0 && !(flags & RFRT_FLAG_FORCE_BVH);
     if (small) P.stack_depth = r ? stack_depth_for(nullptr, r) : 1;
     const bool lstack = !small && P.stack_depth > 16; // deep tree: local-memory stack (<= 64 entries by construction)
     if (lstack && P.stack_depth > 64) { set_error("rfrt_trace: BVH deeper than 64 levels"); return RFRT_ERR_INVALID; }
     if (lstack) P.stack_depth = 0;
-    const size_t smem = stack_bytes(P.stack_depth) + (small ? sizeof(float) * 12 * (size_t)P.n_tris : 0);
-    const void *kern = small    ? (dump ? (const void *)k_trace_env<true, true, false> : (const void *)k_trace_env<false, true, false>)
-                       : lstack ? (dump ? (const void *)k_trace_env<true, false, true> : (const void *)k_trace_env<false, false, true>)
-                                : (dump ? (const void *)k_trace_env<true, false, false> : (const void *)k_trace_env<false, false, false>);
+    const size_t smem = stack_bytes(P.stack_depth) +
+                        (small ? sizeof(float) * small_image_floats(m->small_pairs, (int)P.n_tris) : 0);
+    typedef void (*kern_t)(const TraceParams);
+    const int variant = small ? (m->small_pairs > 16 ? 2 : 1) : (lstack ? 3 : 0);
+    static const kern_t kerns[4][2] = {
+        {k_trace_env<false, 0, false>, k_trace_env<true, 0, false>},
+        {k_trace_env<false, 1, false>, k_trace_env<true, 1, false>},
+        {k_trace_env<false, 2, false>, k_trace_env<true, 2, false>},
+        {k_trace_env<false, 0, true>, k_trace_env<true, 0, true>},
+    };
+    const kern_t kern = kerns[variant][dump ? 1 : 0];
     int grid = 0;
-    int rc = grid_for(kern, smem, &grid);
+    int rc = grid_for((const void *)kern, smem, &grid);
     if (rc) return rc;
     if (r) { rc = upload_faces(r, stream); if (rc) return rc; }
 
@@ -559,16 +592,7 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
         int g = grid;
         int64_t need = (cn + TRACE_THREADS - 1) / TRACE_THREADS;
         if (need < g) g = (int)need;
-        if (small) {
-            if (dump) k_trace_env<true, true, false><<<g, TRACE_THREADS, smem, stream>>>(P);
-            else k_trace_env<false, true, false><<<g, TRACE_THREADS, smem, stream>>>(P);
-        } else if (lstack) {
-            if (dump) k_trace_env<true, false, true><<<g, TRACE_THREADS, smem, stream>>>(P);
-            else k_trace_env<false, false, true><<<g, TRACE_THREADS, smem, stream>>>(P);
-        } else {
-            if (dump) k_trace_env<true, false, false><<<g, TRACE_THREADS, smem, stream>>>(P);
-            else k_trace_env<false, false, false><<<g, TRACE_THREADS, smem, stream>>>(P);
-        }
+        kern<<<g, TRACE_THREADS, smem, stream>>>(P);
     }
     RFRT_CUDA(cudaGetLastError());
     return RFRT_OK;

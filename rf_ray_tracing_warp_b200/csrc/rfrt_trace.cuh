@@ -133,16 +133,48 @@ __device__ __forceinline__ void closest_hit(const BvhNode *__restrict__ nodes, c
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Small scenes (<= 64 triangles, staged in shared memory in ORIGINAL index order, 9 floats each): closest hit by
-// a warp-lockstep sweep over all triangles instead of a BVH walk.  Every lane executes the same instruction stream
-// (no traversal divergence), which on a 44-triangle room beats the BVH although it tests 10x more triangles.
-//   phase 1 (lockstep): the U, V, W edge functions of intersect_ray_tri_woop for every triangle — same fp32
-//            operations as woop_hit; the permuted vertex components are fetched with per-lane shared-memory
-//            addresses (adjacent words: conflict-free), so no selects are needed.  A triangle becomes a candidate
-//            when its signs are not mixed, or when any of U, V, W is 0 / NaN (the fp64 fallback must decide).
-//   phase 2 (per lane, 1-4 candidates): the full woop_hit on the candidates in ascending index order; strict
-//            `t < best` then yields the lowest index among equal t — the same rule as the BVH path.
+// Small scenes (<= RFRT_SMALL_MAX_TRIS triangles): closest hit by a warp-lockstep sweep over the whole scene,
+// staged in shared memory, instead of a BVH walk.  Every lane executes the same instruction stream (no traversal
+// divergence), which on a 44-triangle room beats the BVH although it looks at every triangle.
+//   phase 1 (lockstep): a conservative candidate filter (tables of rfrt_small.cu).  Per supporting plane: ray
+//            parameter t and hit point h; per triangle: the three in-plane edge distances of h.  A triangle is
+//            dropped only when h is farther outside one of its edges than the tolerance, or its plane lies behind
+//            the origin by more than the tolerance.  All loads are warp-uniform (shared-memory broadcasts); NaN /
+//            inf (ray parallel to the plane, degenerate triangle) always KEEP the candidate.
+//   phase 2 (per lane, 1-3 candidates): the exact watertight test — the fp32 operation sequence of woop_hit — on
+//            the candidates; closest t in [0, best), equal t -> lowest triangle index (same rule as the BVH path).
+// The answer is therefore bit-identical to testing all triangles exactly (tests/test_gpu_parity.py compares it
+// with the CPU restatement and with the BVH kernel; tests/test_small_filter_cpu.py checks the superset property).
 // ---------------------------------------------------------------------------------------------------------
+struct SmallScene {
+    const float4 *recs;   // 7 x float4 per pair of coplanar triangles: (n.xyz, d), 2 x 3 x (m_i.xyz, c_i)
+    const int *slot_tri;  // slot -> triangle index (slots 2k, 2k+1 = pair k)
+    const float *soup;    // [9*n] original order
+    const float *normals; // [3*n] original order
+    int n_pairs;
+    float extent;         // max |coordinate| of the scene
+};
+
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// minimum that ignores NaN operands (NaN only when all three are NaN): one FMNMX3 on sm_100a
+__device__ __forceinline__ float min3f(float a, float b, float c)
+{
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 // U, V, W of one shared-memory triangle (offset o = 9*f) with the permuted components fetched through the
 // per-lane base pointers tkx/tky/tkz — the same fp32 operations, in the same order, as woop_hit.
 struct WoopUVW {
@@ -176,56 +208,56 @@ __device__ __forceinline__ WoopUVW woop_uvw_smem(const float *tkx, const float *
     return r;
 }
 
-// sign bit set  <=>  U, V, W have mixed signs (for non-zero, non-NaN values)
-__device__ __forceinline__ bool uvw_candidate(float U, float V, float W)
+// phase 1 over n_pairs records: returns the candidate mask, slot s of 2*n_pairs at bit 2*n_pairs-1-s
+__device__ __forceinline__ unsigned sweep_pairs(const float4 *rec, int n_pairs, float3 pos, float3 dir, float dl, float dl_h)
 {
-    unsigned mixed;
-    asm("lop3.b32 %0, %1, %2, %3, 0x7e;" // (u|v|w) & ~(u&v&w) in one instruction
-        : "=r"(mixed) : "r"(__float_as_uint(U)), "r"(__float_as_uint(V)), "r"(__float_as_uint(W)));
-    const bool all_nonzero = fminf(fminf(fabsf(U), fabsf(V)), fabsf(W)) > 0.0f;         // false for 0 and NaN
-    return !all_nonzero || (int)mixed >= 0;
-}
-
-__device__ __forceinline__ void closest_hit_small(const float *s_tris, int n_tris, const WoopRay &wr, Hit &h)
-{
-    const float *tkx = s_tris + wr.kx, *tky = s_tris + wr.ky, *tkz = s_tris + wr.kz;
-    const float pkx = sel3(wr.px, wr.py, wr.pz, wr.kx), pky = sel3(wr.px, wr.py, wr.pz, wr.ky),
-                pkz = sel3(wr.px, wr.py, wr.pz, wr.kz);
-    // ---- phase 1: lockstep sweep, candidates collected in two 32-bit masks with a walking bit --------------
-    // (bits are shifted in, so triangle f of a group of n sits at bit n-1-f: phase 2 walks from the top bit down)
-    unsigned cand_lo = 0u, cand_hi = 0u;
-    const int n_lo = n_tris < 32 ? n_tris : 32, n_hi = n_tris - n_lo;
-    {
-#pragma unroll 4
-        for (int f = 0; f < n_lo; ++f) {
-            const int o = 9 * f;
-            const float Akx = __fsub_rn(tkx[o], pkx), Aky = __fsub_rn(tky[o], pky), Akz = __fsub_rn(tkz[o], pkz);
-            const float Bkx = __fsub_rn(tkx[o + 3], pkx), Bky = __fsub_rn(tky[o + 3], pky), Bkz = __fsub_rn(tkz[o + 3], pkz);
-            const float Ckx = __fsub_rn(tkx[o + 6], pkx), Cky = __fsub_rn(tky[o + 6], pky), Ckz = __fsub_rn(tkz[o + 6], pkz);
-            const float Ax = __fsub_rn(Akx, __fmul_rn(wr.Sx, Akz)), Ay = __fsub_rn(Aky, __fmul_rn(wr.Sy, Akz));
-            const float Bx = __fsub_rn(Bkx, __fmul_rn(wr.Sx, Bkz)), By = __fsub_rn(Bky, __fmul_rn(wr.Sy, Bkz));
-            const float Cx = __fsub_rn(Ckx, __fmul_rn(wr.Sx, Ckz)), Cy = __fsub_rn(Cky, __fmul_rn(wr.Sy, Ckz));
-            cand_lo = cand_lo + cand_lo +
-                      (uvw_candidate(diff_product(Cx, By, Cy, Bx), diff_product(Ax, Cy, Ay, Cx), diff_product(Bx, Ay, By, Ax)) ? 1u : 0u);
-        }
-#pragma unroll 4
-        for (int f = 32; f < n_tris; ++f) {
-            const int o = 9 * f;
-            const float Akx = __fsub_rn(tkx[o], pkx), Aky = __fsub_rn(tky[o], pky), Akz = __fsub_rn(tkz[o], pkz);
-            const float Bkx = __fsub_rn(tkx[o + 3], pkx), Bky = __fsub_rn(tky[o + 3], pky), Bkz = __fsub_rn(tkz[o + 3], pkz);
-            const float Ckx = __fsub_rn(tkx[o + 6], pkx), Cky = __fsub_rn(tky[o + 6], pky), Ckz = __fsub_rn(tkz[o + 6], pkz);
-            const float Ax = __fsub_rn(Akx, __fmul_rn(wr.Sx, Akz)), Ay = __fsub_rn(Aky, __fmul_rn(wr.Sy, Akz));
-            const float Bx = __fsub_rn(Bkx, __fmul_rn(wr.Sx, Bkz)), By = __fsub_rn(Bky, __fmul_rn(wr.Sy, Bkz));
-            const float Cx = __fsub_rn(Ckx, __fmul_rn(wr.Sx, Ckz)), Cy = __fsub_rn(Cky, __fmul_rn(wr.Sy, Ckz));
-            cand_hi = cand_hi + cand_hi +
-                      (uvw_candidate(diff_product(Cx, By, Cy, Bx), diff_product(Ax, Cy, Ay, Cx), diff_product(Bx, Ay, By, Ax)) ? 1u : 0u);
+    const float INF = __int_as_float(0x7f800000);
+    unsigned dropped = 0u;
+#pragma unroll 2
+    for (int k = 0; k < n_pairs; ++k, rec += 7) {
+        const float4 P = rec[0];
+        const float nd = fmaf(P.x, dir.x, fmaf(P.y, dir.y, P.z * dir.z));
+        const float np = fmaf(P.x, pos.x, fmaf(P.y, pos.y, fmaf(P.z, pos.z, -P.w)));
+        const float r = rcp_approx(nd);
+        const float t = -np * r;
+        const float ar = fabsf(r);
+        // plane behind the origin by more than the tolerance: thr = +inf drops both triangles
+        const float thr = (t < -(dl * ar)) ? INF : -(dl_h * ar);
+        const float hx = fmaf(t, dir.x, pos.x), hy = fmaf(t, dir.y, pos.y), hz = fmaf(t, dir.z, pos.z);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float4 e0 = rec[1 + 3 * j], e1 = rec[2 + 3 * j], e2 = rec[3 + 3 * j];
+            const float d0 = fmaf(e0.x, hx, fmaf(e0.y, hy, fmaf(e0.z, hz, e0.w)));
+            const float d1 = fmaf(e1.x, hx, fmaf(e1.y, hy, fmaf(e1.z, hz, e1.w)));
+            const float d2 = fmaf(e2.x, hx, fmaf(e2.y, hy, fmaf(e2.z, hz, e2.w)));
+            // shift the sign of (min_i d_i - thr) into the mask: 1 = definitely outside.  inf - inf and NaN inputs
+            // give the canonical NaN 0x7fffffff (sign clear), i.e. the triangle is kept.
+            dropped = __funnelshift_l(__float_as_uint(min3f(d0, d1, d2) - thr), dropped, 1);
         }
     }
-    // ---- phase 2: the full test on this lane's candidates, ascending index ----------------------------------
-    while (cand_lo | cand_hi) {
-        int f;
-        if (cand_lo) { const int b = 31 - __clz((int)cand_lo); cand_lo ^= 1u << b; f = n_lo - 1 - b; }
-        else { const int b = 31 - __clz((int)cand_hi); cand_hi ^= 1u << b; f = 32 + n_hi - 1 - b; }
+    return ~dropped & (n_pairs >= 16 ? 0xffffffffu : (1u << (2 * n_pairs)) - 1u);
+}
+
+// WIDE: more than 16 pairs (the candidate mask needs a second word)
+template <bool WIDE>
+__device__ __forceinline__ void closest_hit_small(const SmallScene &S, float3 pos, float3 dir, const WoopRay &wr, Hit &h)
+{
+    // ---- phase 1: lockstep candidate filter ------------------------------------------------------------------
+    // tolerance (metres) = 2^-16 * (extent + |p|_1) / sin(angle between ray and plane); see rfrt_small.cu
+    const float dl = (S.extent + fabsf(pos.x) + fabsf(pos.y) + fabsf(pos.z)) * (1.0f / 65536.0f);
+    const float dl_h = dl * (sqrt_approx(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z) * 1.001f);
+    const int n_lo = WIDE ? 16 : S.n_pairs, n_hi = WIDE ? S.n_pairs - 16 : 0;
+    unsigned lo = sweep_pairs(S.recs, n_lo, pos, dir, dl, dl_h);
+    unsigned hi = WIDE ? sweep_pairs(S.recs + 7 * 16, n_hi, pos, dir, dl, dl_h) : 0u;
+    // ---- phase 2: the exact test on this lane's candidates ---------------------------------------------------
+    const float *tkx = S.soup + wr.kx, *tky = S.soup + wr.ky, *tkz = S.soup + wr.kz;
+    const float pkx = sel3(wr.px, wr.py, wr.pz, wr.kx), pky = sel3(wr.px, wr.py, wr.pz, wr.ky),
+                pkz = sel3(wr.px, wr.py, wr.pz, wr.kz);
+    while (lo | hi) {
+        int slot;
+        if (lo) { const int b = 31 - __clz((int)lo); lo ^= 1u << b; slot = 2 * n_lo - 1 - b; }
+        else { const int b = 31 - __clz((int)hi); hi ^= 1u << b; slot = 32 + 2 * n_hi - 1 - b; }
+        const int f = S.slot_tri[slot];
         const WoopUVW q = woop_uvw_smem(tkx, tky, tkz, 9 * f, pkx, pky, pkz, wr.Sx, wr.Sy);
         const float U = q.U, V = q.V, W = q.W;
         if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) continue;
@@ -236,7 +268,7 @@ __device__ __forceinline__ void closest_hit_small(const float *s_tris, int n_tri
         const float x = __uint_as_float(__float_as_uint(T) ^ (__float_as_uint(det) & 0x80000000u));
         if (x < 0.0f) continue;
         const float t = __fmul_rn(T, __fdiv_rn(1.0f, det));
-        if (t >= 0.0f && t < h.t) { h.t = t; h.face = f; h.slot = f; }
+        if (t >= 0.0f && (t < h.t || (t == h.t && h.face >= 0 && f < h.face))) { h.t = t; h.face = f; h.slot = f; }
     }
 }
 

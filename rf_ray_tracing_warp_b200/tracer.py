@@ -66,7 +66,7 @@ class Tracer:
         self.max_candidates = int(max_candidates)
         self.max_records = int(max_records)
         self.verbose = verbose
-        self.trace_flags = 2 if force_bvh else 0  # RFRT_FLAG_FORCE_BVH
+        self.trace_flags = _lib.FLAG_FORCE_BVH if force_bvh else 0
         self.shard = bool(shard)
         self._world, self._rank = 1, 0
         if self.shard and torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -124,20 +124,25 @@ class Tracer:
         return handle.value
 
     # ------------------------------------------------------------------------------------------
-    def trace_segments(self, tx_pos, ray_range=None, dump=False):
-        """Environment-only trace (no receivers).  Returns dict(segments, env_hits[, hit_tri, hit_t]).
-        ``dump=True`` adds the dense (n, B) parity arrays (hit triangle index, -1 = miss/dead; hit distance)."""
+    def trace_segments(self, tx_pos, ray_range=None, dump=False, checksum=False):
+        """Environment-only trace (no receivers).  Returns dict(segments, env_hits[, hit_tri, hit_t][, checksum]).
+        ``dump=True`` adds the dense (n, B) parity arrays (hit triangle index, -1 = miss/dead; hit distance);
+        ``checksum=True`` adds the order-independent u64 sum of hash(ray, bounce, triangle, t) over all segments
+        (RFRT_CTR_CHECKSUM) — equal checksums mean the same hit triangle and distance on every segment."""
         begin, end = ray_range if ray_range is not None else self.ray_range
         n, B = end - begin, self.max_bounces
         with torch.cuda.device(self.device):
             counters = torch.zeros(_lib.CTR_COUNT, dtype=torch.int64, device=self.device)
             hit_tri = torch.full((n, B), -1, dtype=torch.int32, device=self.device) if dump else None
             hit_t = torch.zeros((n, B), dtype=torch.float32, device=self.device) if dump else None
-            check(self._lib.rfrt_trace(self._env, 0, float3(tx_pos), B, begin, end, self.trace_flags, _ptr(self._scratch(n)),
+            flags = self.trace_flags | (_lib.FLAG_CHECKSUM if checksum else 0)
+            check(self._lib.rfrt_trace(self._env, 0, float3(tx_pos), B, begin, end, flags, _ptr(self._scratch(n)),
                                        self.chunk_rays, _ptr(counters), None, 0, _ptr(hit_tri), _ptr(hit_t),
                                        _stream_ptr()), "rfrt_trace")
             c = counters.cpu().numpy()
         out = dict(segments=int(c[_lib.CTR_SEGMENTS]), env_hits=int(c[_lib.CTR_ENV_HITS]))
+        if checksum or dump:
+            out["checksum"] = int(c[_lib.CTR_CHECKSUM]) & 0xFFFFFFFFFFFFFFFF
         if dump:
             out.update(hit_tri=hit_tri, hit_t=hit_t)
         return out
@@ -397,7 +402,7 @@ class TraceJob:
                                      _stream_ptr()), "rfrt_trace")
                 self.kernel_launches += 2 * max(1, -(-n // t.chunk_rays))
             else:
-                check(lib.rfrt_trace(t._env, self.rxset, tx, B, begin, end, 1 | t.trace_flags, _ptr(dirs), n, _ptr(self.counters_t),
+                check(lib.rfrt_trace(t._env, self.rxset, tx, B, begin, end, _lib.FLAG_DIRS_READY | t.trace_flags, _ptr(dirs), n, _ptr(self.counters_t),
                                      _ptr(self.cands), self.cand_capacity, None, None, _stream_ptr()), "rfrt_trace")
                 self.kernel_launches += 1
             amp0 = tx_power / t.tx_num_rays if t.tx_num_rays else 0.0  # tracer.py:103

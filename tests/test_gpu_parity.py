@@ -211,3 +211,42 @@ def test_kat1_received_set_on_gpu(torch_cuda, almost_empty_stl, repo_root):
     for t, p in zip(rays, paths):
         assert np.linalg.norm(p[1] - gold_entry[int(t)]) < 0.02
     assert out["stats"]["segments"] >= kat["n_rays"]
+
+
+def _oracle_checksum(tri, t, begin):
+    """RFRT_CTR_CHECKSUM restated in NumPy: sum over alive segments of splitmix64(ray, bounce, triangle, bits of t)."""
+    n, B = tri.shape
+    alive = np.ones((n, B), dtype=bool)
+    alive[:, 1:] = np.cumprod(tri[:, :-1] >= 0, axis=1).astype(bool)
+    gid = (np.arange(n, dtype=np.uint64) + np.uint64(begin))[:, None]
+    bounce = np.arange(B, dtype=np.uint64)[None, :]
+    with np.errstate(over="ignore"):
+        z = ((gid << np.uint64(8)) | bounce) * np.uint64(0x9E3779B97F4A7C15) + \
+            ((tri.astype(np.uint32).astype(np.uint64) << np.uint64(32)) | t.view(np.uint32).astype(np.uint64))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        return int(z[alive].sum(dtype=np.uint64))
+
+
+@pytest.mark.parametrize("scene,B,tx", [("room", 8, [10, 0, 5]), ("almost_empty", 4, [1, 0, 1])])
+def test_checksum_sweep_equals_bvh_at_full_size(torch_cuda, room_stl, almost_empty_stl, scene, B, tx):
+    """Size-independent parity: the order-independent checksum over (ray, bounce, hit triangle, t) of EVERY segment.
+    Small size: both GPU strategies == oracle.  BASELINE size (2^26 rays x 8 bounces on room.stl = 4.2e8 segments):
+    candidate-filtered lockstep sweep == BVH walk (two independent closest-hit implementations)."""
+    from oracle import cpu, geometry
+    from rf_ray_tracing_warp_b200 import load_mesh
+    path = room_stl if scene == "room" else almost_empty_stl
+    n_small, begin = 1 << 16, 123_456
+    seg, tri, t = cpu.trace_env(geometry.load_stl_soup(path), tx, B, begin, n_small)
+    want = _oracle_checksum(tri, t, begin)
+    n_big = 1 << 26
+    res = {}
+    for force_bvh in (False, True):
+        tr = _tracer(load_mesh(path), B, n_big, force_bvh=force_bvh)
+        small = tr.trace_segments(tx, ray_range=(begin, begin + n_small), checksum=True)
+        assert small["segments"] == seg and small["checksum"] == want
+        res[force_bvh] = tr.trace_segments(tx, checksum=True)
+    assert res[False]["segments"] == res[True]["segments"] > n_big
+    assert res[False]["env_hits"] == res[True]["env_hits"]
+    assert res[False]["checksum"] == res[True]["checksum"]
