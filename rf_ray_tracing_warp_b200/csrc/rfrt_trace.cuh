@@ -141,8 +141,9 @@ __device__ __forceinline__ void closest_hit(const BvhNode *__restrict__ nodes, c
 //            dropped only when h is farther outside one of its edges than the tolerance, or its plane lies behind
 //            the origin by more than the tolerance.  All loads are warp-uniform (shared-memory broadcasts); NaN /
 //            inf (ray parallel to the plane, degenerate triangle) always KEEP the candidate.
-//   phase 2 (per lane, 1-3 candidates): the exact watertight test — the fp32 operation sequence of woop_hit — on
-//            the candidates; closest t in [0, best), equal t -> lowest triangle index (same rule as the BVH path).
+//   phase 2 (per lane): the exact watertight test — the fp32 operation sequence of woop_hit — on the candidates,
+//            nearest first, until the rest provably lies behind the best hit; closest t in [0, best), equal t ->
+//            lowest triangle index (same rule as the BVH path).
 // The answer is therefore bit-identical to testing all triangles exactly (tests/test_gpu_parity.py compares it
 // with the CPU restatement and with the BVH kernel; tests/test_small_filter_cpu.py checks the superset property).
 // ---------------------------------------------------------------------------------------------------------
@@ -208,13 +209,14 @@ __device__ __forceinline__ WoopUVW woop_uvw_smem(const float *tkx, const float *
     return r;
 }
 
-// phase 1 over n_pairs records: returns the candidate mask, slot s of 2*n_pairs at bit 2*n_pairs-1-s
-__device__ __forceinline__ unsigned sweep_pairs(const float4 *rec, int n_pairs, float3 pos, float3 dir, float dl, float dl_h)
+// phase 1 over n_pairs records (walked backwards, so that slot s ends up at mask bit s): the candidate mask
+__device__ __forceinline__ unsigned sweep_pairs(const float4 *recs, int n_pairs, float3 pos, float3 dir, float dl, float dl_h)
 {
     const float INF = __int_as_float(0x7f800000);
     unsigned dropped = 0u;
+    const float4 *rec = recs + 7 * (n_pairs - 1);
 #pragma unroll 2
-    for (int k = 0; k < n_pairs; ++k, rec += 7) {
+    for (int k = 0; k < n_pairs; ++k, rec -= 7) {
         const float4 P = rec[0];
         const float nd = fmaf(P.x, dir.x, fmaf(P.y, dir.y, P.z * dir.z));
         const float np = fmaf(P.x, pos.x, fmaf(P.y, pos.y, fmaf(P.z, pos.z, -P.w)));
@@ -225,7 +227,7 @@ __device__ __forceinline__ unsigned sweep_pairs(const float4 *rec, int n_pairs, 
         const float thr = (t < -(dl * ar)) ? INF : -(dl_h * ar);
         const float hx = fmaf(t, dir.x, pos.x), hy = fmaf(t, dir.y, pos.y), hz = fmaf(t, dir.z, pos.z);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 1; j >= 0; --j) {
             const float4 e0 = rec[1 + 3 * j], e1 = rec[2 + 3 * j], e2 = rec[3 + 3 * j];
             const float d0 = fmaf(e0.x, hx, fmaf(e0.y, hy, fmaf(e0.z, hz, e0.w)));
             const float d1 = fmaf(e1.x, hx, fmaf(e1.y, hy, fmaf(e1.z, hz, e1.w)));
@@ -236,6 +238,34 @@ __device__ __forceinline__ unsigned sweep_pairs(const float4 *rec, int n_pairs, 
         }
     }
     return ~dropped & (n_pairs >= 16 ? 0xffffffffu : (1u << (2 * n_pairs)) - 1u);
+}
+
+// the exact test of one candidate slot: closest t in [0, best], equal t -> lowest triangle index
+__device__ __forceinline__ void small_exact(const SmallScene &S, int slot, const float *tkx, const float *tky, const float *tkz,
+                                            float pkx, float pky, float pkz, const WoopRay &wr, Hit &h)
+{
+    const int f = S.slot_tri[slot];
+    const WoopUVW q = woop_uvw_smem(tkx, tky, tkz, 9 * f, pkx, pky, pkz, wr.Sx, wr.Sy);
+    const float U = q.U, V = q.V, W = q.W;
+    const bool mixed = (U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f);
+    const float det = __fadd_rn(__fadd_rn(U, V), W);
+    const float Az = __fmul_rn(wr.Sz, q.Akz), Bz = __fmul_rn(wr.Sz, q.Bkz), Cz = __fmul_rn(wr.Sz, q.Ckz);
+    const float T = __fadd_rn(__fadd_rn(__fmul_rn(U, Az), __fmul_rn(V, Bz)), __fmul_rn(W, Cz));
+    const float x = __uint_as_float(__float_as_uint(T) ^ (__float_as_uint(det) & 0x80000000u));
+    if (!mixed && det != 0.0f && !(x < 0.0f)) {
+        const float t = __fmul_rn(T, __fdiv_rn(1.0f, det));
+        if (t >= 0.0f && (t < h.t || (t == h.t && h.face >= 0 && f < h.face))) { h.t = t; h.face = f; h.slot = f; }
+    }
+}
+
+// lower bound of the exact t of the triangles of slot's pair (NaN-free: -inf when undecidable)
+__device__ __forceinline__ float small_t_lower(const SmallScene &S, int slot, float3 pos, float3 dir, float dl)
+{
+    const float4 P = S.recs[7 * (slot >> 1)];
+    const float nd = fmaf(P.x, dir.x, fmaf(P.y, dir.y, P.z * dir.z));
+    const float np = fmaf(P.x, pos.x, fmaf(P.y, pos.y, fmaf(P.z, pos.z, -P.w)));
+    const float r = rcp_approx(nd);
+    return fmaxf(fmaf(-dl, fabsf(r), -np * r), -__int_as_float(0x7f800000)); // t - kt; NaN -> -inf
 }
 
 // WIDE: more than 16 pairs (the candidate mask needs a second word)
@@ -249,26 +279,50 @@ __device__ __forceinline__ void closest_hit_small(const SmallScene &S, float3 po
     const int n_lo = WIDE ? 16 : S.n_pairs, n_hi = WIDE ? S.n_pairs - 16 : 0;
     unsigned lo = sweep_pairs(S.recs, n_lo, pos, dir, dl, dl_h);
     unsigned hi = WIDE ? sweep_pairs(S.recs + 7 * 16, n_hi, pos, dir, dl, dl_h) : 0u;
-    // ---- phase 2: the exact test on this lane's candidates ---------------------------------------------------
+
+    // ---- phase 2: the exact test, nearest candidates first ---------------------------------------------------
+    // The plane parameter minus the tolerance (t_lo) is a lower bound of a candidate's exact t, so once the best
+    // exact hit lies below the t_lo of everything that is left, the rest cannot win (on room.stl this cuts the
+    // exact tests per segment from 2.3 to 1.0: the ray's own surface at t ~ 0 and the shell behind the hit drop out).
+    const float INF = __int_as_float(0x7f800000);
+    float k1 = INF, k2 = INF; // the two smallest t_lo ...
+    int s1 = -1, s2 = -1;     // ... and their slots
+    {
+        unsigned mlo = lo, mhi = hi;
+        while (mlo | mhi) {
+            int slot;
+            if (mlo) { slot = 31 - __clz((int)mlo); mlo ^= 1u << slot; }
+            else { const int b = 31 - __clz((int)mhi); mhi ^= 1u << b; slot = 32 + b; }
+            const float key = small_t_lower(S, slot, pos, dir, dl);
+            const bool lt1 = key < k1, lt2 = key < k2;
+            s2 = lt1 ? s1 : (lt2 ? slot : s2);
+            k2 = lt1 ? k1 : (lt2 ? key : k2);
+            s1 = lt1 ? slot : s1;
+            k1 = lt1 ? key : k1;
+        }
+    }
     const float *tkx = S.soup + wr.kx, *tky = S.soup + wr.ky, *tkz = S.soup + wr.kz;
     const float pkx = sel3(wr.px, wr.py, wr.pz, wr.kx), pky = sel3(wr.px, wr.py, wr.pz, wr.ky),
                 pkz = sel3(wr.px, wr.py, wr.pz, wr.kz);
-    while (lo | hi) {
-        int slot;
-        if (lo) { const int b = 31 - __clz((int)lo); lo ^= 1u << b; slot = 2 * n_lo - 1 - b; }
-        else { const int b = 31 - __clz((int)hi); hi ^= 1u << b; slot = 32 + 2 * n_hi - 1 - b; }
-        const int f = S.slot_tri[slot];
-        const WoopUVW q = woop_uvw_smem(tkx, tky, tkz, 9 * f, pkx, pky, pkz, wr.Sx, wr.Sy);
-        const float U = q.U, V = q.V, W = q.W;
-        if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) continue;
-        const float det = __fadd_rn(__fadd_rn(U, V), W);
-        if (det == 0.0f) continue;
-        const float Az = __fmul_rn(wr.Sz, q.Akz), Bz = __fmul_rn(wr.Sz, q.Bkz), Cz = __fmul_rn(wr.Sz, q.Ckz);
-        const float T = __fadd_rn(__fadd_rn(__fmul_rn(U, Az), __fmul_rn(V, Bz)), __fmul_rn(W, Cz));
-        const float x = __uint_as_float(__float_as_uint(T) ^ (__float_as_uint(det) & 0x80000000u));
-        if (x < 0.0f) continue;
-        const float t = __fmul_rn(T, __fdiv_rn(1.0f, det));
-        if (t >= 0.0f && (t < h.t || (t == h.t && h.face >= 0 && f < h.face))) { h.t = t; h.face = f; h.slot = f; }
+    int cur = s1;
+    int stage = 0;
+    while (cur >= 0) {
+        small_exact(S, cur, tkx, tky, tkz, pkx, pky, pkz, wr, h);
+        if (cur < 32) lo &= ~(1u << cur); else hi &= ~(1u << (cur - 32));
+        int next = -1;
+        if (stage == 0) {
+            if (s2 >= 0 && k2 <= h.t) next = s2;
+        } else if (k2 <= h.t) {
+            // rare: more than two candidates may reach below the best hit -> walk the rest with the bound test
+            while (lo | hi) {
+                int slot;
+                if (lo) { slot = 31 - __clz((int)lo); lo ^= 1u << slot; }
+                else { const int b = 31 - __clz((int)hi); hi ^= 1u << b; slot = 32 + b; }
+                if (small_t_lower(S, slot, pos, dir, dl) <= h.t) { next = slot; break; }
+            }
+        }
+        stage = 1;
+        cur = next;
     }
 }
 
