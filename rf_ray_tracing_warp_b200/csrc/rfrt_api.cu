@@ -183,10 +183,16 @@ extern "C" int rfrt_mesh_create(const float *d_vertices_xyz, int64_t n_vertices,
                 m->small_pairs = n_pairs;
                 std::vector<float> image(small_image_floats(n_pairs, n));
                 float *w = image.data();
+                std::vector<uint32_t> nbr(4 * n);
+                std::vector<int32_t> tri_slot(n);
+                small_scene_neighbours(soup.data(), n, slot_tri.data(), n_pairs, SMALL_REACH_REL * (double)m->small_extent, nbr.data(),
+                                       tri_slot.data());
                 memcpy(w, recs.data(), sizeof(float) * 28 * n_pairs); w += 28 * n_pairs;
+                memcpy(w, nbr.data(), sizeof(uint32_t) * 4 * n); w += 4 * n;
                 memcpy(w, slot_tri.data(), sizeof(int32_t) * 2 * n_pairs); w += 2 * n_pairs;
                 memcpy(w, soup.data(), sizeof(float) * 9 * n); w += 9 * n;
-                memcpy(w, fnorm.data(), sizeof(float) * 3 * n);
+                memcpy(w, fnorm.data(), sizeof(float) * 3 * n); w += 3 * n;
+                memcpy(w, tri_slot.data(), sizeof(int32_t) * n);
                 RFRT_CUDA(cudaMalloc(&m->small, sizeof(float) * image.size()));
                 RFRT_CUDA(cudaMemcpy(m->small, image.data(), sizeof(float) * image.size(), cudaMemcpyHostToDevice));
             } // else: too many distinct planes for 64 slots -> BVH path

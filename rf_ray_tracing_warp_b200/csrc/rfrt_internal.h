@@ -44,7 +44,7 @@ struct Mesh {
     float4 *normals = nullptr;   // [n] sorted order: normalize(cross(b-a, c-a)) precomputed with the trace's own ops
     float *face_normals = nullptr; // [n*3] original order
     // small scenes: shared-memory image of the lockstep sweep (rfrt_small.cu), NULL when the scene does not fit:
-    // recs[28*pairs] | slot_tri[2*pairs] | soup[9*n] | face_normals[3*n]
+    // recs[28*pairs] | nbr[4*n] | slot_tri[2*pairs] | soup[9*n] | face_normals[3*n] | tri_slot[n]   (first two: 16-byte rows)
     float *small = nullptr;
     int32_t small_pairs = 0;
     float small_extent = 0.0f;
@@ -78,7 +78,13 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
 void free_bvh(Bvh *b);
 
 int small_scene_tables(const float *soup, int n_tris, float *recs, int32_t *slot_tri, int32_t *n_pairs, float *extent);
-inline size_t small_image_floats(int n_pairs, int n_tris) { return 30 * (size_t)n_pairs + 12 * (size_t)n_tris; }
+void small_scene_neighbours(const float *soup, int n_tris, const int32_t *slot_tri, int n_pairs, double reach, uint32_t *nbr,
+                            int32_t *tri_slot);
+inline size_t small_image_floats(int n_pairs, int n_tris) { return 30 * (size_t)n_pairs + 17 * (size_t)n_tris; }
+// self-re-hit shortcut (rfrt_trace.cuh): applies to hits of the ray's own triangle within SMALL_TAU_REL * extent
+// (path length); neighbours are collected within SMALL_REACH_REL * extent
+constexpr double SMALL_TAU_REL = 1.0e-4;
+constexpr double SMALL_REACH_REL = 1.0e-3;
 
 Mesh *get_mesh(rfrt_handle h);
 RxSet *get_rxset(rfrt_handle h);

@@ -53,6 +53,7 @@ struct TraceParams {
     float *hit_t;
     int64_t dump_begin;
     int32_t stack_depth;
+    int32_t short_min; // small scenes: run a self-re-hit trip when at least this many lanes stand on a surface
 };
 
 __global__ void k_gen_dirs(int64_t ray_begin, int64_t n, float4 *__restrict__ dirs)
@@ -125,19 +126,23 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
     if (SMALL) {
         float *img = reinterpret_cast<float *>(s_stack_raw + 2 * P.stack_depth * TRACE_THREADS);
         const int n = (int)P.n_tris, np = P.small_pairs;
-        for (int i = threadIdx.x; i < 30 * np + 12 * n; i += TRACE_THREADS) img[i] = __ldg(P.small + i);
+        for (int i = threadIdx.x; i < 30 * np + 17 * n; i += TRACE_THREADS) img[i] = __ldg(P.small + i);
         __syncthreads();
         S.recs = reinterpret_cast<const float4 *>(img);
-        S.slot_tri = reinterpret_cast<const int *>(img + 28 * np);
-        S.soup = img + 30 * np;
-        S.normals = img + 30 * np + 9 * n;
-        S.n_pairs = np; S.extent = P.small_extent;
+        S.nbr = reinterpret_cast<const uint4 *>(img + 28 * np);
+        S.slot_tri = reinterpret_cast<const int *>(img + 28 * np + 4 * n);
+        S.soup = img + 30 * np + 4 * n;
+        S.normals = img + 30 * np + 13 * n;
+        S.tri_slot = reinterpret_cast<const int *>(img + 30 * np + 16 * n);
+        S.n_pairs = np; S.extent = P.small_extent; S.tau = (float)SMALL_TAU_REL * P.small_extent;
+        S.erode = (float)(2.0 * SMALL_REACH_REL) * P.small_extent;
     }
 
     bool has_ray = false;
     bool exhausted = false; // warp-uniform
     float3 pos = make_float3(0.f, 0.f, 0.f), dir = make_float3(0.f, 0.f, 1.f);
     int bounce = 0;
+    int on_face = -1; // SMALL: the triangle the ray stands on (its previous hit); -1 at the transmitter
     int64_t ray = 0;
     unsigned int n_seg = 0, n_hit = 0;
     unsigned long long csum = 0ull;
@@ -156,6 +161,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
                     dir = make_float3(d4.x, d4.y, d4.z);
                     pos = P.tx;
                     bounce = 0;
+                    on_face = -1;
                     ray = r;
                     has_ray = true;
                 }
@@ -163,14 +169,26 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
             if ((int64_t)base + cnt >= P.chunk_n) exhausted = true;
         }
         if (!__any_sync(FULL, has_ray)) break;
-        if (has_ray) {
+        // SMALL: a trip is either a self-re-hit trip (only the lanes standing on a surface work; cheap) or a full
+        // sweep (every lane with a ray).  The full sweep is always valid, so the vote is purely a scheduling choice.
+        bool shortcut = false;
+        if (SMALL) shortcut = __popc(__ballot_sync(FULL, has_ray && on_face >= 0)) >= P.short_min;
+        if (has_ray && (!shortcut || on_face >= 0)) {
         // ---- one bounce iteration (kernel.py:57-98, environment branch) -----------------------
         WoopRay wr = woop_setup(pos, dir);
-        SlabRay sr = slab_setup(pos, dir);
         Hit h;
         h.t = 1.0e6f; h.face = -1; h.slot = -1;
-        if (SMALL) closest_hit_small<SMALL == 2>(S, pos, dir, wr, h);
-        else closest_hit(P.nodes, P.tris, P.n_tris, wr, sr, stack, stack_t, STRIDE, h);
+        bool resolved = true;
+        if (SMALL) {
+            if (shortcut) resolved = small_self_rehit(S, on_face, pos, dir, wr, h);
+            else closest_hit_small<SMALL == 2>(S, pos, dir, wr, h);
+        } else {
+            SlabRay sr = slab_setup(pos, dir);
+            closest_hit(P.nodes, P.tris, P.n_tris, wr, sr, stack, stack_t, STRIDE, h);
+        }
+        if (!resolved) {
+            on_face = -1; // not a self re-hit: this segment goes through the next full sweep
+        } else {
         const bool hit_env = h.face >= 0;
         ++n_seg;
 
@@ -182,6 +200,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
                 rx_filter_and_emit(P, 0, pos, dir, t_limit, gid, bounce);
             } else {
                 // enumerate every receiver whose box overlaps the segment [0, t_limit]
+                SlabRay sr = slab_setup(pos, dir);
                 int sp = 0;
                 int node = 0;
                 while (node >= 0) {
@@ -226,11 +245,13 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
                 nrm = make_float3(n4.x, n4.y, n4.z);
             }
             dir = reflect(dir, nrm);                      // kernel.py:96
+            on_face = h.face;
             ++bounce;
             if (bounce >= P.max_bounces) has_ray = false;
         } else {
             has_ray = false; // a miss repeats forever in the reference (kernel.py:97-98): nothing more to do
         }
+        } // resolved
         } // has_ray
     }
 
@@ -560,6 +581,8 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     P.candidates = (uint4 *)d_candidates; P.cand_capacity = r ? cand_capacity : 0;
     P.hit_tri = d_hit_tri; P.hit_t = d_hit_t; P.dump_begin = ray_begin;
     P.stack_depth = stack_depth_for(m, r);
+    P.short_min = 8;
+    if (const char *e = getenv("RFRT_SHORT_MIN")) P.short_min = atoi(e);
     // DUMP instantiations also accumulate the checksum
     const bool dump = d_hit_tri || d_hit_t || (flags & RFRT_FLAG_CHECKSUM);
     // small scenes: lockstep sweep over the scene staged in shared memory (see closest_hit_small)

@@ -152,8 +152,12 @@ struct SmallScene {
     const int *slot_tri;  // slot -> triangle index (slots 2k, 2k+1 = pair k)
     const float *soup;    // [9*n] original order
     const float *normals; // [3*n] original order
+    const uint4 *nbr;     // [n] neighbour pair masks of triangle f: interior, boundary, interior & lower index, boundary & lower
+    const int *tri_slot;  // [n] a filter slot of triangle f
     int n_pairs;
     float extent;         // max |coordinate| of the scene
+    float tau;            // self-re-hit shortcut: path-length bound
+    float erode;          // ... clearance that rules out the boundary neighbours (2 * reach)
 };
 
 __device__ __forceinline__ float rcp_approx(float x)
@@ -209,43 +213,59 @@ __device__ __forceinline__ WoopUVW woop_uvw_smem(const float *tkx, const float *
     return r;
 }
 
+// filter of one pair record: shifts the two "definitely outside" bits (slot 2k+1, then slot 2k) into `dropped`
+__device__ __forceinline__ unsigned pair_shift_in(const float4 *rec, float3 pos, float3 dir, float dl, float dl_h, unsigned dropped)
+{
+    const float4 P = rec[0];
+    const float nd = fmaf(P.x, dir.x, fmaf(P.y, dir.y, P.z * dir.z));
+    const float np = fmaf(P.x, pos.x, fmaf(P.y, pos.y, fmaf(P.z, pos.z, -P.w)));
+    const float r = rcp_approx(nd);
+    const float t = -np * r;
+    const float ar = fabsf(r);
+    // plane behind the origin by more than the tolerance: thr = +inf drops both triangles
+    const float thr = (t < -(dl * ar)) ? __int_as_float(0x7f800000) : -(dl_h * ar);
+    const float hx = fmaf(t, dir.x, pos.x), hy = fmaf(t, dir.y, pos.y), hz = fmaf(t, dir.z, pos.z);
+#pragma unroll
+    for (int j = 1; j >= 0; --j) {
+        const float4 e0 = rec[1 + 3 * j], e1 = rec[2 + 3 * j], e2 = rec[3 + 3 * j];
+        const float d0 = fmaf(e0.x, hx, fmaf(e0.y, hy, fmaf(e0.z, hz, e0.w)));
+        const float d1 = fmaf(e1.x, hx, fmaf(e1.y, hy, fmaf(e1.z, hz, e1.w)));
+        const float d2 = fmaf(e2.x, hx, fmaf(e2.y, hy, fmaf(e2.z, hz, e2.w)));
+        // shift the sign of (min_i d_i - thr) into the mask: 1 = definitely outside.  inf - inf and NaN inputs
+        // give the canonical NaN 0x7fffffff (sign clear), i.e. the triangle is kept.
+        dropped = __funnelshift_l(__float_as_uint(min3f(d0, d1, d2) - thr), dropped, 1);
+    }
+    return dropped;
+}
+
 // phase 1 over n_pairs records (walked backwards, so that slot s ends up at mask bit s): the candidate mask
 __device__ __forceinline__ unsigned sweep_pairs(const float4 *recs, int n_pairs, float3 pos, float3 dir, float dl, float dl_h)
 {
-    const float INF = __int_as_float(0x7f800000);
     unsigned dropped = 0u;
     const float4 *rec = recs + 7 * (n_pairs - 1);
 #pragma unroll 2
-    for (int k = 0; k < n_pairs; ++k, rec -= 7) {
-        const float4 P = rec[0];
-        const float nd = fmaf(P.x, dir.x, fmaf(P.y, dir.y, P.z * dir.z));
-        const float np = fmaf(P.x, pos.x, fmaf(P.y, pos.y, fmaf(P.z, pos.z, -P.w)));
-        const float r = rcp_approx(nd);
-        const float t = -np * r;
-        const float ar = fabsf(r);
-        // plane behind the origin by more than the tolerance: thr = +inf drops both triangles
-        const float thr = (t < -(dl * ar)) ? INF : -(dl_h * ar);
-        const float hx = fmaf(t, dir.x, pos.x), hy = fmaf(t, dir.y, pos.y), hz = fmaf(t, dir.z, pos.z);
-#pragma unroll
-        for (int j = 1; j >= 0; --j) {
-            const float4 e0 = rec[1 + 3 * j], e1 = rec[2 + 3 * j], e2 = rec[3 + 3 * j];
-            const float d0 = fmaf(e0.x, hx, fmaf(e0.y, hy, fmaf(e0.z, hz, e0.w)));
-            const float d1 = fmaf(e1.x, hx, fmaf(e1.y, hy, fmaf(e1.z, hz, e1.w)));
-            const float d2 = fmaf(e2.x, hx, fmaf(e2.y, hy, fmaf(e2.z, hz, e2.w)));
-            // shift the sign of (min_i d_i - thr) into the mask: 1 = definitely outside.  inf - inf and NaN inputs
-            // give the canonical NaN 0x7fffffff (sign clear), i.e. the triangle is kept.
-            dropped = __funnelshift_l(__float_as_uint(min3f(d0, d1, d2) - thr), dropped, 1);
-        }
-    }
+    for (int k = 0; k < n_pairs; ++k, rec -= 7) dropped = pair_shift_in(rec, pos, dir, dl, dl_h, dropped);
     return ~dropped & (n_pairs >= 16 ? 0xffffffffu : (1u << (2 * n_pairs)) - 1u);
 }
 
-// the exact test of one candidate slot: closest t in [0, best], equal t -> lowest triangle index
-__device__ __forceinline__ void small_exact(const SmallScene &S, int slot, const float *tkx, const float *tky, const float *tkz,
-                                            float pkx, float pky, float pkz, const WoopRay &wr, Hit &h)
+// per-ray constants of the exact test against the shared-memory soup
+struct SmallExact {
+    const float *tkx, *tky, *tkz; // soup base pointers offset by the permuted component
+    float pkx, pky, pkz;
+};
+__device__ __forceinline__ SmallExact small_exact_setup(const SmallScene &S, const WoopRay &wr)
 {
-    const int f = S.slot_tri[slot];
-    const WoopUVW q = woop_uvw_smem(tkx, tky, tkz, 9 * f, pkx, pky, pkz, wr.Sx, wr.Sy);
+    SmallExact x;
+    x.tkx = S.soup + wr.kx; x.tky = S.soup + wr.ky; x.tkz = S.soup + wr.kz;
+    x.pkx = sel3(wr.px, wr.py, wr.pz, wr.kx); x.pky = sel3(wr.px, wr.py, wr.pz, wr.ky);
+    x.pkz = sel3(wr.px, wr.py, wr.pz, wr.kz);
+    return x;
+}
+
+// the exact test of triangle f: closest t in [0, best], equal t -> lowest triangle index
+__device__ __forceinline__ void small_exact(const SmallExact &X, int f, const WoopRay &wr, Hit &h)
+{
+    const WoopUVW q = woop_uvw_smem(X.tkx, X.tky, X.tkz, 9 * f, X.pkx, X.pky, X.pkz, wr.Sx, wr.Sy);
     const float U = q.U, V = q.V, W = q.W;
     const bool mixed = (U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f);
     const float det = __fadd_rn(__fadd_rn(U, V), W);
@@ -268,6 +288,57 @@ __device__ __forceinline__ float small_t_lower(const SmallScene &S, int slot, fl
     return fmaxf(fmaf(-dl, fabsf(r), -np * r), -__int_as_float(0x7f800000)); // t - kt; NaN -> -inf
 }
 
+__device__ __forceinline__ int pop_slot(unsigned &lo, unsigned &hi)
+{
+    if (lo) { const int b = 31 - __clz((int)lo); lo ^= 1u << b; return b; }
+    const int b = 31 - __clz((int)hi); hi ^= 1u << b; return 32 + b;
+}
+
+// phase 2: the exact test on the candidate slots (lo, hi), nearest first.  The plane parameter minus the tolerance
+// (t_lo) is a lower bound of a candidate's exact t, so once the best exact hit lies below the t_lo of everything that
+// is left, the rest cannot win (on room.stl this cuts the exact tests per segment from 2.3 to 1.0: the ray's own
+// surface at t ~ 0 and the shell behind the hit drop out).  SKIP: ignore the slots of triangle `skip` (already in h).
+template <bool SKIP>
+__device__ __forceinline__ void small_resolve(const SmallScene &S, unsigned lo, unsigned hi, float3 pos, float3 dir, float dl,
+                                              const SmallExact &X, const WoopRay &wr, int skip, Hit &h)
+{
+    const float INF = __int_as_float(0x7f800000);
+    float k1 = INF, k2 = INF; // the two smallest t_lo ...
+    int s1 = -1, s2 = -1;     // ... and their slots
+    {
+        unsigned mlo = lo, mhi = hi;
+        while (mlo | mhi) {
+            const int slot = pop_slot(mlo, mhi);
+            float key = small_t_lower(S, slot, pos, dir, dl);
+            if (SKIP && S.slot_tri[slot] == skip) key = INF;
+            const bool lt1 = key < k1, lt2 = key < k2;
+            s2 = lt1 ? s1 : (lt2 ? slot : s2);
+            k2 = lt1 ? k1 : (lt2 ? key : k2);
+            s1 = lt1 ? slot : s1;
+            k1 = lt1 ? key : k1;
+        }
+    }
+    int cur = (s1 >= 0 && k1 <= h.t) ? s1 : -1;
+    int stage = 0;
+    while (cur >= 0) {
+        small_exact(X, S.slot_tri[cur], wr, h);
+        if (cur < 32) lo &= ~(1u << cur); else hi &= ~(1u << (cur - 32));
+        int next = -1;
+        if (stage == 0) {
+            if (s2 >= 0 && k2 <= h.t) next = s2;
+        } else if (k2 <= h.t) {
+            // rare: more than two candidates may reach below the best hit -> walk the rest with the bound test
+            while (lo | hi) {
+                const int slot = pop_slot(lo, hi);
+                if (SKIP && S.slot_tri[slot] == skip) continue;
+                if (small_t_lower(S, slot, pos, dir, dl) <= h.t) { next = slot; break; }
+            }
+        }
+        stage = 1;
+        cur = next;
+    }
+}
+
 // WIDE: more than 16 pairs (the candidate mask needs a second word)
 template <bool WIDE>
 __device__ __forceinline__ void closest_hit_small(const SmallScene &S, float3 pos, float3 dir, const WoopRay &wr, Hit &h)
@@ -277,53 +348,61 @@ __device__ __forceinline__ void closest_hit_small(const SmallScene &S, float3 po
     const float dl = (S.extent + fabsf(pos.x) + fabsf(pos.y) + fabsf(pos.z)) * (1.0f / 65536.0f);
     const float dl_h = dl * (sqrt_approx(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z) * 1.001f);
     const int n_lo = WIDE ? 16 : S.n_pairs, n_hi = WIDE ? S.n_pairs - 16 : 0;
-    unsigned lo = sweep_pairs(S.recs, n_lo, pos, dir, dl, dl_h);
-    unsigned hi = WIDE ? sweep_pairs(S.recs + 7 * 16, n_hi, pos, dir, dl, dl_h) : 0u;
+    const unsigned lo = sweep_pairs(S.recs, n_lo, pos, dir, dl, dl_h);
+    const unsigned hi = WIDE ? sweep_pairs(S.recs + 7 * 16, n_hi, pos, dir, dl, dl_h) : 0u;
+    // ---- phase 2 ---------------------------------------------------------------------------------------------
+    const SmallExact X = small_exact_setup(S, wr);
+    small_resolve<false>(S, lo, hi, pos, dir, dl, X, wr, -1, h);
+}
 
-    // ---- phase 2: the exact test, nearest candidates first ---------------------------------------------------
-    // The plane parameter minus the tolerance (t_lo) is a lower bound of a candidate's exact t, so once the best
-    // exact hit lies below the t_lo of everything that is left, the rest cannot win (on room.stl this cuts the
-    // exact tests per segment from 2.3 to 1.0: the ray's own surface at t ~ 0 and the shell behind the hit drop out).
-    const float INF = __int_as_float(0x7f800000);
-    float k1 = INF, k2 = INF; // the two smallest t_lo ...
-    int s1 = -1, s2 = -1;     // ... and their slots
-    {
-        unsigned mlo = lo, mhi = hi;
-        while (mlo | mhi) {
-            int slot;
-            if (mlo) { slot = 31 - __clz((int)mlo); mlo ^= 1u << slot; }
-            else { const int b = 31 - __clz((int)mhi); mhi ^= 1u << b; slot = 32 + b; }
-            const float key = small_t_lower(S, slot, pos, dir, dl);
-            const bool lt1 = key < k1, lt2 = key < k2;
-            s2 = lt1 ? s1 : (lt2 ? slot : s2);
-            k2 = lt1 ? k1 : (lt2 ? key : k2);
-            s1 = lt1 ? slot : s1;
-            k1 = lt1 ? key : k1;
+// Self-re-hit shortcut.  The reference never offsets a reflected ray (kernel.py:94-96), so most segments that start on
+// a surface hit that very triangle again at t ~ 0 (78 % of all room.stl segments).  For a ray standing on triangle f:
+// run the exact test on f alone; if it is hit within tau (path length), only triangles that come within `reach` of f
+// can beat or tie it, and only if they pass within rho = tau + tolerance of the ray origin.  The host lists their
+// pairs per triangle (rfrt_small.cu: interior / boundary neighbours; boundary neighbours are skipped when the origin
+// keeps a clearance from f's edges; for t == 0 only lower indices matter, since ties go to the lowest index).  The
+// few triangles that survive the distance filter get the same exact test as in the full sweep, so the result is again
+// bit-identical.  Returns false (h untouched) when f is not hit that close: the caller then runs the full sweep.
+__device__ __forceinline__ bool small_self_rehit(const SmallScene &S, int f, float3 pos, float3 dir, const WoopRay &wr, Hit &h)
+{
+    const SmallExact X = small_exact_setup(S, wr);
+    Hit hf;
+    hf.t = 1.0e6f; hf.face = -1; hf.slot = -1;
+    small_exact(X, f, wr, hf);
+    const float dlen = sqrt_approx(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z) * 1.001f;
+    if (!(hf.face >= 0 && hf.t * dlen <= S.tau)) return false;
+    h = hf;
+    const float dl = (S.extent + fabsf(pos.x) + fabsf(pos.y) + fabsf(pos.z)) * (1.0f / 65536.0f);
+    const float rho = fmaf(S.tau, 1.01f, 4.0f * dl); // a winner passes this close to pos
+    // clearance of pos from f's own edges (in-plane distances, positive inside)
+    const int fs = S.tri_slot[f];
+    const float4 *fe = S.recs + 7 * (fs >> 1) + 1 + 3 * (fs & 1);
+    const float4 e0 = fe[0], e1 = fe[1], e2 = fe[2];
+    const float clear = min3f(fmaf(e0.x, pos.x, fmaf(e0.y, pos.y, fmaf(e0.z, pos.z, e0.w))),
+                              fmaf(e1.x, pos.x, fmaf(e1.y, pos.y, fmaf(e1.z, pos.z, e1.w))),
+                              fmaf(e2.x, pos.x, fmaf(e2.y, pos.y, fmaf(e2.z, pos.z, e2.w))));
+    const uint4 nb = S.nbr[f];
+    const bool inner = clear >= S.erode + rho; // false for NaN
+    unsigned m = (hf.t == 0.0f) ? (inner ? nb.z : (nb.z | nb.w)) : (inner ? nb.x : (nb.x | nb.y));
+    while (m) {
+        const int k = 31 - __clz((int)m);
+        m ^= 1u << k;
+        const float4 *rec = S.recs + 7 * k;
+        const float4 P = rec[0];
+        const float np = fmaf(P.x, pos.x, fmaf(P.y, pos.y, fmaf(P.z, pos.z, -P.w)));
+        if (fabsf(np) > rho) continue; // the pair's plane is too far (NaN stays)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float4 g0 = rec[1 + 3 * j], g1 = rec[2 + 3 * j], g2 = rec[3 + 3 * j];
+            const float d = min3f(fmaf(g0.x, pos.x, fmaf(g0.y, pos.y, fmaf(g0.z, pos.z, g0.w))),
+                                  fmaf(g1.x, pos.x, fmaf(g1.y, pos.y, fmaf(g1.z, pos.z, g1.w))),
+                                  fmaf(g2.x, pos.x, fmaf(g2.y, pos.y, fmaf(g2.z, pos.z, g2.w))));
+            if (d < -rho) continue; // pos lies farther than rho outside one edge (NaN stays)
+            const int g = S.slot_tri[2 * k + j];
+            if (g != f) small_exact(X, g, wr, h);
         }
     }
-    const float *tkx = S.soup + wr.kx, *tky = S.soup + wr.ky, *tkz = S.soup + wr.kz;
-    const float pkx = sel3(wr.px, wr.py, wr.pz, wr.kx), pky = sel3(wr.px, wr.py, wr.pz, wr.ky),
-                pkz = sel3(wr.px, wr.py, wr.pz, wr.kz);
-    int cur = s1;
-    int stage = 0;
-    while (cur >= 0) {
-        small_exact(S, cur, tkx, tky, tkz, pkx, pky, pkz, wr, h);
-        if (cur < 32) lo &= ~(1u << cur); else hi &= ~(1u << (cur - 32));
-        int next = -1;
-        if (stage == 0) {
-            if (s2 >= 0 && k2 <= h.t) next = s2;
-        } else if (k2 <= h.t) {
-            // rare: more than two candidates may reach below the best hit -> walk the rest with the bound test
-            while (lo | hi) {
-                int slot;
-                if (lo) { slot = 31 - __clz((int)lo); lo ^= 1u << slot; }
-                else { const int b = 31 - __clz((int)hi); hi ^= 1u << b; slot = 32 + b; }
-                if (small_t_lower(S, slot, pos, dir, dl) <= h.t) { next = slot; break; }
-            }
-        }
-        stage = 1;
-        cur = next;
-    }
+    return true;
 }
 
 // One receiver as seen by the kernels: its fp32 world-space vertices plus the shared unit-icosphere BVH.

@@ -19,8 +19,10 @@ def _tables(soup):
     recs = np.zeros((32, 28), dtype=np.float32)
     slot_tri = np.zeros(64, dtype=np.int32)
     n_pairs, extent = ctypes.c_int32(), ctypes.c_float()
+    nbr = np.zeros((max(soup.shape[0], 1), 4), dtype=np.uint32)
     rc = lib.rfrt_small_scene_tables(soup.ctypes.data, soup.shape[0], recs.ctypes.data, slot_tri.ctypes.data,
-                                     ctypes.byref(n_pairs), ctypes.byref(extent))
+                                     ctypes.byref(n_pairs), ctypes.byref(extent), nbr.ctypes.data)
+    _tables.nbr = nbr[:soup.shape[0]]
     return rc, recs[:n_pairs.value], slot_tri[:2 * n_pairs.value], extent.value
 
 
@@ -113,3 +115,39 @@ def test_tables_refuse_scenes_that_do_not_fit():
     assert rc == -1
     rc, recs, slot_tri, _ = _tables(np.zeros((0, 9), dtype=np.float32))
     assert rc == 0 and recs.shape[0] == 0
+
+
+def test_self_rehit_neighbour_masks(repo_root):
+    """The self-re-hit shortcut (small_self_rehit): when the ray's own triangle f is hit again within tau, the
+    overall closest hit must be f or a triangle of a neighbour pair of f (rfrt_small_scene_tables' h_nbr)."""
+    soup = geometry.load_stl_soup(f"{repo_root}/models/room.stl").reshape(-1, 9)
+    rc, recs, slot_tri, extent = _tables(soup)
+    nbr = _tables.nbr[:, 0] | _tables.nbr[:, 1]  # interior | boundary neighbours
+    assert np.all((_tables.nbr[:, 2] | _tables.nbr[:, 3]) & ~nbr == 0)
+    n, B, tx = 20_000, 8, [10.0, 0.0, 5.0]
+    out = cpu.trace_paths(soup, None, tx, B, 0, n)
+    pos, dirs, face = _segments(soup, tx, B, n)
+    # previous face of every alive segment (same ordering as _segments: bounce-major over alive rays)
+    hit_tri = out["hit_tri"]
+    alive = np.ones(n, dtype=bool)
+    prev = []
+    last = np.full(n, -1)
+    for b in range(B):
+        prev.append(last[alive])
+        last = np.where(alive, hit_tri[:, b], last)
+        alive = alive & (hit_tri[:, b] >= 0)
+    prev = np.concatenate(prev)
+    tau = 1.0e-4 * extent
+    checked = 0
+    for i in np.nonzero(prev >= 0)[0][:60_000]:
+        f = int(prev[i])
+        hit, t_f, _ = cpu.query(soup[f:f + 1], pos[i], dirs[i])
+        if not hit or t_f * float(np.linalg.norm(dirs[i])) * 1.001 > tau:
+            continue
+        g = int(face[i])
+        assert g >= 0
+        if g != f:
+            pairs = {k for k in range(len(slot_tri) // 2) if g in slot_tri[2 * k:2 * k + 2]}
+            assert any(nbr[f] >> k & 1 for k in pairs), (i, f, g)
+        checked += 1
+    assert checked > 20_000
