@@ -120,7 +120,8 @@ __device__ __forceinline__ float3 ray_direction(uint32_t tid)
 struct WoopRay {
     int kx, ky, kz;
     float Sx, Sy, Sz;
-    float px, py, pz; // ray origin
+    float px, py, pz;    // ray origin
+    float pkx, pky, pkz; // ... permuted (p[kx], p[ky], p[kz])
 };
 
 __device__ __forceinline__ float sel3(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
@@ -128,20 +129,25 @@ __device__ __forceinline__ float sel3(float x, float y, float z, int k) { return
 __device__ __forceinline__ WoopRay woop_setup(float3 p, float3 d)
 {
     WoopRay r;
-    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-    int kz;
-    if (ax > ay && ax > az) kz = 0;
-    else if (ay > az) kz = 1;
-    else kz = 2;
-    int kx = kz + 1; if (kx == 3) kx = 0;
-    int ky = kx + 1; if (ky == 3) ky = 0;
-    float dkz = sel3(d.x, d.y, d.z, kz);
-    if (dkz < 0.0f) { int tmp = kx; kx = ky; ky = tmp; }
-    r.kx = kx; r.ky = ky; r.kz = kz;
-    r.Sx = __fdiv_rn(sel3(d.x, d.y, d.z, kx), dkz);
-    r.Sy = __fdiv_rn(sel3(d.x, d.y, d.z, ky), dkz);
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    // kz = dominant axis (x only if strictly greater than both, else y if |y| > |z|, else z); kx, ky follow cyclically
+    const bool k0 = ax > ay && ax > az;
+    const bool k1 = !k0 && ay > az;
+    const float dkz = k0 ? d.x : (k1 ? d.y : d.z);
+    float dkx = k0 ? d.y : (k1 ? d.z : d.x), dky = k0 ? d.z : (k1 ? d.x : d.y);
+    float pkx = k0 ? p.y : (k1 ? p.z : p.x), pky = k0 ? p.z : (k1 ? p.x : p.y);
+    int kx = k0 ? 1 : (k1 ? 2 : 0), ky = k0 ? 2 : (k1 ? 0 : 1);
+    if (dkz < 0.0f) { // swap kx and ky to preserve the winding
+        float tf = dkx; dkx = dky; dky = tf;
+        tf = pkx; pkx = pky; pky = tf;
+        int ti = kx; kx = ky; ky = ti;
+    }
+    r.kx = kx; r.ky = ky; r.kz = k0 ? 0 : (k1 ? 1 : 2);
+    r.Sx = __fdiv_rn(dkx, dkz);
+    r.Sy = __fdiv_rn(dky, dkz);
     r.Sz = __fdiv_rn(1.0f, dkz);
     r.px = p.x; r.py = p.y; r.pz = p.z;
+    r.pkx = pkx; r.pky = pky; r.pkz = k0 ? p.x : (k1 ? p.y : p.z);
     return r;
 }
 

@@ -36,6 +36,7 @@ struct TraceParams {
     const float *rx_verts;
     const double *rx_centers;
     int64_t n_rx;
+    float rx_lo[3], rx_hi[3];   // padded bounds of all receivers (cheap pre-test of a segment's box)
     int32_t n_unit;
     int32_t n_faces;
     float rx_radius;
@@ -53,6 +54,7 @@ struct TraceParams {
     float *hit_t;
     int64_t dump_begin;
     int32_t stack_depth;
+    int32_t fetch_block; // rays a warp claims per atomic (32..256, sized so that every warp sees >= 8 blocks)
     int32_t short_min; // small scenes: run a self-re-hit trip when at least this many lanes stand on a surface
 };
 
@@ -147,16 +149,24 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
     unsigned int n_seg = 0, n_hit = 0;
     unsigned long long csum = 0ull;
 
+    // rays are handed out in blocks per warp: one atomic per block instead of one per trip
+    const int FETCH_BLOCK = P.fetch_block;
+    int64_t blk_next = 0, blk_end = 0; // warp-uniform
+
     for (;;) {
-        unsigned idle = __ballot_sync(FULL, !has_ray);
+        const unsigned idle = __ballot_sync(FULL, !has_ray);
         if (idle != 0u && !exhausted) {
-            int cnt = __popc(idle);
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&P.counters[RFRT_CTR_NEXT_RAY], (unsigned long long)cnt);
-            base = __shfl_sync(FULL, base, 0);
+            if (blk_next == blk_end) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&P.counters[RFRT_CTR_NEXT_RAY], (unsigned long long)FETCH_BLOCK);
+                base = __shfl_sync(FULL, base, 0);
+                blk_next = (int64_t)base;
+                blk_end = blk_next + FETCH_BLOCK < P.chunk_n ? blk_next + FETCH_BLOCK : P.chunk_n;
+                if (blk_next >= P.chunk_n) { exhausted = true; blk_end = blk_next; }
+            }
             if (!has_ray) {
-                int64_t r = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
-                if (r < P.chunk_n) {
+                const int64_t r = blk_next + __popc(idle & ((1u << lane) - 1u));
+                if (r < blk_end) { // (the lanes beyond the end of the block wait one trip)
                     float4 d4 = __ldg(P.dirs + r);
                     dir = make_float3(d4.x, d4.y, d4.z);
                     pos = P.tx;
@@ -166,7 +176,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
                     has_ray = true;
                 }
             }
-            if ((int64_t)base + cnt >= P.chunk_n) exhausted = true;
+            blk_next = blk_next + __popc(idle) < blk_end ? blk_next + __popc(idle) : blk_end;
         }
         if (!__any_sync(FULL, has_ray)) break;
         // SMALL: a trip is either a self-re-hit trip (only the lanes standing on a surface work; cheap) or a full
@@ -179,12 +189,14 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
         Hit h;
         h.t = 1.0e6f; h.face = -1; h.slot = -1;
         bool resolved = true;
+        SlabRay sr_env; // BVH variants: reused by the receiver enumeration
+        sr_env.ix = sr_env.iy = sr_env.iz = sr_env.ox = sr_env.oy = sr_env.oz = 0.0f;
         if (SMALL) {
             if (shortcut) resolved = small_self_rehit(S, on_face, pos, dir, wr, h);
             else closest_hit_small<SMALL == 2>(S, pos, dir, wr, h);
         } else {
-            SlabRay sr = slab_setup(pos, dir);
-            closest_hit(P.nodes, P.tris, P.n_tris, wr, sr, stack, stack_t, STRIDE, h);
+            sr_env = slab_setup(pos, dir);
+            closest_hit(P.nodes, P.tris, P.n_tris, wr, sr_env, stack, stack_t, STRIDE, h);
         }
         if (!resolved) {
             on_face = -1; // not a self re-hit: this segment goes through the next full sweep
@@ -199,10 +211,15 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
             if (P.n_rx == 1) {
                 rx_filter_and_emit(P, 0, pos, dir, t_limit, gid, bounce);
             } else {
-                // enumerate every receiver whose box overlaps the segment [0, t_limit]
-                SlabRay sr = slab_setup(pos, dir);
+                // enumerate every receiver whose box overlaps the segment [0, t_limit]; first the segment's own box
+                // against the bounds of all receivers (no division: most segments of a sparse receiver set stop here)
+                const float ex = fmaf(dir.x, t_limit, pos.x), ey = fmaf(dir.y, t_limit, pos.y), ez = fmaf(dir.z, t_limit, pos.z);
+                const bool near_rx = fminf(pos.x, ex) <= P.rx_hi[0] && fmaxf(pos.x, ex) >= P.rx_lo[0] &&
+                                     fminf(pos.y, ey) <= P.rx_hi[1] && fmaxf(pos.y, ey) >= P.rx_lo[1] &&
+                                     fminf(pos.z, ez) <= P.rx_hi[2] && fmaxf(pos.z, ez) >= P.rx_lo[2];
+                const SlabRay sr = SMALL ? slab_setup_fast(pos, dir) : sr_env;
                 int sp = 0;
-                int node = 0;
+                int node = near_rx ? 0 : -1;
                 while (node >= 0) {
                     const float4 *np = reinterpret_cast<const float4 *>(P.rx_nodes + node);
                     float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
@@ -574,6 +591,10 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     P.rx_verts = r ? r->verts : nullptr; P.rx_centers = r ? r->centers : nullptr;
     P.n_rx = r ? r->n_receivers : 0; P.n_unit = r ? r->n_unit : 0; P.n_faces = r ? r->n_faces : 0;
     P.rx_radius = r ? (float)r->radius : 0.0f;
+    for (int k = 0; k < 3; ++k) {
+        P.rx_lo[k] = r ? r->bvh.bounds[k] - r->bvh.pad : 0.0f;
+        P.rx_hi[k] = r ? r->bvh.bounds[3 + k] + r->bvh.pad : 0.0f;
+    }
     P.tx = make_float3(h_tx_pos[0], h_tx_pos[1], h_tx_pos[2]);
     P.max_bounces = max_bounces;
     P.dirs = (const float4 *)d_dir_scratch;
@@ -615,6 +636,8 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
         int g = grid;
         int64_t need = (cn + TRACE_THREADS - 1) / TRACE_THREADS;
         if (need < g) g = (int)need;
+        int64_t fb = cn / ((int64_t)g * (TRACE_THREADS / 32) * 8);
+        P.fetch_block = fb < 32 ? 32 : (fb > 256 ? 256 : (int)fb);
         kern<<<g, TRACE_THREADS, smem, stream>>>(P);
     }
     RFRT_CUDA(cudaGetLastError());

@@ -26,6 +26,22 @@ __device__ __forceinline__ SlabRay slab_setup(float3 p, float3 d)
     return s;
 }
 
+// rcp.approx instead of IEEE division: for traversals whose boxes carry >= 1e-3 of padding and whose results are
+// re-verified exactly afterwards (receiver enumeration)
+__device__ __forceinline__ SlabRay slab_setup_fast(float3 p, float3 d)
+{
+    SlabRay s;
+    const float tiny = 1.0e-18f;
+    float dx = fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x;
+    float dy = fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y;
+    float dz = fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s.ix) : "f"(dx));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s.iy) : "f"(dy));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s.iz) : "f"(dz));
+    s.ox = p.x * s.ix; s.oy = p.y * s.iy; s.oz = p.z * s.iz;
+    return s;
+}
+
 // entry distance of the padded box; hit iff  max(tnear,0) <= min(tfar, t_max).
 __device__ __forceinline__ bool slab_hit(const SlabRay &s, float lx, float ly, float lz, float hx, float hy, float hz,
                                          float t_max, float &t_near)
@@ -257,8 +273,7 @@ __device__ __forceinline__ SmallExact small_exact_setup(const SmallScene &S, con
 {
     SmallExact x;
     x.tkx = S.soup + wr.kx; x.tky = S.soup + wr.ky; x.tkz = S.soup + wr.kz;
-    x.pkx = sel3(wr.px, wr.py, wr.pz, wr.kx); x.pky = sel3(wr.px, wr.py, wr.pz, wr.ky);
-    x.pkz = sel3(wr.px, wr.py, wr.pz, wr.kz);
+    x.pkx = wr.pkx; x.pky = wr.pky; x.pkz = wr.pkz;
     return x;
 }
 
