@@ -326,7 +326,9 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "kernel": "k_trace_env", "kernel_ms": k_ms, "peak_source": peak_src,
                              "algorithmic_bytes_per_segment": BYTES_PER_SEGMENT,
-                             "note": "44-triangle scene is L1/L2 resident: the binding limit is the FP32/issue pipe, not HBM"},
+                             "note": "the 44-triangle scene is resident in shared memory: HBM traffic is only the direction "
+                                     "buffer, the binding limit is instruction issue (profiles/README.md), so frac can exceed 1",
+                             "traffic_note": "ncu dram__bytes_read+write per launch at 268435456 rays (profiles/ncu_summary.json)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches * 1,
                 "kernel_ms": {"k_gen_dirs": g_ms, "k_trace_env": k_ms, "step": total_ms / args.steps}}
         if args.cpu_sample > 0:

@@ -69,6 +69,26 @@ __global__ void k_bin_ordered(const int32_t *__restrict__ rx, const int64_t *__r
     }
 }
 
+// same result with one CTA per receiver: thread j owns the bins b with b % blockDim == j and walks the receiver's
+// records in order, so every bin still sees its additions in ray-id order (few receivers, many records each)
+__global__ void __launch_bounds__(256) k_bin_ordered_cta(const int32_t *__restrict__ rx, const int64_t *__restrict__ bin,
+                                                         const double *__restrict__ amp, int64_t n,
+                                                         const unsigned long long *d_n, int64_t n_bins, double *ir)
+{
+    const int64_t k = blockIdx.x;
+    if (d_n && (int64_t)*d_n < n) n = (int64_t)*d_n;
+    int64_t lo = 0, hi = n; // lower_bound of k
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (rx[mid] < k) lo = mid + 1; else hi = mid;
+    }
+    double *row = ir + k * n_bins;
+    for (int64_t i = lo; i < n && rx[i] == k; ++i) {
+        const int64_t b = bin[i];
+        if (b >= 0 && b < n_bins && (int)(b % blockDim.x) == (int)threadIdx.x) row[b] = __dadd_rn(row[b], amp[i]);
+    }
+}
+
 // s_tx[m] = sin((2*pi*f) * t_m),  t = np.linspace(0, window, n_bins)
 __global__ void k_stx_table(int64_t n_bins, double window, double carrier, double *table)
 {
@@ -251,8 +271,12 @@ extern "C" int rfrt_bin_ir(const int32_t *d_rec_rx, const int64_t *d_rec_bin, co
     }
     if (n_records == 0 || n_bins == 0) return RFRT_OK;
     if (deterministic) {
-        k_bin_ordered<<<(unsigned)((n_receivers + 127) / 128), 128, 0, stream>>>(d_rec_rx, d_rec_bin, d_rec_amp,
-                                                                                 n_records, d_n, n_receivers, n_bins, d_ir);
+        if (n_receivers <= 2048 && n_records >= 8 * n_receivers)
+            k_bin_ordered_cta<<<(unsigned)n_receivers, 256, 0, stream>>>(d_rec_rx, d_rec_bin, d_rec_amp, n_records, d_n,
+                                                                          n_bins, d_ir);
+        else
+            k_bin_ordered<<<(unsigned)((n_receivers + 127) / 128), 128, 0, stream>>>(d_rec_rx, d_rec_bin, d_rec_amp,
+                                                                                     n_records, d_n, n_receivers, n_bins, d_ir);
     } else {
         const size_t smem = sizeof(double) * (size_t)n_bins;
         if (n_receivers <= 4 && smem <= 200 * 1024 && n_records >= (1 << 16)) {
