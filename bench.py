@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.02)
 
     def stop(self):
         self._stop_evt.set()
@@ -314,6 +314,8 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
                 traffic = json.load(f).get("k_trace_env", {}).get("dram_bytes_per_launch")
+            if traffic is not None:
+                traffic = int(traffic * R / (1 << 28))  # captured at 2^28 rays; it is the direction buffer, linear in rays
         except Exception:
             pass
         line = {"metric": "traced ray-segments/s", "value": value, "unit": "segments/s", "n_gpus": world,
