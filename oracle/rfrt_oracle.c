@@ -92,14 +92,15 @@ static void det_sincos(double x, double *s_out, double *c_out)
 {
     double kf = floor(x * DM_TWO_OVER_PI + 0.5);
     int k = (int)kf;
-    double r = (x - kf * DM_PIO2_1) - kf * DM_PIO2_1T;
+    /* every step is one IEEE fused multiply-add (fma() here, DFMA on the GPU): identical bits on both sides */
+    double r = fma(-kf, DM_PIO2_1T, fma(-kf, DM_PIO2_1, x));
     double w = r * r;
     double ps = DM_S[7];
-    for (int j = 6; j >= 0; --j) ps = DM_S[j] + w * ps;
-    double sn = r + (r * w) * ps;
+    for (int j = 6; j >= 0; --j) ps = fma(w, ps, DM_S[j]);
+    double sn = fma(r * w, ps, r);
     double pc = DM_C[8];
-    for (int j = 7; j >= 0; --j) pc = DM_C[j] + w * pc;
-    double cs = 1.0 + w * pc;
+    for (int j = 7; j >= 0; --j) pc = fma(w, pc, DM_C[j]);
+    double cs = fma(w, pc, 1.0);
     switch (k & 3) {
     case 0: *s_out = sn; *c_out = cs; break;
     case 1: *s_out = cs; *c_out = -sn; break;
@@ -113,7 +114,7 @@ static double det_asin_small(double x)
 {
     double w = x * x;
     double p = DM_A[28];
-    for (int j = 27; j >= 0; --j) p = DM_A[j] + w * p;
+    for (int j = 27; j >= 0; --j) p = fma(w, p, DM_A[j]);
     return x * p;
 }
 

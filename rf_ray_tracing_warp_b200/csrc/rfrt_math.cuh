@@ -30,9 +30,26 @@ __device__ __forceinline__ float randf(uint32_t &state)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Deterministic fp64 sin / cos / acos: IEEE + - * / sqrt / floor only, Horner in a fixed order.
+// Deterministic fp64 sin / cos / acos: IEEE + - * / sqrt / floor / fma only, Horner in a fixed order.
 // Identical bits on any IEEE machine (no libm / libdevice involved).
 // ---------------------------------------------------------------------------------------------
+// polynomial coefficients live in the constant bank so that each Horner step is ONE DFMA with a constant operand
+// (as immediates every fp64 constant costs two extra UMOV issue slots)
+__constant__ double c_det_sin[8] = {-0.16666666666666666, 0.008333333333333333, -0.0001984126984126984, 2.7557319223985893e-06,
+                                    -2.505210838544172e-08, 1.6059043836821613e-10, -7.647163731819816e-13,
+                                    2.8114572543455206e-15};
+__constant__ double c_det_cos[9] = {-0.5, 0.041666666666666664, -0.001388888888888889, 2.48015873015873e-05,
+                                    -2.755731922398589e-07, 2.08767569878681e-09, -1.1470745597729725e-11,
+                                    4.779477332387385e-14, -1.5619206968586225e-16};
+__constant__ double c_det_asin[29] = {
+    1.0, 0.16666666666666666, 0.075, 0.044642857142857144, 0.030381944444444444, 0.022372159090909092,
+    0.017352764423076924, 0.01396484375, 0.011551800896139705, 0.009761609529194078, 0.008390335809616815,
+    0.0073125258735988454, 0.006447210311889649, 0.005740037670841924, 0.005153309682319905,
+    0.004660143486915096, 0.004240907093679363, 0.003880964558837669, 0.0035692053938259347,
+    0.003297059503473485, 0.0030578216492580306, 0.002846178401108942, 0.00265787063820729,
+    0.0024894486782468836, 0.002338091892111975, 0.0022014739737101384, 0.0020776610325181676,
+    0.0019650336162772837, 0.0018622264064031275};
+
 __device__ __forceinline__ void det_sincos(double x, double &s_out, double &c_out)
 {
     const double TWO_OVER_PI = 0.6366197723675814;
@@ -40,27 +57,16 @@ __device__ __forceinline__ void det_sincos(double x, double &s_out, double &c_ou
     const double PIO2_1T = 6.077100506506192e-11; // pi/2 - PIO2_1
     double kf = floor(__dadd_rn(__dmul_rn(x, TWO_OVER_PI), 0.5));
     int k = (int)kf;
-    double r = __dsub_rn(__dsub_rn(x, __dmul_rn(kf, PIO2_1)), __dmul_rn(kf, PIO2_1T));
+    double r = __fma_rn(-kf, PIO2_1T, __fma_rn(-kf, PIO2_1, x));
     double w = __dmul_rn(r, r);
-    double ps = 2.8114572543455206e-15;
-    ps = __dadd_rn(-7.647163731819816e-13, __dmul_rn(w, ps));
-    ps = __dadd_rn(1.6059043836821613e-10, __dmul_rn(w, ps));
-    ps = __dadd_rn(-2.505210838544172e-08, __dmul_rn(w, ps));
-    ps = __dadd_rn(2.7557319223985893e-06, __dmul_rn(w, ps));
-    ps = __dadd_rn(-0.0001984126984126984, __dmul_rn(w, ps));
-    ps = __dadd_rn(0.008333333333333333, __dmul_rn(w, ps));
-    ps = __dadd_rn(-0.16666666666666666, __dmul_rn(w, ps));
-    double sn = __dadd_rn(r, __dmul_rn(__dmul_rn(r, w), ps));
-    double pc = -1.5619206968586225e-16;
-    pc = __dadd_rn(4.779477332387385e-14, __dmul_rn(w, pc));
-    pc = __dadd_rn(-1.1470745597729725e-11, __dmul_rn(w, pc));
-    pc = __dadd_rn(2.08767569878681e-09, __dmul_rn(w, pc));
-    pc = __dadd_rn(-2.755731922398589e-07, __dmul_rn(w, pc));
-    pc = __dadd_rn(2.48015873015873e-05, __dmul_rn(w, pc));
-    pc = __dadd_rn(-0.001388888888888889, __dmul_rn(w, pc));
-    pc = __dadd_rn(0.041666666666666664, __dmul_rn(w, pc));
-    pc = __dadd_rn(-0.5, __dmul_rn(w, pc));
-    double cs = __dadd_rn(1.0, __dmul_rn(w, pc));
+    double ps = c_det_sin[7];
+#pragma unroll
+    for (int j = 6; j >= 0; --j) ps = __fma_rn(w, ps, c_det_sin[j]);
+    double sn = __fma_rn(__dmul_rn(r, w), ps, r);
+    double pc = c_det_cos[8];
+#pragma unroll
+    for (int j = 7; j >= 0; --j) pc = __fma_rn(w, pc, c_det_cos[j]);
+    double cs = __fma_rn(w, pc, 1.0);
     switch (k & 3) {
     case 0: s_out = sn; c_out = cs; break;
     case 1: s_out = cs; c_out = -sn; break;
@@ -71,18 +77,10 @@ __device__ __forceinline__ void det_sincos(double x, double &s_out, double &c_ou
 
 __device__ __forceinline__ double det_asin_small(double x)
 {
-    const double A[29] = {
-        1.0, 0.16666666666666666, 0.075, 0.044642857142857144, 0.030381944444444444, 0.022372159090909092,
-        0.017352764423076924, 0.01396484375, 0.011551800896139705, 0.009761609529194078, 0.008390335809616815,
-        0.0073125258735988454, 0.006447210311889649, 0.005740037670841924, 0.005153309682319905,
-        0.004660143486915096, 0.004240907093679363, 0.003880964558837669, 0.0035692053938259347,
-        0.003297059503473485, 0.0030578216492580306, 0.002846178401108942, 0.00265787063820729,
-        0.0024894486782468836, 0.002338091892111975, 0.0022014739737101384, 0.0020776610325181676,
-        0.0019650336162772837, 0.0018622264064031275};
     double w = __dmul_rn(x, x);
-    double p = A[28];
+    double p = c_det_asin[28];
 #pragma unroll
-    for (int j = 27; j >= 0; --j) p = __dadd_rn(A[j], __dmul_rn(w, p));
+    for (int j = 27; j >= 0; --j) p = __fma_rn(w, p, c_det_asin[j]);
     return __dmul_rn(x, p);
 }
 

@@ -54,7 +54,7 @@ struct TraceParams {
     float *hit_t;
     int64_t dump_begin;
     int32_t stack_depth;
-    int32_t fetch_block; // rays a warp claims per atomic (32..256, sized so that every warp sees >= 8 blocks)
+    int32_t fetch_block; // rays a warp claims per atomic (32..256, sized so that every warp sees >= 64 blocks)
     int32_t short_min; // small scenes: run a self-re-hit trip when at least this many lanes stand on a surface
 };
 
@@ -154,8 +154,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
     int64_t blk_next = 0, blk_end = 0; // warp-uniform
 
     for (;;) {
-        const unsigned idle = __ballot_sync(FULL, !has_ray);
-        if (idle != 0u && !exhausted) {
+        unsigned idle = __ballot_sync(FULL, !has_ray);
+        // (second pass: the block ran out in the middle of the refill -> continue from a fresh block in the same trip)
+#pragma unroll 1
+        for (int pass = 0; pass < 2 && idle != 0u && !exhausted; ++pass) {
             if (blk_next == blk_end) {
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(&P.counters[RFRT_CTR_NEXT_RAY], (unsigned long long)FETCH_BLOCK);
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
             }
             if (!has_ray) {
                 const int64_t r = blk_next + __popc(idle & ((1u << lane) - 1u));
-                if (r < blk_end) { // (the lanes beyond the end of the block wait one trip)
+                if (r < blk_end) {
                     float4 d4 = __ldg(P.dirs + r);
                     dir = make_float3(d4.x, d4.y, d4.z);
                     pos = P.tx;
@@ -177,6 +179,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
                 }
             }
             blk_next = blk_next + __popc(idle) < blk_end ? blk_next + __popc(idle) : blk_end;
+            idle = __ballot_sync(FULL, !has_ray);
         }
         if (!__any_sync(FULL, has_ray)) break;
         // SMALL: a trip is either a self-re-hit trip (only the lanes standing on a surface work; cheap) or a full
@@ -636,7 +639,7 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
         int g = grid;
         int64_t need = (cn + TRACE_THREADS - 1) / TRACE_THREADS;
         if (need < g) g = (int)need;
-        int64_t fb = cn / ((int64_t)g * (TRACE_THREADS / 32) * 8);
+        int64_t fb = cn / ((int64_t)g * (TRACE_THREADS / 32) * 64);
         P.fetch_block = fb < 32 ? 32 : (fb > 256 ? 256 : (int)fb);
         kern<<<g, TRACE_THREADS, smem, stream>>>(P);
     }

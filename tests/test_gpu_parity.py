@@ -250,3 +250,30 @@ def test_checksum_sweep_equals_bvh_at_full_size(torch_cuda, room_stl, almost_emp
     assert res[False]["segments"] == res[True]["segments"] > n_big
     assert res[False]["env_hits"] == res[True]["env_hits"]
     assert res[False]["checksum"] == res[True]["checksum"]
+
+
+def test_fused_directions_equal_buffered_directions(torch_cuda, room_stl):
+    """rfrt_trace generates the directions inside the kernel (default) or reads them from a caller buffer filled by
+    rfrt_ray_directions (RFRT_FLAG_DIRS_READY): both must give the same candidates and records."""
+    from rf_ray_tracing_warp_b200 import load_mesh
+    n, B, tx = (1 << 18) + 777, 5, [10, 0, 5]
+    rxs = np.array([[3.0, 6.0, 5.0], [-8.0, 8.0, 3.0]])
+    tr = _tracer(load_mesh(room_stl), B, n)
+    begin, end = 1000, 1000 + n
+    out = {}
+    for mode in ("fused", "buffer"):
+        job = tr.make_job(rxs, 0.6, want_paths=True)
+        dirs = None
+        if mode == "buffer":
+            dirs = torch_cuda.empty((n, 4), dtype=torch_cuda.float32, device=tr.device)
+            tr.ray_directions(begin, end, out=dirs)
+        job.enqueue(tx, 1.0, ray_range=(begin, end), dirs=dirs)
+        c = job.counters()
+        m = c["records"]
+        order = torch_cuda.argsort((job.rec["rx"][:m].to(torch_cuda.int64) << 32) | (job.rec["ray"][:m].to(torch_cuda.int64) & 0xFFFFFFFF))
+        out[mode] = (c, {k: v[:m][order].cpu().numpy() for k, v in job.rec.items() if v is not None})
+        job.close()
+    assert out["fused"][0] == out["buffer"][0] and out["fused"][0]["records"] > 100
+    for k in out["fused"][1]:
+        a, b = out["fused"][1][k], out["buffer"][1][k]
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), k
