@@ -55,6 +55,7 @@ enum rfrt_status {
 #define RFRT_FLAG_NONE 0u
 #define RFRT_FLAG_FORCE_BVH 2u  /* always walk the BVH (default: scenes of <= 64 triangles use the lockstep sweep) */
 #define RFRT_FLAG_DIRS_READY 1u /* d_dir_scratch already holds rfrt_ray_directions(ray_begin, ray_end): one wave */
+#define RFRT_FLAG_NO_RAY_SORT 16u /* BVH scenes: keep ray-id order (default: each wave is traced in direction-coherent order) */
 #define RFRT_FLAG_CHECKSUM 8u   /* also accumulate RFRT_CTR_CHECKSUM (costs a few instructions per segment) */
 
 #define RFRT_SMALL_MAX_TRIS 64  /* scenes that fit this many filter slots take the lockstep sweep instead of the BVH walk */

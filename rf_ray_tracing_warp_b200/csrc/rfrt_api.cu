@@ -223,6 +223,9 @@ extern "C" int rfrt_mesh_destroy(rfrt_handle mesh)
     if (m->normals) cudaFree(m->normals);
     if (m->face_normals) cudaFree(m->face_normals);
     if (m->small) cudaFree(m->small);
+    if (m->ray_keys[0]) cudaFree(m->ray_keys[0]);
+    if (m->ray_keys[1]) cudaFree(m->ray_keys[1]);
+    if (m->ray_hist) cudaFree(m->ray_hist);
     delete m;
     return RFRT_OK;
 }

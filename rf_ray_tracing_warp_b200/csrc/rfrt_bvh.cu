@@ -390,4 +390,22 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
     return RFRT_OK;
 }
 
+// LSD radix sort of 64-bit keys on bits [shift, shift + 8*passes): returns the buffer holding the result (a or b).
+// hist must hold 256 * sort_hist_blocks(n) counters.
+int64_t sort_hist_blocks(int64_t n) { return (n + SORT_TILE - 1) / SORT_TILE; }
+
+uint64_t *radix_sort_u64(uint64_t *a, uint64_t *b, uint32_t *hist, int64_t n, int shift, int passes, cudaStream_t stream)
+{
+    const int nblocks = (int)sort_hist_blocks(n);
+    uint64_t *src = a, *dst = b;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int sh = shift + 8 * pass;
+        k_sort_hist<<<nblocks, SORT_THREADS, 0, stream>>>(src, n, sh, hist, nblocks);
+        k_scan_exclusive<<<1, 1024, 0, stream>>>(hist, 256ll * nblocks);
+        k_sort_scatter<<<nblocks, SORT_THREADS, 0, stream>>>(src, dst, n, sh, hist, nblocks);
+        uint64_t *tmp = src; src = dst; dst = tmp;
+    }
+    return src;
+}
+
 } // namespace rfrt

@@ -49,6 +49,10 @@ struct Mesh {
     int32_t small_pairs = 0;
     float small_extent = 0.0f;
     float build_ms = 0.0f;
+    // BVH scenes: workspace of the direction-coherent ray order (grown on demand by rfrt_trace, freed with the mesh)
+    uint64_t *ray_keys[2] = {nullptr, nullptr};
+    uint32_t *ray_hist = nullptr;
+    int64_t ray_cap = 0;
 };
 
 struct RxSet {
@@ -76,6 +80,8 @@ int cuda_fail(cudaError_t e, const char *what);
 // Allocates bvh.nodes / bvh.prim_order.  Synchronises the stream.
 int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t stream, Bvh *out);
 void free_bvh(Bvh *b);
+int64_t sort_hist_blocks(int64_t n);
+uint64_t *radix_sort_u64(uint64_t *a, uint64_t *b, uint32_t *hist, int64_t n, int shift, int passes, cudaStream_t stream);
 
 int small_scene_tables(const float *soup, int n_tris, float *recs, int32_t *slot_tri, int32_t *n_pairs, float *extent);
 void small_scene_neighbours(const float *soup, int n_tris, const int32_t *slot_tri, int n_pairs, double reach, uint32_t *nbr,

@@ -37,6 +37,7 @@ struct TraceParams {
     const double *rx_centers;
     int64_t n_rx;
     float rx_lo[3], rx_hi[3];   // padded bounds of all receivers (cheap pre-test of a segment's box)
+    float env_lo[3], env_hi[3]; // padded bounds of the environment (BVH variants: box trips)
     int32_t n_unit;
     int32_t n_faces;
     float rx_radius;
@@ -46,6 +47,7 @@ struct TraceParams {
     int64_t chunk_begin; // global id of the first ray of this chunk
     int64_t chunk_n;
     const float4 *dirs;
+    const uint64_t *order; // BVH scenes: (direction cell << 32 | ray index in chunk), sorted -> coherent warps; or NULL
     // outputs
     unsigned long long *counters;
     uint4 *candidates;
@@ -64,6 +66,35 @@ __global__ void k_gen_dirs(int64_t ray_begin, int64_t n, float4 *__restrict__ di
     if (i >= n) return;
     float3 d = ray_direction((uint32_t)(ray_begin + i));
     dirs[i] = make_float4(d.x, d.y, d.z, 0.0f);
+}
+
+// Sort key of a ray: 24-bit Morton code of its direction in the octahedral map, above the ray's index in the chunk.
+// Rays are independent (kernel.py:48-55), so the trace may visit them in any order; neighbouring lanes that share a
+// direction cell walk the same BVH nodes (primary rays all start at the transmitter), which is what turns the
+// scattered node fetches of a big scene into cache hits and equalises the walk lengths inside a warp.
+__device__ __forceinline__ uint32_t spread12(uint32_t v)
+{
+    v &= 0xfffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+__global__ void k_dir_keys(const float4 *__restrict__ dirs, int64_t n, uint64_t *__restrict__ keys)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 d = dirs[i];
+    const float s = 1.0f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z) + 1.0e-30f);
+    float u = d.x * s, v = d.y * s;
+    if (d.z < 0.0f) { // fold the lower hemisphere over the diagonals
+        const float uu = (1.0f - fabsf(v)) * (u >= 0.0f ? 1.0f : -1.0f), vv = (1.0f - fabsf(u)) * (v >= 0.0f ? 1.0f : -1.0f);
+        u = uu; v = vv;
+    }
+    const uint32_t qu = (uint32_t)fminf(fmaxf((u * 0.5f + 0.5f) * 4096.0f, 0.0f), 4095.0f);
+    const uint32_t qv = (uint32_t)fminf(fmaxf((v * 0.5f + 0.5f) * 4096.0f, 0.0f), 4095.0f);
+    keys[i] = ((uint64_t)(spread12(qu) | (spread12(qv) << 1)) << 32) | (uint64_t)(uint32_t)i;
 }
 
 // Conservative sphere filter in front of the exact 80-triangle receiver query: can the segment
@@ -145,6 +176,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
     float3 pos = make_float3(0.f, 0.f, 0.f), dir = make_float3(0.f, 0.f, 1.f);
     int bounce = 0;
     int on_face = -1; // SMALL: the triangle the ray stands on (its previous hit); -1 at the transmitter
+    bool entered = false; // BVH variants: the current segment is known to enter the scene's bounding box
     int64_t ray = 0;
     unsigned int n_seg = 0, n_hit = 0;
     unsigned long long csum = 0ull;
@@ -167,13 +199,15 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
                 if (blk_next >= P.chunk_n) { exhausted = true; blk_end = blk_next; }
             }
             if (!has_ray) {
-                const int64_t r = blk_next + __popc(idle & ((1u << lane) - 1u));
+                int64_t r = blk_next + __popc(idle & ((1u << lane) - 1u));
                 if (r < blk_end) {
+                    if (P.order) r = (int64_t)(uint32_t)__ldg(P.order + r); // direction-coherent order
                     float4 d4 = __ldg(P.dirs + r);
                     dir = make_float3(d4.x, d4.y, d4.z);
                     pos = P.tx;
                     bounce = 0;
                     on_face = -1;
+                    entered = false;
                     ray = r;
                     has_ray = true;
                 }
@@ -186,23 +220,36 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
         // sweep (every lane with a ray).  The full sweep is always valid, so the vote is purely a scheduling choice.
         bool shortcut = false;
         if (SMALL) shortcut = __popc(__ballot_sync(FULL, has_ray && on_face >= 0)) >= P.short_min;
-        if (has_ray && (!shortcut || on_face >= 0)) {
+        // BVH variants: a trip is either a box trip (the lanes whose segment has not been tested against the scene's
+        // bounding box do just that: a miss finishes the segment at once and frees the lane for the next refill) or a
+        // walk.  Without it the many rays that leave the scene immediately (half of them above an open terrain) would
+        // sit idle in warps whose other lanes walk 50 nodes (measured: 5.6 of 32 lanes active).
+        bool boxtrip = false;
+        if (!SMALL) boxtrip = __any_sync(FULL, has_ray && !entered);
+        if (has_ray && (SMALL ? (!shortcut || on_face >= 0) : (!boxtrip || !entered))) {
         // ---- one bounce iteration (kernel.py:57-98, environment branch) -----------------------
-        WoopRay wr = woop_setup(pos, dir);
         Hit h;
         h.t = 1.0e6f; h.face = -1; h.slot = -1;
         bool resolved = true;
         SlabRay sr_env; // BVH variants: reused by the receiver enumeration
         sr_env.ix = sr_env.iy = sr_env.iz = sr_env.ox = sr_env.oy = sr_env.oz = 0.0f;
         if (SMALL) {
+            const WoopRay wr = woop_setup(pos, dir);
             if (shortcut) resolved = small_self_rehit(S, on_face, pos, dir, wr, h);
             else closest_hit_small<SMALL == 2>(S, pos, dir, wr, h);
         } else {
             sr_env = slab_setup(pos, dir);
-            closest_hit(P.nodes, P.tris, P.n_tris, wr, sr_env, stack, stack_t, STRIDE, h);
+            if (boxtrip) {
+                float tn;
+                entered = slab_hit(sr_env, P.env_lo[0], P.env_lo[1], P.env_lo[2], P.env_hi[0], P.env_hi[1], P.env_hi[2], 1.0e6f, tn);
+                resolved = !entered; // outside the box: a miss (h stays empty)
+            } else {
+                const WoopRay wr = woop_setup(pos, dir);
+                closest_hit(P.nodes, P.tris, P.n_tris, wr, sr_env, stack, stack_t, STRIDE, h);
+            }
         }
         if (!resolved) {
-            on_face = -1; // not a self re-hit: this segment goes through the next full sweep
+            if (SMALL) on_face = -1; // not a self re-hit: this segment goes through the next full sweep
         } else {
         const bool hit_env = h.face >= 0;
         ++n_seg;
@@ -266,6 +313,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
             }
             dir = reflect(dir, nrm);                      // kernel.py:96
             on_face = h.face;
+            entered = false;
             ++bounce;
             if (bounce >= P.max_bounces) has_ray = false;
         } else {
@@ -598,6 +646,10 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
         P.rx_lo[k] = r ? r->bvh.bounds[k] - r->bvh.pad : 0.0f;
         P.rx_hi[k] = r ? r->bvh.bounds[3 + k] + r->bvh.pad : 0.0f;
     }
+    for (int k = 0; k < 3; ++k) {
+        P.env_lo[k] = m->bvh.bounds[k] - m->bvh.pad;
+        P.env_hi[k] = m->bvh.bounds[3 + k] + m->bvh.pad;
+    }
     P.tx = make_float3(h_tx_pos[0], h_tx_pos[1], h_tx_pos[2]);
     P.max_bounces = max_bounces;
     P.dirs = (const float4 *)d_dir_scratch;
@@ -631,9 +683,30 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     if (rc) return rc;
     if (r) { rc = upload_faces(r, stream); if (rc) return rc; }
 
+    // BVH scenes: trace the rays of a chunk in direction-coherent order (workspace cached with the mesh)
+    const bool sorted = !small && !(flags & RFRT_FLAG_NO_RAY_SORT) && n >= 4096;
+    if (sorted) {
+        const int64_t cap = n < chunk_rays ? n : chunk_rays;
+        if (m->ray_cap < cap) {
+            if (m->ray_keys[0]) cudaFree(m->ray_keys[0]);
+            if (m->ray_keys[1]) cudaFree(m->ray_keys[1]);
+            if (m->ray_hist) cudaFree(m->ray_hist);
+            m->ray_keys[0] = m->ray_keys[1] = nullptr; m->ray_hist = nullptr; m->ray_cap = 0;
+            RFRT_CUDA(cudaMalloc(&m->ray_keys[0], sizeof(uint64_t) * cap));
+            RFRT_CUDA(cudaMalloc(&m->ray_keys[1], sizeof(uint64_t) * cap));
+            RFRT_CUDA(cudaMalloc(&m->ray_hist, sizeof(uint32_t) * 256 * (size_t)sort_hist_blocks(cap)));
+            m->ray_cap = cap;
+        }
+    }
+
     for (int64_t c0 = ray_begin; c0 < ray_end; c0 += chunk_rays) {
         int64_t cn = ray_end - c0 < chunk_rays ? ray_end - c0 : chunk_rays;
         if (!dirs_ready) k_gen_dirs<<<(unsigned)((cn + 255) / 256), 256, 0, stream>>>(c0, cn, (float4 *)d_dir_scratch);
+        P.order = nullptr;
+        if (sorted) {
+            k_dir_keys<<<(unsigned)((cn + 255) / 256), 256, 0, stream>>>((const float4 *)d_dir_scratch, cn, m->ray_keys[0]);
+            P.order = radix_sort_u64(m->ray_keys[0], m->ray_keys[1], m->ray_hist, cn, 32, 3, stream);
+        }
         RFRT_CUDA(cudaMemsetAsync(d_counters + RFRT_CTR_NEXT_RAY, 0, sizeof(uint64_t), stream));
         P.chunk_begin = c0; P.chunk_n = cn;
         int g = grid;
