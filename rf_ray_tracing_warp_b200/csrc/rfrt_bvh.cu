@@ -110,14 +110,17 @@ k_sort_hist(const uint64_t *__restrict__ keys, int64_t n, int shift, uint32_t *_
     ghist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(1024) k_scan_exclusive(uint32_t *data, int64_t total)
+// Exclusive scan of the digit-major histogram [256][nblocks] in two levels: every digit row by its own CTA (in place,
+// row total to row_tot[digit]), then the 256 row totals by one CTA; the scatter adds the two.
+__global__ void __launch_bounds__(256) k_scan_rows(uint32_t *hist, int nblocks, uint32_t *row_tot)
 {
-    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t warp_sums[8];
+    uint32_t *row = hist + (int64_t)blockIdx.x * nblocks;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t carry = 0;
-    for (int64_t base = 0; base < total; base += 1024) {
-        int64_t i = base + threadIdx.x;
-        uint32_t v = i < total ? data[i] : 0u;
+    for (int base = 0; base < nblocks; base += 256) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < nblocks ? row[i] : 0u;
         uint32_t x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -126,32 +129,40 @@ __global__ void __launch_bounds__(1024) k_scan_exclusive(uint32_t *data, int64_t
         }
         if (lane == 31) warp_sums[warp] = x;
         __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warp_sums[lane];
+        uint32_t prefix = 0, total = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
-            }
-            warp_sums[lane] = w;
+        for (int w = 0; w < 8; ++w) {
+            if (w < warp) prefix += warp_sums[w];
+            total += warp_sums[w];
         }
+        if (i < nblocks) row[i] = carry + prefix + x - v;
+        carry += total;
         __syncthreads();
-        uint32_t prefix = warp > 0 ? warp_sums[warp - 1] : 0u;
-        if (i < total) data[i] = carry + prefix + x - v;
-        uint32_t tile_total = warp_sums[31];
-        __syncthreads();
-        carry += tile_total;
     }
+    if (threadIdx.x == 0) row_tot[blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(256) k_scan_totals(uint32_t *row_tot)
+{
+    __shared__ uint32_t s[256];
+    s[threadIdx.x] = row_tot[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int d = 0; d < 256; ++d) { uint32_t v = s[d]; s[d] = acc; acc += v; }
+    }
+    __syncthreads();
+    row_tot[threadIdx.x] = s[threadIdx.x];
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
 k_sort_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int64_t n, int shift,
-               const uint32_t *__restrict__ gscan, int nblocks)
+               const uint32_t *__restrict__ gscan, const uint32_t *__restrict__ row_base, int nblocks)
 {
     __shared__ uint32_t base[256];
     __shared__ uint32_t cnt[SORT_THREADS / 32][256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    base[tid] = gscan[(int64_t)tid * nblocks + blockIdx.x];
+    base[tid] = gscan[(int64_t)tid * nblocks + blockIdx.x] + row_base[tid];
     const int64_t tile = (int64_t)blockIdx.x * SORT_TILE;
     for (int it = 0; it < SORT_ITEMS; ++it) {
 #pragma unroll
@@ -336,7 +347,7 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
 
     RFRT_CUDA(cudaMalloc(&keys_a, sizeof(uint64_t) * n));
     RFRT_CUDA(cudaMalloc(&keys_b, sizeof(uint64_t) * n));
-    RFRT_CUDA(cudaMalloc(&ghist, sizeof(uint32_t) * 256 * (size_t)nblocks));
+    RFRT_CUDA(cudaMalloc(&ghist, sizeof(uint32_t) * 256 * ((size_t)nblocks + 1)));
     RFRT_CUDA(cudaMalloc(&bounds_enc, sizeof(int) * 8));
     RFRT_CUDA(cudaMalloc(&d_bounds, sizeof(float) * 8));
     RFRT_CUDA(cudaMalloc(&node_parent, sizeof(int) * n_nodes));
@@ -363,8 +374,9 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
     for (int pass = 0; pass < 4; ++pass) {
         int shift = 32 + 8 * pass;
         k_sort_hist<<<nblocks, SORT_THREADS, 0, stream>>>(src, n, shift, ghist, nblocks);
-        k_scan_exclusive<<<1, 1024, 0, stream>>>(ghist, 256ll * nblocks);
-        k_sort_scatter<<<nblocks, SORT_THREADS, 0, stream>>>(src, dst, n, shift, ghist, nblocks);
+        k_scan_rows<<<256, 256, 0, stream>>>(ghist, nblocks, ghist + 256ll * nblocks);
+        k_scan_totals<<<1, 256, 0, stream>>>(ghist + 256ll * nblocks);
+        k_sort_scatter<<<nblocks, SORT_THREADS, 0, stream>>>(src, dst, n, shift, ghist, ghist + 256ll * nblocks, nblocks);
         uint64_t *tmp = src; src = dst; dst = tmp;
     }
     // after 4 passes the sorted keys are back in keys_a (src)
@@ -391,7 +403,7 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
 }
 
 // LSD radix sort of 64-bit keys on bits [shift, shift + 8*passes): returns the buffer holding the result (a or b).
-// hist must hold 256 * sort_hist_blocks(n) counters.
+// hist must hold 256 * (sort_hist_blocks(n) + 1) counters.
 int64_t sort_hist_blocks(int64_t n) { return (n + SORT_TILE - 1) / SORT_TILE; }
 
 uint64_t *radix_sort_u64(uint64_t *a, uint64_t *b, uint32_t *hist, int64_t n, int shift, int passes, cudaStream_t stream)
@@ -401,8 +413,9 @@ uint64_t *radix_sort_u64(uint64_t *a, uint64_t *b, uint32_t *hist, int64_t n, in
     for (int pass = 0; pass < passes; ++pass) {
         const int sh = shift + 8 * pass;
         k_sort_hist<<<nblocks, SORT_THREADS, 0, stream>>>(src, n, sh, hist, nblocks);
-        k_scan_exclusive<<<1, 1024, 0, stream>>>(hist, 256ll * nblocks);
-        k_sort_scatter<<<nblocks, SORT_THREADS, 0, stream>>>(src, dst, n, sh, hist, nblocks);
+        k_scan_rows<<<256, 256, 0, stream>>>(hist, nblocks, hist + 256ll * nblocks);
+        k_scan_totals<<<1, 256, 0, stream>>>(hist + 256ll * nblocks);
+        k_sort_scatter<<<nblocks, SORT_THREADS, 0, stream>>>(src, dst, n, sh, hist, hist + 256ll * nblocks, nblocks);
         uint64_t *tmp = src; src = dst; dst = tmp;
     }
     return src;

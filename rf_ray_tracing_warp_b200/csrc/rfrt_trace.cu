@@ -694,7 +694,7 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
             m->ray_keys[0] = m->ray_keys[1] = nullptr; m->ray_hist = nullptr; m->ray_cap = 0;
             RFRT_CUDA(cudaMalloc(&m->ray_keys[0], sizeof(uint64_t) * cap));
             RFRT_CUDA(cudaMalloc(&m->ray_keys[1], sizeof(uint64_t) * cap));
-            RFRT_CUDA(cudaMalloc(&m->ray_hist, sizeof(uint32_t) * 256 * (size_t)sort_hist_blocks(cap)));
+            RFRT_CUDA(cudaMalloc(&m->ray_hist, sizeof(uint32_t) * 256 * ((size_t)sort_hist_blocks(cap) + 1)));
             m->ray_cap = cap;
         }
     }
