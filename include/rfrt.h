@@ -201,6 +201,28 @@ RFRT_API int rfrt_rx_power_dense(const double *d_ir, int64_t n_receivers, int64_
                         double carrier_hz, double *d_power, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * "Physical" mode (what the reference's quirks Q1-Q6 approximate; NOT reference behaviour).
+ * Same deterministic rays (kernel.py:51-52) and the same exact closest-hit test (kernel.py:82), but the triangle a ray
+ * has just left is excluded from its next query, receivers are analytic spheres crossed once per segment, and every
+ * arrival adds the field  E = (L lambda / (pi N r^2)) * prod Gamma_i * exp(-j 2 pi L / lambda)  (free-space loss x
+ * reception-sphere weight x Fresnel amplitude coefficients x carrier phase; L = unfolded path length to the point of
+ * closest approach) to its receiver: received power = P_tx * |d_field[k]|^2.
+ *   rxset          : receiver set whose unit shape is the cube (+-1)^3, so that its boxes are centre +- radius
+ *                    (the Python layer builds it); 0 = trace without receivers
+ *   n_rays_total   : N of the formula (rays of the whole job, all GPUs)
+ *   d_materials    : [n_triangles] float32 refractive index per triangle, or NULL (5.0 everywhere = tracer.py:43)
+ *   d_field        : [n_receivers*2] float64 (re, im), ACCUMULATED (zeroed by the caller)
+ *   d_ir           : optional [n_receivers*n_bins*2] float64 complex impulse response, accumulated; bin =
+ *                    int(L / light_speed * sample_rate) (tracer.py:115)
+ *   d_counters     : as rfrt_trace (RFRT_CTR_RECORDS counts the arrivals)
+ * ------------------------------------------------------------------------------------------- */
+RFRT_API int rfrt_trace_physical(rfrt_handle env_mesh, rfrt_handle rxset, const float *h_tx_pos, int32_t max_bounces,
+                        int64_t ray_begin, int64_t ray_end, int64_t n_rays_total, double carrier_hz,
+                        double light_speed_mps, double sample_rate_hz, int64_t n_bins, const float *d_materials,
+                        float *d_dir_scratch, int64_t chunk_rays, uint64_t *d_counters, double *d_field, double *d_ir,
+                        void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Compatibility launch with the reference kernel's exact contract (kernel.py:38-47 as launched at
  * tracer.py:75-79): dense outputs for ray ids [ray_begin, ray_begin+n_rays) against receiver
  * `rx_index` of `rxset`.  The caller pre-fills d_traced_paths / d_received_paths with NaN and zeroes

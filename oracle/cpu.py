@@ -41,6 +41,11 @@ def lib():
         L.oracle_trace_env.restype = ctypes.c_uint64
         L.oracle_trace_env.argtypes = [_f32p, ctypes.c_int64, ctypes.c_void_p, _f32p, ctypes.c_int, ctypes.c_int64,
                                        ctypes.c_int64, _i32p, _f32p, ctypes.c_int]
+        L.oracle_trace_physical.restype = ctypes.c_uint64
+        L.oracle_trace_physical.argtypes = [_f32p, ctypes.c_int64, ctypes.c_void_p, _f32p, _f64p, ctypes.c_int64,
+                                            ctypes.c_double, _f32p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                            ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                            ctypes.c_int64, _f64p, _f64p, ctypes.POINTER(ctypes.c_uint64)]
         L.oracle_ray_directions.argtypes = [ctypes.c_int64, ctypes.c_int64, _f32p]
         L.oracle_ray_directions_list.argtypes = [_i64p, ctypes.c_int64, _f32p]
         L.oracle_pcg.restype = ctypes.c_uint32
@@ -170,6 +175,25 @@ def trace_env(env_soup, tx_pos, max_bounces, tid_begin, n, instrument=True, bvh=
     seg = lib().oracle_trace_env(_p(env, _f32p), env.shape[0], bvh.handle if bvh else None, _p(tx, _f32p), B,
                                  int(tid_begin), int(n), _p(hit_tri, _i32p), _p(hit_t, _f32p), int(nthreads))
     return int(seg), hit_tri, hit_t
+
+
+def trace_physical(env_soup, rx_centers, rx_radius, tx_pos, max_bounces, tid_begin, n, n_total, carrier_hz, light_speed,
+                   materials=None, sample_rate=0.0, n_bins=0, bvh=None):
+    """Physical mode (oracle_trace_physical): returns dict(field (R,) complex128, ir (R,L) complex128 or None,
+    segments, arrivals)."""
+    env = _soup(env_soup if bvh is None else bvh.soup)
+    c = np.ascontiguousarray(np.asarray(rx_centers, dtype=np.float64).reshape(-1, 3))
+    tx = np.ascontiguousarray(np.asarray(tx_pos, dtype=np.float32))
+    mat = np.ascontiguousarray(np.asarray(materials, dtype=np.float32)) if materials is not None else None
+    field = np.zeros((c.shape[0], 2), dtype=np.float64)
+    ir = np.zeros((c.shape[0], int(n_bins), 2), dtype=np.float64) if n_bins else None
+    arr = ctypes.c_uint64(0)
+    seg = lib().oracle_trace_physical(_p(env, _f32p), env.shape[0], bvh.handle if bvh else None, _p(mat, _f32p),
+                                      _p(c, _f64p), c.shape[0], float(rx_radius), _p(tx, _f32p), int(max_bounces),
+                                      int(tid_begin), int(n), int(n_total), float(carrier_hz), float(light_speed),
+                                      float(sample_rate), int(n_bins), _p(field, _f64p), _p(ir, _f64p), ctypes.byref(arr))
+    return dict(field=field[:, 0] + 1j * field[:, 1], ir=None if ir is None else ir[..., 0] + 1j * ir[..., 1],
+                segments=int(seg), arrivals=int(arr.value))
 
 
 def max_threads():

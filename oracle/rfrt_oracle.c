@@ -261,8 +261,8 @@ static inline int woop(const float p[3], const float dir[3], const float a[3], c
 
 /* mesh_query_ray [restated]: closest accepted hit with 0 <= t < max_t.  Brute force in
  * index order with strict '<'  ==>  equal-t ties go to the lowest triangle index. */
-static int query_closest(const float *tris, int64_t ntris, const float p[3], const float dir[3], float max_t,
-                         float *t_out, int *face_out)
+static int query_closest_skip(const float *tris, int64_t ntris, const float p[3], const float dir[3], float max_t,
+                              int skip, float *t_out, int *face_out)
 {
     float min_t = max_t;
     int min_face = -1;
@@ -271,7 +271,7 @@ static int query_closest(const float *tris, int64_t ntris, const float p[3], con
     for (int64_t i = 0; i < ntris; ++i) {
         const float *a = tris + 9 * i;
         float t;
-        if (woop_tri(&wr, a, a + 3, a + 6, &t)) {
+        if ((int)i != skip && woop_tri(&wr, a, a + 3, a + 6, &t)) {
             if (t < min_t && t >= 0.0f) {
                 min_t = t;
                 min_face = (int)i;
@@ -408,7 +408,8 @@ ORACLE_API void oracle_bvh_destroy(void *h)
     free(b);
 }
 
-static int obvh_query(const OBvh *b, const float p[3], const float dir[3], float max_t, float *t_out, int *face_out)
+static int obvh_query_skip(const OBvh *b, const float p[3], const float dir[3], float max_t, int skip, float *t_out,
+                           int *face_out)
 {
     if (b->ntris == 0) return 0;
     float pad = 1.0e-3f;
@@ -451,7 +452,7 @@ static int obvh_query(const OBvh *b, const float p[3], const float dir[3], float
                 int f = b->prim[i];
                 const float *a = b->tris + 9 * (int64_t)f;
                 float t;
-                if (woop_tri(&wr, a, a + 3, a + 6, &t)) {
+                if (f != skip && woop_tri(&wr, a, a + 3, a + 6, &t)) {
                     if (t >= 0.0f && (t < min_t || (t == min_t && min_face >= 0 && f < min_face))) {
                         min_t = t;
                         min_face = f;
@@ -471,11 +472,17 @@ static int obvh_query(const OBvh *b, const float p[3], const float dir[3], float
     return 0;
 }
 
+static inline int query_skip(const float *tris, int64_t ntris, const OBvh *bvh, const float p[3], const float dir[3],
+                             float max_t, int skip, float *t, int *face)
+{
+    if (bvh) return obvh_query_skip(bvh, p, dir, max_t, skip, t, face);
+    return query_closest_skip(tris, ntris, p, dir, max_t, skip, t, face);
+}
+
 static inline int query(const float *tris, int64_t ntris, const OBvh *bvh, const float p[3], const float dir[3],
                         float max_t, float *t, int *face)
 {
-    if (bvh) return obvh_query(bvh, p, dir, max_t, t, face);
-    return query_closest(tris, ntris, p, dir, max_t, t, face);
+    return query_skip(tris, ntris, bvh, p, dir, max_t, -1, t, face);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -678,6 +685,93 @@ ORACLE_API int oracle_query(const float *tris, int64_t ntris, void *bvh, const f
 }
 
 ORACLE_API void oracle_tri_normal(const float *tri9, float *n) { tri_normal(tri9, tri9 + 3, tri9 + 6, n); }
+
+/* ------------------------------------------------------------------------------------------
+ * "Physical" mode (NOT reference behaviour — it removes quirks Q1-Q6):
+ *   - the triangle a ray has just left is excluded from its next closest-hit query;
+ *   - receivers are analytic spheres; a segment [0, t_env] whose closest approach to a centre lies inside the
+ *     sphere (origin outside it) is one arrival with unfolded path length L = L_prev + t_c * |dir|;
+ *   - field (unit transmit power, isotropic antennas):
+ *         E = (L * lambda / (pi * N * r^2)) * prod_i Gamma_i * exp(-j 2 pi L / lambda)
+ *     i.e. free-space loss lambda / (4 pi L) times the reception-sphere weight 4 L^2 / (N r^2);
+ *     Gamma = (cos(theta_t) - n cos(theta_i)) / (cos(theta_t) + n cos(theta_i)), sin(theta_t) = sin(theta_i) / n
+ *     (p-polarised Fresnel amplitude coefficient, air -> index n; tracer.py:43-53 uses its square with n = 5);
+ *   - field[k] (re, im) = sum of E over all arrivals at receiver k; optional complex impulse response
+ *     ir[k][bin] += E with bin = int(L / c * rate) (tracer.py:115).
+ * Geometry is fp32 with the trace's own operations; the sphere test and the field are fp64.
+ * materials: per-triangle index n, or NULL for 5.0.
+ * ---------------------------------------------------------------------------------------- */
+ORACLE_API uint64_t oracle_trace_physical(const float *env, int64_t nenv, void *env_bvh, const float *materials,
+                                          const double *rx_centers, int64_t nrx, double rx_radius, const float *tx,
+                                          int max_bounces, int64_t tid_begin, int64_t n, int64_t n_total,
+                                          double carrier_hz, double light_speed, double sample_rate, int64_t n_bins,
+                                          double *field, double *ir, uint64_t *arrivals_out)
+{
+    const double lambda = light_speed / carrier_hz;
+    const double wk = lambda / (3.141592653589793 * (double)n_total * (rx_radius * rx_radius));
+    const double two_pi_over_lambda = (2.0 * 3.141592653589793) / lambda;
+    const double r2 = rx_radius * rx_radius;
+    uint64_t segments = 0, arrivals = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        float dir[3], pos[3] = {tx[0], tx[1], tx[2]};
+        ray_direction((uint32_t)(tid_begin + i), dir);
+        int prev = -1;
+        double L = 0.0, gamma = 1.0;
+        for (int b = 0; b < max_bounces; ++b) {
+            float t_env = 0.0f;
+            int face = -1;
+            int hit = query_skip(env, nenv, (const OBvh *)env_bvh, pos, dir, 1.0e6f, prev, &t_env, &face);
+            ++segments;
+            const float dlen = sqrtf((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]);
+            const double t_lim = hit ? (double)t_env : 1.0e6;
+            const double dd = ((double)dir[0] * (double)dir[0] + (double)dir[1] * (double)dir[1]) + (double)dir[2] * (double)dir[2];
+            for (int64_t k = 0; k < nrx; ++k) {
+                const double ox = rx_centers[3 * k] - (double)pos[0], oy = rx_centers[3 * k + 1] - (double)pos[1],
+                             oz = rx_centers[3 * k + 2] - (double)pos[2];
+                const double oo = (ox * ox + oy * oy) + oz * oz;
+                if (oo <= r2) continue; /* the segment starts inside the sphere: no new arrival */
+                const double od = (ox * (double)dir[0] + oy * (double)dir[1]) + oz * (double)dir[2];
+                const double tc = od / dd;
+                if (!(tc >= 0.0) || !(tc <= t_lim)) continue;
+                const double perp2 = oo - tc * od;
+                if (!(perp2 <= r2)) continue;
+                const double Lk = L + tc * (double)dlen;
+                const double a = (Lk * wk) * gamma;
+                const double ph = two_pi_over_lambda * Lk;
+                const double re = a * cos(ph), im = -(a * sin(ph));
+                field[2 * k] += re;
+                field[2 * k + 1] += im;
+                if (ir) {
+                    const int64_t bin = (int64_t)((Lk / light_speed) * sample_rate);
+                    if (bin >= 0 && bin < n_bins) {
+                        ir[2 * (k * n_bins + bin)] += re;
+                        ir[2 * (k * n_bins + bin) + 1] += im;
+                    }
+                }
+                ++arrivals;
+            }
+            if (!hit) break;
+            const float *a = env + 9 * (int64_t)face;
+            float nrm[3];
+            tri_normal(a, a + 3, a + 6, nrm);
+            const float dn = (dir[0] * nrm[0] + dir[1] * nrm[1]) + dir[2] * nrm[2];
+            const double nmat = materials ? (double)materials[face] : 5.0;
+            double ci = fabs((double)dn) / (double)dlen;
+            if (ci > 1.0) ci = 1.0;
+            const double si2 = 1.0 - ci * ci;
+            const double ct = sqrt(1.0 - si2 / (nmat * nmat));
+            gamma = gamma * ((ct - nmat * ci) / (ct + nmat * ci));
+            L = L + (double)t_env * (double)dlen;
+            pos[0] = pos[0] + dir[0] * t_env;
+            pos[1] = pos[1] + dir[1] * t_env;
+            pos[2] = pos[2] + dir[2] * t_env;
+            reflect(dir, nrm);
+            prev = face;
+        }
+    }
+    if (arrivals_out) *arrivals_out = arrivals;
+    return segments;
+}
 
 ORACLE_API int oracle_max_threads(void)
 {

@@ -49,6 +49,8 @@ SIGNATURES = {
     "rfrt_rx_power": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_d, c_d, c_void_p, c_void_p,
                                      c_void_p]),
     "rfrt_rx_power_dense": (ctypes.c_int, [c_void_p, c_i64, c_i64, c_d, c_d, c_void_p, c_void_p]),
+    "rfrt_trace_physical": (ctypes.c_int, [c_u64, c_u64, ctypes.POINTER(c_f), c_i32, c_i64, c_i64, c_i64, c_d, c_d, c_d,
+                                           c_i64, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rfrt_trace_paths_compat": (ctypes.c_int, [c_u64, ctypes.POINTER(c_f), c_u64, c_i64, c_i32, c_i64, c_i64,
                                                c_void_p, c_void_p, c_void_p, c_void_p]),
     "rfrt_query_closest": (ctypes.c_int, [c_u64, c_void_p, c_void_p, c_i64, c_f, c_void_p, c_void_p, c_void_p]),

@@ -118,13 +118,14 @@ __device__ __forceinline__ int node_step(const BvhNode *__restrict__ nodes, int 
 }
 
 // test the triangle of one leaf (closest t, 0 <= t < best; equal t -> lowest triangle index), then pop
+// (skip: a triangle index the query ignores — physical mode's "the triangle just left"; -1 = none)
 __device__ __forceinline__ int leaf_step(const BvhTri *__restrict__ tris, int node, const WoopRay &wr, Hit &h,
-                                         int *stack, float *stack_t, int stride, int &sp)
+                                         int *stack, float *stack_t, int stride, int &sp, int skip = -1)
 {
     const int slot = ~node;
     float3 a, b, c; int idx; float t;
     tri_vertices(tris, slot, a, b, c, idx);
-    if (woop_hit(wr, a, b, c, t) && t >= 0.0f && (t < h.t || (t == h.t && h.face >= 0 && idx < h.face))) {
+    if (idx != skip && woop_hit(wr, a, b, c, t) && t >= 0.0f && (t < h.t || (t == h.t && h.face >= 0 && idx < h.face))) {
         h.t = t; h.face = idx; h.slot = slot;
     }
     return stack_pop(stack, stack_t, stride, sp, h.t);
@@ -138,13 +139,13 @@ __device__ __forceinline__ int leaf_step(const BvhTri *__restrict__ tris, int no
 // lanes active; testing leaves inside the node loop: 3/32 active in the triangle test).
 __device__ __forceinline__ void closest_hit(const BvhNode *__restrict__ nodes, const BvhTri *__restrict__ tris,
                                             int64_t n_prims, const WoopRay &wr, const SlabRay &sr, int *stack,
-                                            float *stack_t, int stride, Hit &h)
+                                            float *stack_t, int stride, Hit &h, int skip = -1)
 {
     int sp = 0;
     int node = n_prims > 0 ? 0 : TRAV_DONE;
     while (node != TRAV_DONE) {
         while (node >= 0) node = node_step(nodes, node, sr, h.t, stack, stack_t, stride, sp);
-        if (node != TRAV_DONE) node = leaf_step(tris, node, wr, h, stack, stack_t, stride, sp);
+        if (node != TRAV_DONE) node = leaf_step(tris, node, wr, h, stack, stack_t, stride, sp, skip);
     }
 }
 

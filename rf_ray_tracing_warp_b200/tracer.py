@@ -86,6 +86,7 @@ class Tracer:
                                              faces.shape[0] // 3, _stream_ptr(), handle), "rfrt_mesh_create")
         self._env = handle.value
         self._unit_v, self._unit_f = unit_icosphere(1)  # tracer.py:27 (subdivisions=1)
+        self._materials = None
         self._dir_scratch = None
         self.last_stats = {}
 
@@ -112,11 +113,17 @@ class Tracer:
             self._dir_scratch = torch.empty(need, dtype=torch.float32, device=self.device)
         return self._dir_scratch
 
-    def _make_rxset(self, centers, radius):
-        """tracer.py:26-30, batched: centers (R,3) float64 device tensor."""
+    def _make_rxset(self, centers, radius, shape="icosphere"):
+        """tracer.py:26-30, batched: centers (R,3) float64 device tensor.  shape="cube": the unit shape is the cube
+        (+-1)^3, i.e. the receiver boxes are centre +- radius (physical mode's analytic spheres)."""
         handle = c_u64(0)
-        uv = np.ascontiguousarray(self._unit_v, dtype=np.float64)
-        uf = np.ascontiguousarray(self._unit_f, dtype=np.int32)
+        if shape == "cube":
+            uv = np.array([[x, y, z] for x in (-1.0, 1.0) for y in (-1.0, 1.0) for z in (-1.0, 1.0)], dtype=np.float64)
+            uf = np.array([[0, 1, 3], [0, 3, 2], [4, 6, 7], [4, 7, 5], [0, 4, 5], [0, 5, 1], [2, 3, 7], [2, 7, 6],
+                           [0, 2, 6], [0, 6, 4], [1, 5, 7], [1, 7, 3]], dtype=np.int32)
+        else:
+            uv = np.ascontiguousarray(self._unit_v, dtype=np.float64)
+            uf = np.ascontiguousarray(self._unit_f, dtype=np.int32)
         check(self._lib.rfrt_rxset_create(_ptr(centers), centers.shape[0], float(radius),
                                           uv.ctypes.data_as(_lib.ctypes.POINTER(_lib.c_d)), uv.shape[0],
                                           uf.ctypes.data_as(_lib.ctypes.POINTER(c_i32)), uf.shape[0], _stream_ptr(),
@@ -314,6 +321,61 @@ class Tracer:
         return dict(power=p, dbm=to_dbm(p), stats=dict(stats), impulse_response=ir)
 
     # ------------------------------------------------------------------------------------------
+    def set_materials(self, refractive_index):
+        """Per-triangle refractive index (array of n_triangles floats; None = 5.0 everywhere, tracer.py:43).  Used by
+        ``trace_physical``."""
+        if refractive_index is None:
+            self._materials = None
+            return
+        mat = np.ascontiguousarray(np.asarray(refractive_index, dtype=np.float32).reshape(-1))
+        if mat.shape[0] != self.mesh_info()["n_triangles"]:
+            raise ValueError("set_materials: need one refractive index per triangle")
+        self._materials = torch.from_numpy(mat).to(self.device)
+
+    def trace_physical(self, tx_pos, tx_power, rx_positions, rx_radius, carrier_hz=2.4e9, want_ir=False):
+        """Physical mode (rfrt_trace_physical; NOT reference behaviour, see include/rfrt.h): no t ~ 0 re-hits,
+        analytic-sphere receivers, explicit free-space loss, Fresnel amplitude coefficients and carrier phase.
+        Returns dict(field (R,) complex128 for unit transmit power, power (R,) = tx_power * |field|^2, dbm,
+        impulse_response (R,L) complex128 tensor if want_ir, stats).  With ``shard=True`` the per-GPU fields (and
+        impulse responses) are combined with one all-reduce (NCCL)."""
+        centers = np.ascontiguousarray(np.asarray(rx_positions, dtype=np.float64).reshape(-1, 3))
+        n_rx = centers.shape[0]
+        L = int(self.sample_window_s * self.sample_rate_hz)
+        begin, end = self.ray_range
+        with torch.cuda.device(self.device):
+            d_centers = torch.from_numpy(centers).to(self.device)
+            rxset = self._make_rxset(d_centers, rx_radius, shape="cube")
+            try:
+                field = torch.zeros((n_rx, 2), dtype=torch.float64, device=self.device)
+                ir = torch.zeros((n_rx, L, 2), dtype=torch.float64, device=self.device) if want_ir else None
+                counters = torch.zeros(_lib.CTR_COUNT, dtype=torch.int64, device=self.device)
+                chunk = min(self.chunk_rays, max(end - begin, 1))
+                scratch = torch.empty(chunk * 4, dtype=torch.float32, device=self.device)
+                mat = getattr(self, "_materials", None)
+                check(self._lib.rfrt_trace_physical(self._env, rxset, float3(tx_pos), self.max_bounces, begin, end,
+                                                    self.tx_num_rays, float(carrier_hz), float(self.light_speed_mps),
+                                                    float(self.sample_rate_hz), L, _ptr(mat), _ptr(scratch), chunk,
+                                                    _ptr(counters), _ptr(field), _ptr(ir), _stream_ptr()),
+                      "rfrt_trace_physical")
+                c = counters.cpu().numpy()
+                stats = dict(segments=int(c[_lib.CTR_SEGMENTS]), env_hits=int(c[_lib.CTR_ENV_HITS]),
+                             arrivals=int(c[_lib.CTR_RECORDS]))
+            finally:
+                self._lib.rfrt_rxset_destroy(rxset)
+            if self._world > 1:
+                torch.distributed.all_reduce(field)  # the one exchange step: sum of the per-GPU coherent fields
+                if ir is not None:
+                    torch.distributed.all_reduce(ir)
+                stats = sharding.sum_stats(stats, self.device)
+            f = field.cpu().numpy()
+        f = f[:, 0] + 1j * f[:, 1]
+        power = float(tx_power) * np.abs(f) ** 2
+        out = dict(field=f, power=power, dbm=to_dbm(power), stats=stats)
+        if want_ir:
+            out["impulse_response"] = torch.view_as_complex(ir)
+        self.last_stats = stats
+        return out
+
     def trace_paths_kernel(self, tx_pos, rx_pos, rx_radius, ray_range=None):
         """The reference kernel's dense contract (kernel.py:38-47 launched at tracer.py:75-79): returns
         (traced_paths (n,B+1,3), received_paths (n,B+1,3), row_mask (n,)) device tensors, NaN / zero
