@@ -87,6 +87,10 @@ RFRT_API int rfrt_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_
 RFRT_API int rfrt_mesh_create(const float *d_vertices_xyz, int64_t n_vertices, const int32_t *d_indices,
                      int64_t n_triangles, void *stream, rfrt_handle *out_mesh);
 RFRT_API int rfrt_mesh_destroy(rfrt_handle mesh);
+/* Material table for the reference-mode amplitude: tracer.py:43 hard-codes the refractive index n_1 = 5.0 in
+ * _bounce_amplitude; with a table the triangle of each path vertex supplies n_1 (receiver vertices keep 5.0).
+ *   d_refractive_index : [n_triangles] float32 (device; copied), or NULL to restore the reference's constant. */
+RFRT_API int rfrt_mesh_set_materials(rfrt_handle mesh, const float *d_refractive_index, void *stream);
 /* bounds6 = {lo.xyz, hi.xyz} (unpadded); any output pointer may be NULL. */
 RFRT_API int rfrt_mesh_info(rfrt_handle mesh, int64_t *n_triangles, int64_t *n_nodes, float *h_bounds6,
                    int32_t *max_depth, float *build_ms);

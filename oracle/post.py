@@ -37,13 +37,14 @@ def _dot32(a, b):
     return _f32(_f32(_f32(a[0] * b[0]) + _f32(a[1] * b[1])) + _f32(a[2] * b[2]))
 
 
-def bounce_amplitude(angle_between):
-    """tracer.py:34-61 (p-polarised Fresnel power reflectance, n1=5 -> n2=1, clamp, NaN -> 0)."""
+def bounce_amplitude(angle_between, n_1=5.0):
+    """tracer.py:34-61 (p-polarised Fresnel power reflectance, n1=5 -> n2=1, clamp, NaN -> 0).
+    n_1: material-table extension; the reference hard-codes 5.0."""
     angle_between = float(angle_between)
     if math.isnan(angle_between):
         return 0.0
     theta = (math.pi / 2) - (angle_between / 2)
-    n_1 = 5.0
+    n_1 = float(n_1)
     n_2 = 1.0
     theta_i = math.asin((n_2 * math.sin(theta)) / n_1)
     num = n_2 * math.cos(theta_i) - n_1 * math.cos(theta)
@@ -56,12 +57,13 @@ def bounce_amplitude(angle_between):
     return -amp
 
 
-def path_amplitude_delay(path, tx_power, tx_num_rays, light_speed_mps, sample_rate_hz):
-    """tracer.py:103-115 for one cleaned path -> (amplitude fp64, distance fp64, delay_samples int)."""
+def path_amplitude_delay(path, tx_power, tx_num_rays, light_speed_mps, sample_rate_hz, vertex_n=None):
+    """tracer.py:103-115 for one cleaned path -> (amplitude fp64, distance fp64, delay_samples int).
+    vertex_n: optional refractive index per path vertex (material table; default 5.0 = tracer.py:43)."""
     path = np.asarray(path, dtype=np.float32)
     amplitude = tx_power / tx_num_rays
     distance = 0.0
-    for p1, p2, p3 in zip(path[:-2], path[1:-1], path[2:]):
+    for k, (p1, p2, p3) in enumerate(zip(path[:-2], path[1:-1], path[2:])):
         seg1 = (p2 - p1).astype(np.float32)
         seg2 = (p3 - p2).astype(np.float32)
         seg1_len = _norm32(seg1)
@@ -73,18 +75,20 @@ def path_amplitude_delay(path, tx_power, tx_num_rays, light_speed_mps, sample_ra
             angle_between = _f32(np.nan)
         else:
             angle_between = _f32(math.acos(float(q)))
-        amplitude *= bounce_amplitude(angle_between)
+        amplitude *= bounce_amplitude(angle_between, 5.0 if vertex_n is None else vertex_n[k + 1])
         distance += float(seg1_len)
     distance += float(_norm32((path[-2] - path[-1]).astype(np.float32)))
     delay_samples = int((distance / light_speed_mps) * sample_rate_hz)
     return amplitude, distance, delay_samples
 
 
-def impulse_response(cleaned_paths, tx_power, tx_num_rays, light_speed_mps, sample_rate_hz, sample_window_s):
-    """tracer.py:101-117."""
+def impulse_response(cleaned_paths, tx_power, tx_num_rays, light_speed_mps, sample_rate_hz, sample_window_s,
+                     vertex_n=None):
+    """tracer.py:101-117.  vertex_n: optional list (one array per path) of per-vertex refractive indices."""
     ir = np.zeros(int(sample_window_s * sample_rate_hz))
-    for path in cleaned_paths:
-        amp, _, d = path_amplitude_delay(path, tx_power, tx_num_rays, light_speed_mps, sample_rate_hz)
+    for i, path in enumerate(cleaned_paths):
+        amp, _, d = path_amplitude_delay(path, tx_power, tx_num_rays, light_speed_mps, sample_rate_hz,
+                                         None if vertex_n is None else vertex_n[i])
         if d < ir.shape[0]:
             ir[d] += amp
     return ir

@@ -6,7 +6,8 @@
 
 The compute path is librfrt.so (rf_ray_tracing_warp_b200/csrc, C ABI in include/rfrt.h).  No CPU fallback.
 """
-from .mesh_io import Mesh, load_mesh, load_stl_triangles, mesh_from_triangles, synthetic_terrain, unit_icosphere
+from .mesh_io import (Mesh, load_mesh, load_stl_attributes, load_stl_triangles, materials_from_attributes,
+                      mesh_from_triangles, synthetic_terrain, unit_icosphere)
 from ._lib import RfrtError
 
 
@@ -18,5 +19,6 @@ def __getattr__(name):
     raise AttributeError(name)
 
 
-__all__ = ["Tracer", "to_dbm", "Mesh", "load_mesh", "load_stl_triangles", "mesh_from_triangles",
+__all__ = ["Tracer", "to_dbm", "Mesh", "load_mesh", "load_stl_attributes", "load_stl_triangles", "materials_from_attributes",
+           "mesh_from_triangles",
            "synthetic_terrain", "unit_icosphere", "RfrtError"]

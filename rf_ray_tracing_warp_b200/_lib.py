@@ -29,6 +29,7 @@ SIGNATURES = {
     "rfrt_device_info": (ctypes.c_int, [ctypes.POINTER(c_i32)] * 3),
     "rfrt_mesh_create": (ctypes.c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, ctypes.POINTER(c_u64)]),
     "rfrt_mesh_destroy": (ctypes.c_int, [c_u64]),
+    "rfrt_mesh_set_materials": (ctypes.c_int, [c_u64, c_void_p, c_void_p]),
     "rfrt_mesh_info": (ctypes.c_int, [c_u64, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_f),
                                       ctypes.POINTER(c_i32), ctypes.POINTER(c_f)]),
     "rfrt_mesh_export": (ctypes.c_int, [c_u64, c_void_p, c_void_p, c_void_p]),

@@ -45,6 +45,10 @@ def main(argv=None):
     ap.add_argument("--rays", type=int, default=TX_NUM_RAYS)
     ap.add_argument("--bounces", type=int, default=MAX_BOUNCES)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--mode", default="reference", choices=["reference", "physical"],
+                    help="reference = coverage.py:43-55 per receiver; physical = Tracer.trace_physical (free-space "
+                         "loss, Fresnel amplitude, carrier phase; analytic-sphere receivers)")
+    ap.add_argument("--carrier", type=float, default=2.4e9)              # coverage.py:46
     args = ap.parse_args(argv)
 
     from . import Tracer, load_mesh
@@ -55,7 +59,11 @@ def main(argv=None):
         rx, shape = plane_lattice(nx, ny, z=args.z), (nx, ny)
     tracer = Tracer(load_mesh(args.model), LIGHT_SPEED_MPS, SAMPLE_RATE_HZ, SAMPLE_WINDOW_S, args.bounces, args.rays,
                     max_candidates=1 << 22, max_records=1 << 22)
-    cov = tracer.coverage(np.array(args.tx), args.tx_power, rx, args.rx_radius)
+    if args.mode == "physical":
+        cov = tracer.trace_physical(np.array(args.tx), args.tx_power, rx, args.rx_radius, carrier_hz=args.carrier)
+        cov["dbm"] = np.where(cov["power"] > 0, cov["dbm"], np.nan)
+    else:
+        cov = tracer.coverage(np.array(args.tx), args.tx_power, rx, args.rx_radius, carrier_hz=args.carrier)
     dbm = cov["dbm"].reshape(shape)
     covered = int(np.isfinite(dbm).sum())
     print(f"coverage: {rx.shape[0]} receivers, {covered} with signal, "

@@ -223,10 +223,30 @@ extern "C" int rfrt_mesh_destroy(rfrt_handle mesh)
     if (m->normals) cudaFree(m->normals);
     if (m->face_normals) cudaFree(m->face_normals);
     if (m->small) cudaFree(m->small);
+    if (m->materials) cudaFree(m->materials);
     if (m->ray_keys[0]) cudaFree(m->ray_keys[0]);
     if (m->ray_keys[1]) cudaFree(m->ray_keys[1]);
     if (m->ray_hist) cudaFree(m->ray_hist);
     delete m;
+    return RFRT_OK;
+}
+
+extern "C" int rfrt_mesh_set_materials(rfrt_handle mesh, const float *d_refractive_index, void *stream_)
+{
+    Mesh *m = get_mesh(mesh);
+    if (!m) { set_error("rfrt_mesh_set_materials: unknown handle"); return RFRT_ERR_HANDLE; }
+    if (!d_refractive_index) {
+        if (m->materials) cudaFree(m->materials);
+        m->materials = nullptr;
+        return RFRT_OK;
+    }
+    if (m->bvh.n_prims >= 32768) {
+        set_error("rfrt_mesh_set_materials: the reference-mode material table supports fewer than 32768 triangles");
+        return RFRT_ERR_INVALID;
+    }
+    if (!m->materials) RFRT_CUDA(cudaMalloc(&m->materials, sizeof(float) * (size_t)(m->bvh.n_prims > 0 ? m->bvh.n_prims : 1)));
+    RFRT_CUDA(cudaMemcpyAsync(m->materials, d_refractive_index, sizeof(float) * (size_t)m->bvh.n_prims, cudaMemcpyDeviceToDevice,
+                              (cudaStream_t)stream_));
     return RFRT_OK;
 }
 

@@ -49,6 +49,7 @@ struct Mesh {
     int32_t small_pairs = 0;
     float small_extent = 0.0f;
     float build_ms = 0.0f;
+    float *materials = nullptr;  // [n] refractive index per triangle (rfrt_mesh_set_materials) or NULL = 5.0 everywhere
     // BVH scenes: workspace of the direction-coherent ray order (grown on demand by rfrt_trace, freed with the mesh)
     uint64_t *ray_keys[2] = {nullptr, nullptr};
     uint32_t *ray_hist = nullptr;

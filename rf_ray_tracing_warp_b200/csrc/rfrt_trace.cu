@@ -371,6 +371,7 @@ __device__ __forceinline__ void literal_trace(const LiteralEnv &E, const RxView 
         } else if (maybe_hit_env) {
             pos = advance(pos, dir, h.t);   // :94
             sink.vertex(bounce + 1, pos);   // :95
+            sink.env_face(bounce + 1, h.face);
             float3 a, b, c; int idx;
             tri_vertices(E.tris, h.slot, a, b, c, idx);
             dir = reflect(dir, tri_normal(a, b, c)); // :96
@@ -384,6 +385,7 @@ struct CompatSink {
     float *traced;
     float *recv_row;
     uint32_t *mask;
+    __device__ __forceinline__ void env_face(int, int) {}
     __device__ __forceinline__ void vertex(int i, float3 p)
     {
         traced[3 * i] = p.x; traced[3 * i + 1] = p.y; traced[3 * i + 2] = p.z;
@@ -412,8 +414,11 @@ k_trace_compat(LiteralEnv E, RxView rx, int has_rx, int n_faces, float3 tx, int 
 
 struct RecordSink {
     float path[3 * (MAX_RECV_BOUNCES + 1)];
+    short face[MAX_RECV_BOUNCES + 1]; // triangle of an environment vertex, -1 for tx / receiver vertices (materials)
     int last_rx_bounce;
     int first_rx_bounce;
+    bool want_faces;
+    __device__ __forceinline__ void env_face(int i, int f) { if (want_faces) face[i] = (short)f; }
     __device__ __forceinline__ void vertex(int i, float3 p)
     {
         path[3 * i] = p.x; path[3 * i + 1] = p.y; path[3 * i + 2] = p.z;
@@ -431,12 +436,12 @@ __device__ __forceinline__ float norm3_f32(float x, float y, float z)
 }
 
 // tracer.py:34-61
-__device__ __forceinline__ double bounce_amplitude(double angle_between)
+__device__ __forceinline__ double bounce_amplitude(double angle_between, double n_1 = 5.0)
 {
     if (isnan(angle_between)) return 0.0;
     const double PI = 3.141592653589793;
     double theta = PI / 2 - angle_between / 2;
-    const double n_1 = 5.0, n_2 = 1.0;
+    const double n_2 = 1.0;
     double theta_i = asin((n_2 * sin(theta)) / n_1);
     double num = n_2 * cos(theta_i) - n_1 * cos(theta);
     double denom = n_2 * cos(theta_i) + n_1 * cos(theta);
@@ -449,6 +454,7 @@ __device__ __forceinline__ double bounce_amplitude(double angle_between)
 
 struct ReceiveParams {
     LiteralEnv env;
+    const float *materials; // [n_tris] refractive index per triangle (rfrt_mesh_set_materials) or NULL
     const float *rx_verts;
     const double *rx_centers;
     const BvhNode *unit_nodes;
@@ -490,6 +496,9 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_receive(const ReceivePa
         RecordSink sink;
         sink.last_rx_bounce = -1;
         sink.first_rx_bounce = -1;
+        sink.want_faces = P.materials != nullptr;
+        if (sink.want_faces)
+            for (int v = 0; v <= P.max_bounces; ++v) sink.face[v] = -1;
         RxView rx;
         rx.verts = P.rx_verts + (int64_t)cand.y * P.n_unit * 3;
         rx.unit_nodes = P.unit_nodes; rx.unit_order = P.unit_order;
@@ -518,7 +527,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_receive(const ReceivePa
                 float q = __fdiv_rn(dot, __fmul_rn(l1, l2));
                 float angle = (q > 1.0f || q < -1.0f || isnan(q)) ? __int_as_float(0x7fc00000)
                                                                    : __double2float_rn(acos((double)q));
-                amplitude *= bounce_amplitude((double)angle);
+                // tracer.py:43 hard-codes n_1 = 5; with a material table the vertex's triangle decides
+                double n_1 = 5.0;
+                if (P.materials && sink.face[v + 1] >= 0) n_1 = (double)__ldg(P.materials + sink.face[v + 1]);
+                amplitude *= bounce_amplitude((double)angle, n_1);
                 distance = __dadd_rn(distance, (double)l1);
             }
             const float *u = p + 3 * (nverts - 2), *w = p + 3 * (nverts - 1);
@@ -741,6 +753,7 @@ extern "C" int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const
     }
     ReceiveParams P;
     P.env.nodes = m->bvh.nodes; P.env.tris = m->tris; P.env.n_tris = m->bvh.n_prims;
+    P.materials = (m->materials && m->bvh.n_prims < 32768) ? m->materials : nullptr;
     P.rx_verts = r->verts; P.n_unit = r->n_unit; P.n_faces = r->n_faces;
     P.rx_centers = r->centers; P.unit_nodes = r->unit_bvh.nodes; P.unit_order = r->unit_bvh.prim_order;
     P.inv_r = (float)(1.0 / r->radius);

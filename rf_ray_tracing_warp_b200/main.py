@@ -27,7 +27,9 @@ def main(argv=None):
     ap.add_argument("--rx-radius", type=float, default=0.1)              # main.py:34
     ap.add_argument("--rays", type=int, default=TX_NUM_RAYS)
     ap.add_argument("--bounces", type=int, default=MAX_BOUNCES)
-    ap.add_argument("--out", default=None, help="directory for impulse_response.npy / paths.npz / result.json")
+    ap.add_argument("--out", default=None, help="directory for impulse_response.npy / paths.npz / result.json / scene.glb")
+    ap.add_argument("--scene", default="glb", choices=["glb", "html", "none"],
+                    help="scene export written next to the results (replaces viz/visualization.py)")
     args = ap.parse_args(argv)
 
     from . import Tracer, load_mesh, to_dbm
@@ -46,6 +48,9 @@ def main(argv=None):
         np.savez(os.path.join(args.out, "paths.npz"), *paths)
         with open(os.path.join(args.out, "result.json"), "w") as f:
             json.dump(result, f)
+        if args.scene != "none":  # main.py:67 visualize(mesh, tx_pos, rx_pos, paths)
+            from .scene_export import export_scene
+            export_scene(os.path.join(args.out, "scene." + args.scene), mesh, args.tx, args.rx, paths)
     return result
 
 

@@ -46,6 +46,28 @@ def load_stl_triangles(path):
     return _parse_ascii_stl(raw.decode("ascii", errors="replace"))
 
 
+def load_stl_attributes(path):
+    """(F,) uint16 "attribute byte count" word of every facet of a binary STL (zeros for ASCII).  room.stl carries
+    20083 on every facet; CAD exporters use the word for colour / material ids."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    if len(raw) >= 84:
+        count = int(np.frombuffer(raw, dtype="<u4", count=1, offset=80)[0])
+        if len(raw) == 84 + 50 * count:
+            rec = np.dtype([("n", "<f4", (3,)), ("v", "<f4", (3, 3)), ("attr", "<u2")])
+            return np.ascontiguousarray(np.frombuffer(raw, dtype=rec, count=count, offset=84)["attr"])
+    return np.zeros(load_stl_triangles(path).shape[0], dtype=np.uint16)
+
+
+def materials_from_attributes(attributes, table, default=5.0):
+    """Per-triangle refractive index from the STL attribute words: ``table`` maps word -> index; anything else gets
+    ``default`` (the reference's hard-coded 5.0, tracer.py:43)."""
+    out = np.full(len(attributes), float(default), dtype=np.float32)
+    for word, n in table.items():
+        out[np.asarray(attributes) == int(word)] = float(n)
+    return out
+
+
 def load_mesh(path):
     """Equivalent of ``trimesh.load_mesh`` for STL: bit-identical corners are merged into shared vertices;
     face order and winding are the file's, no face is dropped.  Triangle i == facet i of the file."""

@@ -322,15 +322,20 @@ class Tracer:
 
     # ------------------------------------------------------------------------------------------
     def set_materials(self, refractive_index):
-        """Per-triangle refractive index (array of n_triangles floats; None = 5.0 everywhere, tracer.py:43).  Used by
-        ``trace_physical``."""
+        """Per-triangle refractive index (array of n_triangles floats; None = 5.0 everywhere, tracer.py:43): the n_1
+        of ``_bounce_amplitude`` (tracer.py:43) in compute_cir / coverage, and the Fresnel index of ``trace_physical``."""
         if refractive_index is None:
             self._materials = None
+            check(self._lib.rfrt_mesh_set_materials(self._env, None, _stream_ptr()), "rfrt_mesh_set_materials")
             return
         mat = np.ascontiguousarray(np.asarray(refractive_index, dtype=np.float32).reshape(-1))
         if mat.shape[0] != self.mesh_info()["n_triangles"]:
             raise ValueError("set_materials: need one refractive index per triangle")
         self._materials = torch.from_numpy(mat).to(self.device)
+        if mat.shape[0] < 32768:  # reference mode keeps per-vertex triangle ids as 16-bit
+            with torch.cuda.device(self.device):
+                check(self._lib.rfrt_mesh_set_materials(self._env, _ptr(self._materials), _stream_ptr()),
+                      "rfrt_mesh_set_materials")
 
     def trace_physical(self, tx_pos, tx_power, rx_positions, rx_radius, carrier_hz=2.4e9, want_ir=False):
         """Physical mode (rfrt_trace_physical; NOT reference behaviour, see include/rfrt.h): no t ~ 0 re-hits,

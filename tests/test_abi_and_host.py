@@ -102,3 +102,26 @@ def test_synthetic_terrain_is_deterministic():
     assert np.array_equal(a.vertices, b.vertices) and np.array_equal(a.faces, b.faces)
     assert a.faces.shape == (2048, 3) and np.abs(a.vertices[:, 2]).max() <= 1.5
     assert not np.array_equal(a.vertices, synthetic_terrain(32, seed=18).vertices)
+
+
+def test_scene_export_round_trip_and_reads_trimesh_pages(tmp_path, room_stl):
+    """viz/visualization.py replacement: GLB/HTML written by export_scene parse back to the same polylines, and the
+    reader also understands a trimesh scene_to_html page (structure of the reference's web/scene.html)."""
+    from rf_ray_tracing_warp_b200 import load_mesh
+    from rf_ray_tracing_warp_b200.scene_export import export_scene, read_glb_paths
+    rng = np.random.default_rng(0)
+    paths = [rng.normal(size=(k, 3)).astype(np.float32) for k in (2, 3, 5, 4)]
+    for name in ("scene.glb", "scene.html"):
+        p = tmp_path / name
+        assert export_scene(str(p), load_mesh(room_stl), [10, 0, 5], [-10, 0, 5], paths) > 2000
+        back = read_glb_paths(str(p))
+        assert len(back) == len(paths) and all(np.array_equal(a, b) for a, b in zip(back, paths))
+
+
+def test_stl_attribute_words_and_material_table(room_stl, almost_empty_stl):
+    from rf_ray_tracing_warp_b200 import load_stl_attributes, materials_from_attributes
+    a = load_stl_attributes(room_stl)
+    assert a.dtype == np.uint16 and a.shape == (44,) and np.all(a == 20083)  # SURVEY.md 2.1 row 7
+    assert np.all(load_stl_attributes(almost_empty_stl) == 0)
+    m = materials_from_attributes(np.array([1, 2, 2, 7]), {2: 3.5, 7: 1.2})
+    assert m.dtype == np.float32 and np.allclose(m, [5.0, 3.5, 3.5, 1.2])

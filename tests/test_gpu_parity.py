@@ -277,3 +277,39 @@ def test_fused_directions_equal_buffered_directions(torch_cuda, room_stl):
     for k in out["fused"][1]:
         a, b = out["fused"][1][k], out["buffer"][1][k]
         assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), k
+
+
+def test_material_table_in_reference_mode(torch_cuda, room_stl):
+    """per-triangle refractive index instead of tracer.py:43's hard-coded n_1 = 5.  Paths are
+    unchanged (materials do not steer rays); every interior path vertex on an environment triangle takes that
+    triangle's index, receiver vertices keep 5.0."""
+    from oracle import cpu, geometry, post
+    from rf_ray_tracing_warp_b200 import load_mesh, load_stl_attributes, materials_from_attributes
+    n, B, tx, rx, r = 1 << 18, 4, [10, 0, 5], [3.0, 6.0, 5.0], 0.5
+    soup = geometry.load_stl_soup(room_stl)
+    attrs = load_stl_attributes(room_stl)
+    assert attrs.shape == (44,) and np.all(attrs == 20083)
+    mats = materials_from_attributes(attrs, {20083: 3.0})
+    mats[::3] = np.linspace(1.5, 9.0, len(mats[::3]))  # and some variety
+    tr = _tracer(load_mesh(room_stl), B, n)
+    base_paths, base_ir = tr.compute_cir(tx, 1, rx, r)
+    tr.set_materials(mats)
+    paths, ir = tr.compute_cir(tx, 1, rx, r)
+    assert len(paths) == len(base_paths) and all(np.array_equal(a, b) for a, b in zip(paths, base_paths))
+    assert not np.allclose(ir, base_ir)
+    o = cpu.trace_paths(soup, geometry.rx_soup(rx, r), tx, B, 0, n)
+    o_paths = post.clean_paths(o["received"], o["mask"])
+    rows = np.nonzero(o["mask"])[0]
+    vertex_n = []
+    for row, p in zip(rows, o_paths):
+        vn = np.full(len(p), 5.0)
+        for b in range(len(p) - 1):
+            if o["event"][row, b] == 1:
+                vn[b + 1] = mats[o["hit_tri"][row, b]]
+        vertex_n.append(vn)
+    o_ir = post.impulse_response(o_paths, 1, n, C, 100e9, 200e-9, vertex_n=vertex_n)
+    assert np.array_equal(ir != 0, o_ir != 0)
+    np.testing.assert_allclose(ir, o_ir, rtol=1e-5, atol=1e-12 / n)
+    tr.set_materials(None)
+    _, ir5 = tr.compute_cir(tx, 1, rx, r)
+    assert np.array_equal(ir5, base_ir)
