@@ -69,23 +69,39 @@ __global__ void k_bin_ordered(const int32_t *__restrict__ rx, const int64_t *__r
     }
 }
 
-// same result with one CTA per receiver: thread j owns the bins b with b % blockDim == j and walks the receiver's
-// records in order, so every bin still sees its additions in ray-id order (few receivers, many records each)
+// same result with one CTA per receiver: thread j owns the bins b with b % blockDim == j; the receiver's records are
+// staged tile by tile in shared memory (coalesced) and every thread walks the tile in order, so every bin still sees
+// its additions in ray-id order (few receivers, many records each)
 __global__ void __launch_bounds__(256) k_bin_ordered_cta(const int32_t *__restrict__ rx, const int64_t *__restrict__ bin,
                                                          const double *__restrict__ amp, int64_t n,
                                                          const unsigned long long *d_n, int64_t n_bins, double *ir)
 {
+    __shared__ int64_t s_bin[256];
+    __shared__ double s_amp[256];
     const int64_t k = blockIdx.x;
     if (d_n && (int64_t)*d_n < n) n = (int64_t)*d_n;
-    int64_t lo = 0, hi = n; // lower_bound of k
+    int64_t lo = 0, hi = n; // [lo, hi) = the records of receiver k (records are sorted by receiver)
     while (lo < hi) {
         int64_t mid = (lo + hi) >> 1;
         if (rx[mid] < k) lo = mid + 1; else hi = mid;
     }
+    int64_t end = lo, top = n;
+    while (end < top) {
+        int64_t mid = (end + top) >> 1;
+        if (rx[mid] <= k) end = mid + 1; else top = mid;
+    }
     double *row = ir + k * n_bins;
-    for (int64_t i = lo; i < n && rx[i] == k; ++i) {
-        const int64_t b = bin[i];
-        if (b >= 0 && b < n_bins && (int)(b % blockDim.x) == (int)threadIdx.x) row[b] = __dadd_rn(row[b], amp[i]);
+    for (int64_t base = lo; base < end; base += 256) {
+        const int64_t i = base + threadIdx.x;
+        s_bin[threadIdx.x] = i < end ? bin[i] : -1;
+        s_amp[threadIdx.x] = i < end ? amp[i] : 0.0;
+        __syncthreads();
+        const int cnt = (int)(end - base < 256 ? end - base : 256);
+        for (int j = 0; j < cnt; ++j) {
+            const int64_t b = s_bin[j];
+            if (b >= 0 && b < n_bins && (int)(b & 255) == (int)threadIdx.x) row[b] = __dadd_rn(row[b], s_amp[j]);
+        }
+        __syncthreads();
     }
 }
 

@@ -51,7 +51,7 @@ class Tracer:
     """
 
     def __init__(self, environment_trimesh, light_speed_mps, sample_rate_hz, sample_window_s, max_bounces,
-                 tx_num_rays, *, device=None, ray_range=None, shard=False, chunk_rays=1 << 24,
+                 tx_num_rays, *, device=None, ray_range=None, shard=False, chunk_rays=1 << 26,
                  max_candidates=1 << 20, max_records=1 << 20, verbose=False, force_bvh=False):
         if not torch.cuda.is_available():
             raise RfrtError("rf_ray_tracing_warp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
