@@ -136,3 +136,44 @@ def test_far_receiver_uses_exact_fallback(torch_cuda, almost_empty_stl):
     assert sorted(expect) == sorted(int(t) & 0xFFFFFFFF for t in rec["ray"])
     for t, row, nv in zip(rec["ray"], rec["paths"], rec["nverts"]):
         assert np.array_equal(row[:nv], expect[int(t) & 0xFFFFFFFF])
+
+
+@pytest.mark.parametrize("case", ["far_from_origin", "many_planes_fallback", "degenerates_and_duplicates", "box_rooms"])
+def test_small_scene_sweep_equals_bvh_and_oracle(torch_cuda, case):
+    """The shared-memory sweep (candidate filter + nearest-first exact tests + self-re-hit shortcut) on awkward small
+    scenes: hit triangle / distance per (ray, bounce) == oracle, and the order-independent checksum == the BVH walk."""
+    from oracle import cpu
+    from rf_ray_tracing_warp_b200 import Tracer
+    rng = np.random.default_rng(11)
+    if case == "far_from_origin":      # large coordinates: the filter tolerance scales with |coordinate|
+        tris = rng.uniform(-3, 3, size=(24, 3, 3)).astype(np.float32) + np.array([1000.0, -2000.0, 500.0], dtype=np.float32)
+        tx = [1000.2, -2000.1, 500.3]
+    elif case == "many_planes_fallback":  # 40 distinct planes need 80 filter slots -> the BVH path takes over
+        tris = rng.uniform(-3, 3, size=(40, 3, 3)).astype(np.float32)
+        tx = [0.1, 0.2, 0.3]
+    elif case == "degenerates_and_duplicates":
+        tris = rng.uniform(-3, 3, size=(20, 3, 3)).astype(np.float32)
+        tris[3] = tris[2]                      # exact duplicate: equal-t tie -> lowest index
+        tris[5, 2] = tris[5, 1]                # two equal vertices
+        tris[7, 2] = 0.5 * (tris[7, 0] + tris[7, 1])  # collinear
+        tris[9] = np.float32(1.25)             # a point
+        tx = [0.0, 0.1, -0.2]
+    else:                                    # nested axis-aligned boxes: coplanar pairs, T-junction-free rooms, rays stuck at t == 0
+        def box(lo, hi):
+            x0, y0, z0 = lo; x1, y1, z1 = hi
+            v = np.array([[x0, y0, z0], [x1, y0, z0], [x1, y1, z0], [x0, y1, z0], [x0, y0, z1], [x1, y0, z1], [x1, y1, z1], [x0, y1, z1]], np.float32)
+            f = [[0, 1, 2], [0, 2, 3], [4, 6, 5], [4, 7, 6], [0, 5, 1], [0, 4, 5], [1, 6, 2], [1, 5, 6], [2, 7, 3], [2, 6, 7], [3, 4, 0], [3, 7, 4]]
+            return v[np.array(f)]
+        tris = np.concatenate([box((-4, -3, 0), (4, 3, 3)), box((-1, -1, 0), (1, 1, 3)), box((2, -3, 0), (4, -1, 1))]).astype(np.float32)
+        tx = [-2.5, 0.5, 1.5]
+    n, B = 1 << 17, 7
+    res = {}
+    for force_bvh in (False, True):
+        tr = Tracer(_mesh(tris), C, 100e9, 200e-9, B, n, force_bvh=force_bvh)
+        res[force_bvh] = tr.trace_segments(tx, dump=True)
+    seg, tri, t = cpu.trace_env(tris, tx, B, 0, n)
+    for k in (False, True):
+        assert res[k]["segments"] == seg and (tri >= 0).sum() > 1000
+        assert np.array_equal(res[k]["hit_tri"].cpu().numpy(), tri), (case, k)
+        assert np.array_equal(res[k]["hit_t"].cpu().numpy().view(np.uint32), t.view(np.uint32)), (case, k)
+    assert res[False]["checksum"] == res[True]["checksum"]
