@@ -285,6 +285,7 @@ extern "C" int rfrt_rxset_create(const double *d_centers_xyz, int64_t n_receiver
         set_error("rfrt_rxset_create: bad arguments (need 1..255 unit vertices, 1..128 faces, radius > 0)");
         return RFRT_ERR_INVALID;
     }
+    keep_pool_memory();
     std::unique_ptr<RxSet> r(new RxSet());
     r->n_receivers = n_receivers; r->n_unit = n_unit_vertices; r->n_faces = n_faces; r->radius = radius;
     for (int i = 0; i < 3 * n_faces; ++i) {
@@ -293,11 +294,11 @@ extern "C" int rfrt_rxset_create(const double *d_centers_xyz, int64_t n_receiver
     }
     double *d_unit = nullptr;
     float4 *lo = nullptr, *hi = nullptr;
-    RFRT_CUDA(cudaMalloc(&d_unit, sizeof(double) * 3 * n_unit_vertices));
-    RFRT_CUDA(cudaMalloc(&r->centers, sizeof(double) * 3 * n_receivers));
-    RFRT_CUDA(cudaMalloc(&r->verts, sizeof(float) * 3 * n_unit_vertices * n_receivers));
-    RFRT_CUDA(cudaMalloc(&lo, sizeof(float4) * n_receivers));
-    RFRT_CUDA(cudaMalloc(&hi, sizeof(float4) * n_receivers));
+    RFRT_CUDA(cudaMallocAsync(&d_unit, sizeof(double) * 3 * n_unit_vertices, stream));
+    RFRT_CUDA(cudaMallocAsync(&r->centers, sizeof(double) * 3 * n_receivers, stream));
+    RFRT_CUDA(cudaMallocAsync(&r->verts, sizeof(float) * 3 * n_unit_vertices * n_receivers, stream));
+    RFRT_CUDA(cudaMallocAsync(&lo, sizeof(float4) * n_receivers, stream));
+    RFRT_CUDA(cudaMallocAsync(&hi, sizeof(float4) * n_receivers, stream));
     RFRT_CUDA(cudaMemcpyAsync(d_unit, h_unit_vertices, sizeof(double) * 3 * n_unit_vertices, cudaMemcpyHostToDevice, stream));
     RFRT_CUDA(cudaMemcpyAsync(r->centers, d_centers_xyz, sizeof(double) * 3 * n_receivers, cudaMemcpyDeviceToDevice, stream));
     const int T = 128;
@@ -305,8 +306,8 @@ extern "C" int rfrt_rxset_create(const double *d_centers_xyz, int64_t n_receiver
                                                                            n_unit_vertices, r->verts, lo, hi);
     RFRT_CUDA(cudaGetLastError());
     int rc = build_lbvh(lo, hi, n_receivers, stream, &r->bvh);
-    cudaFree(d_unit); cudaFree(lo); cudaFree(hi);
-    if (rc) { cudaFree(r->centers); cudaFree(r->verts); return rc; }
+    cudaFreeAsync(d_unit, stream); cudaFreeAsync(lo, stream); cudaFreeAsync(hi, stream);
+    if (rc) { cudaFreeAsync(r->centers, stream); cudaFreeAsync(r->verts, stream); return rc; }
     {
         // BVH over the unit icosphere's faces, used (after mapping the ray into unit space) to prune the exact
         // per-receiver triangle tests.  Boxes are inflated: the mapping (o - c) / r is only approximate in fp32.
@@ -323,13 +324,13 @@ extern "C" int rfrt_rxset_create(const double *d_centers_xyz, int64_t n_receiver
             uhi[f] = make_float4(h[0] + infl, h[1] + infl, h[2] + infl, 0.f);
         }
         float4 *dlo = nullptr, *dhi = nullptr;
-        RFRT_CUDA(cudaMalloc(&dlo, sizeof(float4) * n_faces));
-        RFRT_CUDA(cudaMalloc(&dhi, sizeof(float4) * n_faces));
+        RFRT_CUDA(cudaMallocAsync(&dlo, sizeof(float4) * n_faces, stream));
+        RFRT_CUDA(cudaMallocAsync(&dhi, sizeof(float4) * n_faces, stream));
         RFRT_CUDA(cudaMemcpyAsync(dlo, ulo.data(), sizeof(float4) * n_faces, cudaMemcpyHostToDevice, stream));
         RFRT_CUDA(cudaMemcpyAsync(dhi, uhi.data(), sizeof(float4) * n_faces, cudaMemcpyHostToDevice, stream));
         rc = build_lbvh(dlo, dhi, n_faces, stream, &r->unit_bvh); // synchronises the stream
-        cudaFree(dlo); cudaFree(dhi);
-        if (rc) { cudaFree(r->centers); cudaFree(r->verts); free_bvh(&r->bvh); return rc; }
+        cudaFreeAsync(dlo, stream); cudaFreeAsync(dhi, stream);
+        if (rc) { cudaFreeAsync(r->centers, stream); cudaFreeAsync(r->verts, stream); free_bvh(&r->bvh); return rc; }
     }
     std::lock_guard<std::mutex> lock(g_mutex);
     rfrt_handle h = g_next_handle++;
@@ -350,8 +351,8 @@ extern "C" int rfrt_rxset_destroy(rfrt_handle rxset)
     }
     free_bvh(&r->bvh);
     free_bvh(&r->unit_bvh);
-    if (r->verts) cudaFree(r->verts);
-    if (r->centers) cudaFree(r->centers);
+    if (r->verts) cudaFreeAsync(r->verts, 0);
+    if (r->centers) cudaFreeAsync(r->centers, 0);
     delete r;
     return RFRT_OK;
 }

@@ -320,16 +320,33 @@ __global__ void k_prim_order(const uint64_t *__restrict__ keys, int64_t n, int32
 
 } // namespace
 
+// (stream-ordered frees on the legacy default stream: no device-wide synchronisation as with cudaFree)
 void free_bvh(Bvh *b)
 {
-    if (b->nodes) cudaFree(b->nodes);
-    if (b->prim_order) cudaFree(b->prim_order);
+    if (b->nodes) cudaFreeAsync(b->nodes, 0);
+    if (b->prim_order) cudaFreeAsync(b->prim_order, 0);
     b->nodes = nullptr;
     b->prim_order = nullptr;
 }
 
+// Stream-ordered allocations come from the device's default memory pool; without a release threshold the pool gives
+// its memory back at every synchronisation and the next build pays for cudaMalloc again.
+void keep_pool_memory()
+{
+    static bool done = false;
+    if (done) return;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t threshold = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    done = true;
+}
+
 int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t stream, Bvh *out)
 {
+    keep_pool_memory();
     *out = Bvh();
     out->n_prims = n;
     if (n <= 0) return RFRT_OK;
@@ -345,18 +362,18 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
     int2 *children = nullptr;
     const int64_t n_nodes = n > 1 ? n - 1 : 1;
 
-    RFRT_CUDA(cudaMalloc(&keys_a, sizeof(uint64_t) * n));
-    RFRT_CUDA(cudaMalloc(&keys_b, sizeof(uint64_t) * n));
-    RFRT_CUDA(cudaMalloc(&ghist, sizeof(uint32_t) * 256 * ((size_t)nblocks + 1)));
-    RFRT_CUDA(cudaMalloc(&bounds_enc, sizeof(int) * 8));
-    RFRT_CUDA(cudaMalloc(&d_bounds, sizeof(float) * 8));
-    RFRT_CUDA(cudaMalloc(&node_parent, sizeof(int) * n_nodes));
-    RFRT_CUDA(cudaMalloc(&leaf_parent, sizeof(int) * n));
-    RFRT_CUDA(cudaMalloc(&arrive, sizeof(int) * n_nodes));
-    RFRT_CUDA(cudaMalloc(&children, sizeof(int2) * n_nodes));
-    RFRT_CUDA(cudaMalloc(&d_depth, sizeof(int)));
-    RFRT_CUDA(cudaMalloc(&out->nodes, sizeof(BvhNode) * n_nodes));
-    RFRT_CUDA(cudaMalloc(&out->prim_order, sizeof(int32_t) * n));
+    RFRT_CUDA(cudaMallocAsync(&keys_a, sizeof(uint64_t) * n, stream));
+    RFRT_CUDA(cudaMallocAsync(&keys_b, sizeof(uint64_t) * n, stream));
+    RFRT_CUDA(cudaMallocAsync(&ghist, sizeof(uint32_t) * 256 * ((size_t)nblocks + 1), stream));
+    RFRT_CUDA(cudaMallocAsync(&bounds_enc, sizeof(int) * 8, stream));
+    RFRT_CUDA(cudaMallocAsync(&d_bounds, sizeof(float) * 8, stream));
+    RFRT_CUDA(cudaMallocAsync(&node_parent, sizeof(int) * n_nodes, stream));
+    RFRT_CUDA(cudaMallocAsync(&leaf_parent, sizeof(int) * n, stream));
+    RFRT_CUDA(cudaMallocAsync(&arrive, sizeof(int) * n_nodes, stream));
+    RFRT_CUDA(cudaMallocAsync(&children, sizeof(int2) * n_nodes, stream));
+    RFRT_CUDA(cudaMallocAsync(&d_depth, sizeof(int), stream));
+    RFRT_CUDA(cudaMallocAsync(&out->nodes, sizeof(BvhNode) * n_nodes, stream));
+    RFRT_CUDA(cudaMallocAsync(&out->prim_order, sizeof(int32_t) * n, stream));
 
     const int T = 256;
     const int nb = (int)((n + T - 1) / T);
@@ -397,8 +414,8 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
     RFRT_CUDA(cudaStreamSynchronize(stream));
     RFRT_CUDA(cudaGetLastError());
 
-    cudaFree(keys_a); cudaFree(keys_b); cudaFree(ghist); cudaFree(bounds_enc); cudaFree(d_bounds);
-    cudaFree(node_parent); cudaFree(leaf_parent); cudaFree(arrive); cudaFree(children); cudaFree(d_depth);
+    cudaFreeAsync(keys_a, stream); cudaFreeAsync(keys_b, stream); cudaFreeAsync(ghist, stream); cudaFreeAsync(bounds_enc, stream); cudaFreeAsync(d_bounds, stream);
+    cudaFreeAsync(node_parent, stream); cudaFreeAsync(leaf_parent, stream); cudaFreeAsync(arrive, stream); cudaFreeAsync(children, stream); cudaFreeAsync(d_depth, stream);
     return RFRT_OK;
 }
 

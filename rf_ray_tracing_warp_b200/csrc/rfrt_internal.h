@@ -81,6 +81,7 @@ int cuda_fail(cudaError_t e, const char *what);
 // Allocates bvh.nodes / bvh.prim_order.  Synchronises the stream.
 int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t stream, Bvh *out);
 void free_bvh(Bvh *b);
+void keep_pool_memory();
 int64_t sort_hist_blocks(int64_t n);
 uint64_t *radix_sort_u64(uint64_t *a, uint64_t *b, uint32_t *hist, int64_t n, int shift, int passes, cudaStream_t stream);
 

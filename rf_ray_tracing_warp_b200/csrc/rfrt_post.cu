@@ -159,7 +159,11 @@ k_rx_power(const int64_t *__restrict__ offsets, const int32_t *__restrict__ abin
 // bin the valid j form a contiguous range -> a prefix-sum difference.  Agrees with the direct sum to ~1e-13
 // relative; a sample counts as non-zero exactly when the direct sum has a non-zero term (np.nonzero, main.py:48).
 constexpr int RXP_THREADS = 256;
-constexpr int RXP_CAP = 6144; // arrivals staged in shared memory per receiver
+// arrivals staged in shared memory per receiver: a first launch with the small capacity (20 KB -> ~10 CTAs per SM; one
+// 123 KB CTA per SM left the row reads latency-bound: 25 ms for 65 536 x 10 000 bins) marks the rare denser rows with
+// power = -1, a second launch with the large capacity redoes just those
+constexpr int RXP_CAP_SMALL = 1024;
+constexpr int RXP_CAP_BIG = 6144;
 
 __device__ __forceinline__ double stx_arg(int64_t m, int64_t n_bins, double window, double K)
 {
@@ -170,9 +174,11 @@ __device__ __forceinline__ double stx_arg(int64_t m, int64_t n_bins, double wind
     return __dmul_rn(K, t);
 }
 
+template <int RXP_CAP, bool SECOND>
 __global__ void __launch_bounds__(RXP_THREADS)
 k_rx_power_dense(const double *__restrict__ ir, int64_t n_bins, double window, double carrier, double *__restrict__ power)
 {
+    if (SECOND && power[blockIdx.x] != -1.0) return; // only the rows the first launch could not stage
     extern __shared__ double s_dyn[];
     double *s_re = s_dyn;                       // [RXP_CAP+1]  after the scan: exclusive prefix sums of the phasors
     double *s_im = s_dyn + (RXP_CAP + 1);       // [RXP_CAP+1]
@@ -253,6 +259,9 @@ k_rx_power_dense(const double *__restrict__ ir, int64_t n_bins, double window, d
             const double s = sn_q * pr + cs_q * pi;
             if (s != 0.0) { sum += s * s; ++cnt; }
         }
+    } else if (!SECOND) {
+        if (tid == 0) power[blockIdx.x] = -1.0; // too dense for the small staging area: left to the second launch
+        return;
     } else {
         // fallback for very dense rows: the direct O(L * nnz) sum straight from the row
         for (int64_t n = tid; n < n_bins; n += RXP_THREADS) {
@@ -346,9 +355,14 @@ extern "C" int rfrt_rx_power_dense(const double *d_ir, int64_t n_receivers, int6
         set_error("rfrt_rx_power_dense: bad arguments");
         return RFRT_ERR_INVALID;
     }
-    const size_t smem = sizeof(double) * 2 * (RXP_CAP + 1) + sizeof(int) * RXP_CAP;
-    RFRT_CUDA(cudaFuncSetAttribute((const void *)k_rx_power_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_rx_power_dense<<<(unsigned)n_receivers, RXP_THREADS, smem, stream>>>(d_ir, n_bins, sample_window_s, carrier_hz, d_power);
+    const size_t smem_small = sizeof(double) * 2 * (RXP_CAP_SMALL + 1) + sizeof(int) * RXP_CAP_SMALL;
+    const size_t smem_big = sizeof(double) * 2 * (RXP_CAP_BIG + 1) + sizeof(int) * RXP_CAP_BIG;
+    RFRT_CUDA(cudaFuncSetAttribute((const void *)k_rx_power_dense<RXP_CAP_BIG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem_big));
+    k_rx_power_dense<RXP_CAP_SMALL, false><<<(unsigned)n_receivers, RXP_THREADS, smem_small, stream>>>(d_ir, n_bins, sample_window_s,
+                                                                                                     carrier_hz, d_power);
+    k_rx_power_dense<RXP_CAP_BIG, true><<<(unsigned)n_receivers, RXP_THREADS, smem_big, stream>>>(d_ir, n_bins, sample_window_s,
+                                                                                                carrier_hz, d_power);
     RFRT_CUDA(cudaGetLastError());
     return RFRT_OK;
 }
