@@ -332,6 +332,13 @@ extern "C" int rfrt_rxset_create(const double *d_centers_xyz, int64_t n_receiver
         cudaFreeAsync(dlo, stream); cudaFreeAsync(dhi, stream);
         if (rc) { cudaFreeAsync(r->centers, stream); cudaFreeAsync(r->verts, stream); free_bvh(&r->bvh); return rc; }
     }
+    {
+        std::vector<float> recs(16 * (size_t)n_faces);
+        unit_face_records(h_unit_vertices, h_faces, n_faces, recs.data());
+        RFRT_CUDA(cudaMallocAsync(&r->unit_recs, sizeof(float) * recs.size(), stream));
+        RFRT_CUDA(cudaMemcpyAsync(r->unit_recs, recs.data(), sizeof(float) * recs.size(), cudaMemcpyHostToDevice, stream));
+        RFRT_CUDA(cudaStreamSynchronize(stream)); // (recs is a host temporary)
+    }
     std::lock_guard<std::mutex> lock(g_mutex);
     rfrt_handle h = g_next_handle++;
     g_rxsets[h] = r.release();
@@ -353,6 +360,7 @@ extern "C" int rfrt_rxset_destroy(rfrt_handle rxset)
     free_bvh(&r->unit_bvh);
     if (r->verts) cudaFreeAsync(r->verts, 0);
     if (r->centers) cudaFreeAsync(r->centers, 0);
+    if (r->unit_recs) cudaFreeAsync(r->unit_recs, 0);
     delete r;
     return RFRT_OK;
 }

@@ -66,6 +66,7 @@ struct RxSet {
     uint8_t faces[3 * 128];   // host copy of the face table (<= 128 faces), uploaded to __constant__
     double radius = 0.0;
     double *centers = nullptr; // [R*3] device copy
+    float *unit_recs = nullptr; // [n_faces*16] unit-space face records of the receiver-query filter (rfrt_small.cu)
 };
 
 void set_error(const std::string &msg);
@@ -93,6 +94,8 @@ inline size_t small_image_floats(int n_pairs, int n_tris) { return 30 * (size_t)
 // (path length); neighbours are collected within SMALL_REACH_REL * extent
 constexpr double SMALL_TAU_REL = 1.0e-4;
 constexpr double SMALL_REACH_REL = 1.0e-3;
+
+void unit_face_records(const double *unit_v, const int32_t *faces, int n_faces, float *recs);
 
 Mesh *get_mesh(rfrt_handle h);
 RxSet *get_rxset(rfrt_handle h);

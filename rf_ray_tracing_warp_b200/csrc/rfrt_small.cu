@@ -242,6 +242,36 @@ int small_scene_tables(const float *soup, int n_tris, float *recs, int32_t *slot
     return RFRT_OK;
 }
 
+// Receiver face records in UNIT space (one per face of the unit shape, shared by all receivers of a set):
+// recs[16*f] = plane (n.xyz, d) + three in-plane edge functions (m.xyz, c) — the candidate filter of the receiver query
+// in the replay kernel (rx_query_sweep).  A degenerate face gets n = 0 (always a candidate).
+void unit_face_records(const double *unit_v, const int32_t *faces, int n_faces, float *recs)
+{
+    for (int f = 0; f < n_faces; ++f) {
+        V3 vv[3];
+        for (int c = 0; c < 3; ++c) vv[c] = {unit_v[3 * faces[3 * f + c]], unit_v[3 * faces[3 * f + c] + 1], unit_v[3 * faces[3 * f + c] + 2]};
+        float *R = recs + 16 * f;
+        V3 n = cross(sub(vv[1], vv[0]), sub(vv[2], vv[0]));
+        double l = len(n);
+        double emax = std::fmax(len(sub(vv[1], vv[0])), std::fmax(len(sub(vv[2], vv[0])), len(sub(vv[2], vv[1]))));
+        const bool degenerate = !(l > 1.0e-5 * emax * emax) || !std::isfinite(l);
+        if (degenerate) {
+            for (int i = 0; i < 16; ++i) R[i] = 0.0f;
+            continue;
+        }
+        n = {n.x / l, n.y / l, n.z / l};
+        R[0] = (float)n.x; R[1] = (float)n.y; R[2] = (float)n.z; R[3] = (float)dot(n, vv[0]);
+        for (int i = 0; i < 3; ++i) {
+            V3 e = sub(vv[(i + 1) % 3], vv[i]);
+            V3 m = cross(n, e);
+            double ml = len(m);
+            m = {m.x / ml, m.y / ml, m.z / ml};
+            if (dot(m, sub(vv[(i + 2) % 3], vv[i])) < 0) m = {-m.x, -m.y, -m.z};
+            R[4 + 4 * i] = (float)m.x; R[5 + 4 * i] = (float)m.y; R[6 + 4 * i] = (float)m.z; R[7 + 4 * i] = (float)(-dot(m, vv[i]));
+        }
+    }
+}
+
 } // namespace rfrt
 
 extern "C" int rfrt_small_scene_tables(const float *h_soup, int32_t n_triangles, float *h_recs, int32_t *h_slot_tri,

@@ -352,10 +352,11 @@ struct LiteralEnv {
 };
 
 // kernel.py:38-98 for one ray and one receiver.  Sink receives the vertex writes and RX-hit events.
+// s_recs: unit-space face records in shared memory (lockstep receiver query) or NULL (unit-BVH walk)
 template <class Sink>
 __device__ __forceinline__ void literal_trace(const LiteralEnv &E, const RxView *rx, int n_faces, float3 tx,
                                               int max_bounces, uint32_t tid, int *stack, float *stack_t, int stride,
-                                              Sink &sink)
+                                              Sink &sink, const float4 *s_recs = nullptr)
 {
     float3 dir = ray_direction(tid); // kernel.py:51-52
     float3 pos = tx;                 // :53
@@ -364,7 +365,9 @@ __device__ __forceinline__ void literal_trace(const LiteralEnv &E, const RxView 
         WoopRay wr = woop_setup(pos, dir);
         SlabRay sr = slab_setup(pos, dir);
         float t_rx = 0.0f;
-        bool maybe_hit_rx = rx ? rx_query(*rx, c_rx_faces, n_faces, wr, pos, dir, 1.0e6f, stack, stack_t, stride, t_rx) : false; // :71
+        bool maybe_hit_rx = false; // :71
+        if (rx) maybe_hit_rx = s_recs ? rx_query_sweep(*rx, s_recs, c_rx_faces, n_faces, wr, pos, dir, 1.0e6f, t_rx)
+                                      : rx_query(*rx, c_rx_faces, n_faces, wr, pos, dir, 1.0e6f, stack, stack_t, stride, t_rx);
         Hit h;
         h.t = 1.0e6f; h.face = -1; h.slot = -1;
         closest_hit(E.nodes, E.tris, E.n_tris, wr, sr, stack, stack_t, stride, h);                          // :82
@@ -465,6 +468,7 @@ struct ReceiveParams {
     const double *rx_centers;
     const BvhNode *unit_nodes;
     const int32_t *unit_order;
+    const float *unit_recs; // [n_faces*16] face records of the lockstep receiver query
     float inv_r;
     int32_t n_unit;
     int32_t n_faces;
@@ -488,12 +492,16 @@ struct ReceiveParams {
 template <bool LSTACK>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_receive(const ReceiveParams P)
 {
-    extern __shared__ int s_stack_raw[];
+    extern __shared__ __align__(16) int s_stack_raw[];
     int l_stack[LSTACK ? 64 : 1];
     float l_stack_t[LSTACK ? 64 : 1];
     int *stack = LSTACK ? l_stack : s_stack_raw + threadIdx.x;
     float *stack_t = LSTACK ? l_stack_t : reinterpret_cast<float *>(s_stack_raw + P.stack_depth * TRACE_THREADS) + threadIdx.x;
     constexpr int STRIDE = LSTACK ? 1 : TRACE_THREADS;
+    // the receiver shape's face records live behind the stacks
+    float4 *s_recs = reinterpret_cast<float4 *>(s_stack_raw + 2 * P.stack_depth * TRACE_THREADS);
+    for (int i = threadIdx.x; i < 4 * P.n_faces; i += TRACE_THREADS) s_recs[i] = __ldg(reinterpret_cast<const float4 *>(P.unit_recs) + i);
+    __syncthreads();
     int64_t n_cand = (int64_t)P.counters[RFRT_CTR_CANDIDATES];
     if (n_cand > P.cand_capacity) n_cand = P.cand_capacity;
     const int row = 3 * (P.max_bounces + 1);
@@ -510,7 +518,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_receive(const ReceivePa
         rx.unit_nodes = P.unit_nodes; rx.unit_order = P.unit_order;
         rx.cx = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y); rx.cy = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y + 1);
         rx.cz = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y + 2); rx.inv_r = P.inv_r;
-        literal_trace(P.env, &rx, P.n_faces, P.tx, P.max_bounces, cand.x, stack, stack_t, STRIDE, sink);
+        literal_trace(P.env, &rx, P.n_faces, P.tx, P.max_bounces, cand.x, stack, stack_t, STRIDE, sink, s_recs);
         // a candidate raised at a later bounce than the replay's first receiver hit is a duplicate
         if (sink.last_rx_bounce < 0 || sink.first_rx_bounce != (int)cand.z) continue;
         int nverts = sink.last_rx_bounce + 2;
@@ -762,6 +770,7 @@ extern "C" int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const
     P.materials = (m->materials && m->bvh.n_prims < 32768) ? m->materials : nullptr;
     P.rx_verts = r->verts; P.n_unit = r->n_unit; P.n_faces = r->n_faces;
     P.rx_centers = r->centers; P.unit_nodes = r->unit_bvh.nodes; P.unit_order = r->unit_bvh.prim_order;
+    P.unit_recs = r->unit_recs;
     P.inv_r = (float)(1.0 / r->radius);
     P.tx = make_float3(h_tx_pos[0], h_tx_pos[1], h_tx_pos[2]);
     P.max_bounces = max_bounces;
@@ -770,11 +779,11 @@ extern "C" int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const
     P.amp0 = amp0; P.light_speed = light_speed_mps; P.sample_rate = sample_rate_hz;
     P.rec_ray = d_rec_ray; P.rec_rx = d_rec_rx; P.rec_nverts = d_rec_nverts; P.rec_bin = d_rec_bin;
     P.rec_amp = d_rec_amp; P.rec_dist = d_rec_dist; P.rec_paths = d_rec_paths; P.rec_capacity = rec_capacity;
-    P.stack_depth = stack_depth_for(m, r);
+    P.stack_depth = stack_depth_for(m, nullptr); // only the environment BVH is walked here (receiver query: lockstep sweep)
     const bool lstack = P.stack_depth > 16;
     if (lstack && P.stack_depth > 64) { set_error("rfrt_trace_receive: BVH deeper than 64 levels"); return RFRT_ERR_INVALID; }
     if (lstack) P.stack_depth = 0;
-    const size_t smem = stack_bytes(P.stack_depth);
+    const size_t smem = stack_bytes(P.stack_depth) + sizeof(float4) * 4 * (size_t)r->n_faces;
     int grid = 0;
     int rc = grid_for(lstack ? (const void *)k_trace_receive<true> : (const void *)k_trace_receive<false>, smem, &grid);
     if (rc) return rc;
