@@ -69,6 +69,7 @@ enum rfrt_status {
 #define RFRT_CTR_NEXT_CAND 5   /* internal: candidate fetch cursor */
 #define RFRT_CTR_CHECKSUM 6    /* with RFRT_FLAG_CHECKSUM: sum over segments of hash(ray id, bounce, hit triangle, bits of t)
                                   (mod 2^64; order-independent, so it compares whole runs of different kernels / GPU counts) */
+#define RFRT_CTR_QUEUE_OVERFLOW 7 /* receiver-enumeration queue overflows (must stay 0: results would be incomplete) */
 #define RFRT_CTR_COUNT 8
 
 RFRT_API int rfrt_version(void);

@@ -18,7 +18,8 @@ c_u64 = ctypes.c_uint64
 c_f = ctypes.c_float
 c_d = ctypes.c_double
 
-CTR_SEGMENTS, CTR_CANDIDATES, CTR_RECORDS, CTR_ENV_HITS, CTR_NEXT_RAY, CTR_NEXT_CAND, CTR_CHECKSUM, CTR_COUNT = 0, 1, 2, 3, 4, 5, 6, 8
+CTR_SEGMENTS, CTR_CANDIDATES, CTR_RECORDS, CTR_ENV_HITS, CTR_NEXT_RAY, CTR_NEXT_CAND, CTR_CHECKSUM, CTR_QUEUE_OVERFLOW, CTR_COUNT = \
+    0, 1, 2, 3, 4, 5, 6, 7, 8
 FLAG_DIRS_READY, FLAG_FORCE_BVH, FLAG_CHECKSUM = 1, 2, 8
 SMALL_MAX_TRIS = 64
 

@@ -39,6 +39,7 @@ struct PhysParams {
     double *ir;    // [n_rx*n_bins*2] or NULL
     int64_t n_bins;
     int32_t stack_depth;
+    int32_t rx_coop; // dense receiver sets: warp-cooperative enumeration (see rfrt_trace.cu)
 };
 
 // one receiver against one segment: fp64 closest-approach test + field accumulation
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(PHYS_THREADS) k_trace_phys(const PhysParams P)
     constexpr int STRIDE = LSTACK ? 1 : PHYS_THREADS;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
+    int *rx_queue = s_stack_raw + 2 * P.stack_depth * PHYS_THREADS + RX_QUEUE_CAP * (threadIdx.x >> 5); // this warp's node queue
 
     bool has_ray = false, exhausted = false;
     float3 pos = make_float3(0.f, 0.f, 0.f), dir = make_float3(0.f, 0.f, 1.f);
@@ -109,44 +111,68 @@ __global__ void __launch_bounds__(PHYS_THREADS) k_trace_phys(const PhysParams P)
             if ((int64_t)base + cnt >= P.chunk_n) exhausted = true;
         }
         if (!__any_sync(FULL, has_ray)) break;
+        Hit h;
+        h.t = 1.0e6f; h.face = -1; h.slot = -1;
+        float dlen_f = 1.0f;
         if (has_ray) {
             const WoopRay wr = woop_setup(pos, dir);
             const SlabRay sr = slab_setup(pos, dir);
-            Hit h;
-            h.t = 1.0e6f; h.face = -1; h.slot = -1;
             closest_hit(P.nodes, P.tris, P.n_tris, wr, sr, stack, stack_t, STRIDE, h, prev);
-            const bool hit = h.face >= 0;
             ++n_seg;
-            const float dlen_f = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dir.x, dir.x), __fmul_rn(dir.y, dir.y)), __fmul_rn(dir.z, dir.z)));
-            const double dlen = (double)dlen_f;
-            if (P.n_rx > 0) {
-                const double dd = __dadd_rn(__dadd_rn(__dmul_rn((double)dir.x, (double)dir.x), __dmul_rn((double)dir.y, (double)dir.y)),
-                                            __dmul_rn((double)dir.z, (double)dir.z));
-                const double t_lim = hit ? (double)h.t : 1.0e6;
-                const float t_limit = hit ? h.t : 1.0e6f;
-                int sp = 0;
-                int node = 0;
-                while (node >= 0) { // every receiver whose bounding cube overlaps the segment [0, t_limit]
-                    const float4 *np = reinterpret_cast<const float4 *>(P.rx_nodes + node);
-                    const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-                    const int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
-                    float tn0, tn1;
-                    bool h0 = slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_limit, tn0);
-                    bool h1 = slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_limit, tn1);
-                    const int c0 = q3.x, c1 = q3.y;
-                    if (c1 == c0) h1 = false;
-                    if (h0) {
-                        if (c0 < 0) phys_arrival(P, __ldg(P.rx_order + (~c0)), pos, dir, dd, dlen, t_lim, L, gamma, n_arr);
-                        else { stack[sp * STRIDE] = c0; ++sp; }
-                    }
-                    if (h1) {
-                        if (c1 < 0) phys_arrival(P, __ldg(P.rx_order + (~c1)), pos, dir, dd, dlen, t_lim, L, gamma, n_arr);
-                        else { stack[sp * STRIDE] = c1; ++sp; }
-                    }
-                    node = -1;
-                    if (sp > 0) { --sp; node = stack[sp * STRIDE]; }
+            dlen_f = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dir.x, dir.x), __fmul_rn(dir.y, dir.y)), __fmul_rn(dir.z, dir.z)));
+        }
+        const bool hit = h.face >= 0;
+        const double dlen = (double)dlen_f;
+        if (P.n_rx > 0 && P.rx_coop) {
+            // dense receiver sets: the warp enumerates, segment by segment, the receivers whose bounding cube overlaps
+            // [0, t_limit] (rx_enumerate_coop)
+            const float t_limit = hit ? h.t : 1.0e6f;
+            double L_b = 0.0, gamma_b = 1.0, dlen_b = 1.0;
+            const bool ok = rx_enumerate_coop(
+                P.rx_nodes, P.rx_order, has_ray, rx_queue,
+                [&](int src, float3 &bp, float3 &bd, float &bt) {
+                    bp.x = __shfl_sync(FULL, pos.x, src); bp.y = __shfl_sync(FULL, pos.y, src); bp.z = __shfl_sync(FULL, pos.z, src);
+                    bd.x = __shfl_sync(FULL, dir.x, src); bd.y = __shfl_sync(FULL, dir.y, src); bd.z = __shfl_sync(FULL, dir.z, src);
+                    bt = __shfl_sync(FULL, t_limit, src);
+                    L_b = __shfl_sync(FULL, L, src); gamma_b = __shfl_sync(FULL, gamma, src); dlen_b = __shfl_sync(FULL, dlen, src);
+                },
+                [&](int k, float3 bp, float3 bd, float bt) {
+                    const double dd = __dadd_rn(__dadd_rn(__dmul_rn((double)bd.x, (double)bd.x), __dmul_rn((double)bd.y, (double)bd.y)),
+                                                __dmul_rn((double)bd.z, (double)bd.z));
+                    phys_arrival(P, k, bp, bd, dd, dlen_b, bt < 1.0e6f ? (double)bt : 1.0e6, L_b, gamma_b, n_arr);
+                });
+            if (!ok && lane == 0) atomicAdd(&P.counters[RFRT_CTR_QUEUE_OVERFLOW], 1ull);
+        } else if (P.n_rx > 0 && has_ray) {
+            // sparse receiver sets: every lane walks the receiver BVH for its own segment
+            const double dd = __dadd_rn(__dadd_rn(__dmul_rn((double)dir.x, (double)dir.x), __dmul_rn((double)dir.y, (double)dir.y)),
+                                        __dmul_rn((double)dir.z, (double)dir.z));
+            const double t_lim = hit ? (double)h.t : 1.0e6;
+            const float t_limit = hit ? h.t : 1.0e6f;
+            const SlabRay sr = slab_setup_fast(pos, dir);
+            int sp = 0;
+            int node = 0;
+            while (node >= 0) {
+                const float4 *np = reinterpret_cast<const float4 *>(P.rx_nodes + node);
+                const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+                const int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
+                float tn0, tn1;
+                bool h0 = slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_limit, tn0);
+                bool h1 = slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_limit, tn1);
+                const int c0 = q3.x, c1 = q3.y;
+                if (c1 == c0) h1 = false;
+                if (h0) {
+                    if (c0 < 0) phys_arrival(P, __ldg(P.rx_order + (~c0)), pos, dir, dd, dlen, t_lim, L, gamma, n_arr);
+                    else { stack[sp * STRIDE] = c0; ++sp; }
                 }
+                if (h1) {
+                    if (c1 < 0) phys_arrival(P, __ldg(P.rx_order + (~c1)), pos, dir, dd, dlen, t_lim, L, gamma, n_arr);
+                    else { stack[sp * STRIDE] = c1; ++sp; }
+                }
+                node = -1;
+                if (sp > 0) { --sp; node = stack[sp * STRIDE]; }
             }
+        }
+        if (has_ray) {
             if (hit) {
                 ++n_hit;
                 const float4 n4 = __ldg(P.normals + h.slot);
@@ -235,14 +261,24 @@ extern "C" int rfrt_trace_physical(rfrt_handle env_mesh, rfrt_handle rxset, cons
     P.dirs = (const float4 *)d_dir_scratch;
     P.counters = (unsigned long long *)d_counters;
     P.field = d_field; P.ir = d_ir; P.n_bins = n_bins;
+    // receiver enumeration: per lane (stack) for sparse sets, warp-cooperative (queue) for dense ones (rfrt_trace.cu)
+    P.rx_coop = 0;
+    if (r && r->n_receivers > 1) {
+        const double ex = r->bvh.bounds[3] - r->bvh.bounds[0], ey = r->bvh.bounds[4] - r->bvh.bounds[1], ez = r->bvh.bounds[5] - r->bvh.bounds[2];
+        double face = ex * ey > ey * ez ? ex * ey : ey * ez;
+        if (ex * ez > face) face = ex * ez;
+        const double d2 = 4.0 * r->radius * r->radius;
+        P.rx_coop = (double)r->n_receivers * d2 >= 8.0 * (face > d2 ? face : d2) ? 1 : 0;
+    }
     int depth = m->bvh.max_depth;
-    if (r && r->bvh.max_depth > depth) depth = r->bvh.max_depth;
+    if (r && !P.rx_coop && r->bvh.max_depth > depth) depth = r->bvh.max_depth;
     depth += 2;
     if (depth < 8) depth = 8;
     const bool lstack = depth > 16;
     if (lstack && depth > 64) { set_error("rfrt_trace_physical: BVH deeper than 64 levels"); return RFRT_ERR_INVALID; }
     P.stack_depth = lstack ? 0 : depth;
-    const size_t smem = (size_t)P.stack_depth * PHYS_THREADS * 2 * sizeof(int);
+    const size_t smem = (size_t)P.stack_depth * PHYS_THREADS * 2 * sizeof(int) +
+                        (P.rx_coop ? sizeof(int) * RX_QUEUE_CAP * (PHYS_THREADS / 32) : 0);
     const void *kern = lstack ? (const void *)k_trace_phys<true> : (const void *)k_trace_phys<false>;
     int dev = 0, sms = 0, per_sm = 0;
     RFRT_CUDA(cudaGetDevice(&dev));

@@ -57,6 +57,7 @@ struct TraceParams {
     int64_t dump_begin;
     int32_t stack_depth;
     int32_t fetch_block; // rays a warp claims per atomic (32..256, sized so that every warp sees >= 64 blocks)
+    int32_t rx_coop;   // dense receiver sets: the warp enumerates its lanes' segments together (rx_enumerate_coop)
     int32_t short_min; // small scenes: run a self-re-hit trip when at least this many lanes stand on a surface
 };
 
@@ -151,8 +152,10 @@ __device__ __forceinline__ unsigned long long segment_hash(uint32_t gid, int bou
 }
 
 // SMALL: 0 = BVH walk, 1 = lockstep sweep of <= 16 triangle pairs, 2 = of <= 32 pairs
-template <bool DUMP, int SMALL, bool LSTACK>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P)
+// COOP: dense receiver sets — the warp enumerates its lanes' segments together (rx_enumerate_coop) at a converged point
+//       after the closest hit; otherwise every lane handles its own receivers right where its segment is finished
+template <bool DUMP, int SMALL, bool LSTACK, bool COOP>
+__global__ void __launch_bounds__(TRACE_THREADS, 8) k_trace_env(const TraceParams P)
 {
     extern __shared__ __align__(16) int s_stack_raw[];
     int l_stack[LSTACK ? 64 : 1];
@@ -162,10 +165,12 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
     constexpr int STRIDE = LSTACK ? 1 : TRACE_THREADS;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    // SMALL: the whole scene (filter tables + exact-test data) lives in shared memory behind the stacks
+    // behind the stacks: the warps' receiver-enumeration queues, then (SMALL) the scene image
+    int *s_queue_base = s_stack_raw + 2 * P.stack_depth * TRACE_THREADS;
+    // SMALL: the whole scene (filter tables + exact-test data) lives in shared memory
     SmallScene S;
     if (SMALL) {
-        float *img = reinterpret_cast<float *>(s_stack_raw + 2 * P.stack_depth * TRACE_THREADS);
+        float *img = reinterpret_cast<float *>(s_queue_base + (COOP ? RX_QUEUE_CAP * (TRACE_THREADS / 32) : 0));
         const int n = (int)P.n_tris, np = P.small_pairs;
         for (int i = threadIdx.x; i < 30 * np + 17 * n; i += TRACE_THREADS) img[i] = __ldg(P.small + i);
         __syncthreads();
@@ -178,6 +183,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
         S.n_pairs = np; S.extent = P.small_extent; S.tau = (float)SMALL_TAU_REL * P.small_extent;
         S.erode = (float)(2.0 * SMALL_REACH_REL) * P.small_extent;
     }
+
+    int *rx_queue = s_queue_base + (COOP ? RX_QUEUE_CAP * (threadIdx.x >> 5) : 0); // this warp's node queue
 
     bool has_ray = false;
     bool exhausted = false; // warp-uniform
@@ -234,48 +241,75 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
         // sit idle in warps whose other lanes walk 50 nodes (measured: 5.6 of 32 lanes active).
         bool boxtrip = false;
         if (!SMALL) boxtrip = __any_sync(FULL, has_ray && !entered);
-        if (has_ray && (SMALL ? (!shortcut || on_face >= 0) : (!boxtrip || !entered))) {
         // ---- one bounce iteration (kernel.py:57-98, environment branch) -----------------------
         Hit h;
         h.t = 1.0e6f; h.face = -1; h.slot = -1;
-        bool resolved = true;
-        SlabRay sr_env; // BVH variants: reused by the receiver enumeration
-        sr_env.ix = sr_env.iy = sr_env.iz = sr_env.ox = sr_env.oy = sr_env.oz = 0.0f;
-        if (SMALL) {
-            const WoopRay wr = woop_setup(pos, dir);
-            if (shortcut) resolved = small_self_rehit(S, on_face, pos, dir, wr, h);
-            else closest_hit_small<SMALL == 2>(S, pos, dir, wr, h);
-        } else {
-            sr_env = slab_setup(pos, dir);
-            if (boxtrip) {
-                float tn;
-                entered = slab_hit(sr_env, P.env_lo[0], P.env_lo[1], P.env_lo[2], P.env_hi[0], P.env_hi[1], P.env_hi[2], 1.0e6f, tn);
-                resolved = !entered; // outside the box: a miss (h stays empty)
-            } else {
+        bool seg_done = false; // this lane finished a segment in this trip (h = its closest hit)
+        if (has_ray && (SMALL ? (!shortcut || on_face >= 0) : (!boxtrip || !entered))) {
+            bool resolved = true;
+            if (SMALL) {
                 const WoopRay wr = woop_setup(pos, dir);
-                closest_hit(P.nodes, P.tris, P.n_tris, wr, sr_env, stack, stack_t, STRIDE, h);
+                if (shortcut) resolved = small_self_rehit(S, on_face, pos, dir, wr, h);
+                else closest_hit_small<SMALL == 2>(S, pos, dir, wr, h);
+                if (!resolved) on_face = -1; // not a self re-hit: this segment goes through the next full sweep
+            } else {
+                const SlabRay sr_env = slab_setup(pos, dir);
+                if (boxtrip) {
+                    float tn;
+                    entered = slab_hit(sr_env, P.env_lo[0], P.env_lo[1], P.env_lo[2], P.env_hi[0], P.env_hi[1], P.env_hi[2], 1.0e6f, tn);
+                    resolved = !entered; // outside the box: a miss (h stays empty)
+                } else {
+                    const WoopRay wr = woop_setup(pos, dir);
+                    closest_hit(P.nodes, P.tris, P.n_tris, wr, sr_env, stack, stack_t, STRIDE, h);
+                }
+            }
+            seg_done = resolved;
+        }
+
+        // ---- receivers hit strictly before the environment, or at all if it is missed (kernel.py:71,85) ----
+        if (COOP) {
+            // first the segment's own box against the bounds of all receivers, then the warp enumerates together
+            const float t_limit = h.face >= 0 ? h.t : 1.0e6f;
+            bool near_rx = false;
+            if (seg_done) {
+                const float ex = fmaf(dir.x, t_limit, pos.x), ey = fmaf(dir.y, t_limit, pos.y), ez = fmaf(dir.z, t_limit, pos.z);
+                near_rx = fminf(pos.x, ex) <= P.rx_hi[0] && fmaxf(pos.x, ex) >= P.rx_lo[0] &&
+                          fminf(pos.y, ey) <= P.rx_hi[1] && fmaxf(pos.y, ey) >= P.rx_lo[1] &&
+                          fminf(pos.z, ez) <= P.rx_hi[2] && fmaxf(pos.z, ez) >= P.rx_lo[2];
+            }
+            if (__any_sync(FULL, near_rx)) {
+                uint32_t gid_b = 0; int bounce_b = 0;
+                const bool ok = rx_enumerate_coop(
+                    P.rx_nodes, P.rx_order, near_rx, rx_queue,
+                    [&](int src, float3 &bp, float3 &bd, float &bt) {
+                        bp.x = __shfl_sync(FULL, pos.x, src); bp.y = __shfl_sync(FULL, pos.y, src); bp.z = __shfl_sync(FULL, pos.z, src);
+                        bd.x = __shfl_sync(FULL, dir.x, src); bd.y = __shfl_sync(FULL, dir.y, src); bd.z = __shfl_sync(FULL, dir.z, src);
+                        bt = __shfl_sync(FULL, t_limit, src);
+                        gid_b = __shfl_sync(FULL, (uint32_t)(P.chunk_begin + ray), src);
+                        bounce_b = __shfl_sync(FULL, bounce, src);
+                    },
+                    [&](int k, float3 bp, float3 bd, float bt) { rx_filter_and_emit(P, k, bp, bd, bt, gid_b, bounce_b); });
+                if (!ok && lane == 0) atomicAdd(&P.counters[RFRT_CTR_QUEUE_OVERFLOW], 1ull);
             }
         }
-        if (!resolved) {
-            if (SMALL) on_face = -1; // not a self re-hit: this segment goes through the next full sweep
-        } else {
+
+        if (seg_done) {
         const bool hit_env = h.face >= 0;
         ++n_seg;
 
-        if (P.n_rx > 0) {
-            // kernel.py:71,85: receivers hit strictly before the environment (or at all, if it is missed)
+        if (!COOP && P.n_rx > 0) {
             const float t_limit = hit_env ? h.t : 1.0e6f;
             const uint32_t gid = (uint32_t)(P.chunk_begin + ray);
             if (P.n_rx == 1) {
                 rx_filter_and_emit(P, 0, pos, dir, t_limit, gid, bounce);
             } else {
-                // enumerate every receiver whose box overlaps the segment [0, t_limit]; first the segment's own box
-                // against the bounds of all receivers (no division: most segments of a sparse receiver set stop here)
+                // the segment's own box against the bounds of all receivers (no division: most segments of a sparse
+                // receiver set stop here), then this lane walks the receiver BVH
                 const float ex = fmaf(dir.x, t_limit, pos.x), ey = fmaf(dir.y, t_limit, pos.y), ez = fmaf(dir.z, t_limit, pos.z);
                 const bool near_rx = fminf(pos.x, ex) <= P.rx_hi[0] && fmaxf(pos.x, ex) >= P.rx_lo[0] &&
                                      fminf(pos.y, ey) <= P.rx_hi[1] && fmaxf(pos.y, ey) >= P.rx_lo[1] &&
                                      fminf(pos.z, ez) <= P.rx_hi[2] && fmaxf(pos.z, ez) >= P.rx_lo[2];
-                const SlabRay sr = SMALL ? slab_setup_fast(pos, dir) : sr_env;
+                const SlabRay sr = slab_setup_fast(pos, dir);
                 int sp = 0;
                 int node = near_rx ? 0 : -1;
                 while (node >= 0) {
@@ -327,8 +361,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
         } else {
             has_ray = false; // a miss repeats forever in the reference (kernel.py:97-98): nothing more to do
         }
-        } // resolved
-        } // has_ray
+        } // seg_done
     }
 
     // warp-reduced counters
@@ -684,27 +717,42 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     P.counters = (unsigned long long *)d_counters;
     P.candidates = (uint4 *)d_candidates; P.cand_capacity = r ? cand_capacity : 0;
     P.hit_tri = d_hit_tri; P.hit_t = d_hit_t; P.dump_begin = ray_begin;
-    P.stack_depth = stack_depth_for(m, r);
+    // Receiver enumeration: per lane (stack) for sparse sets, warp-cooperative (queue) when a segment that crosses the
+    // set overlaps many receivers at once — estimated as the receivers' cross-sections over the largest face of their
+    // bounding box (C3's lattice: ~46; C2's: 3; C4's 16 receivers: 0.1).
+    P.rx_coop = 0;
+    if (r && r->n_receivers > 1) {
+        const double ex = r->bvh.bounds[3] - r->bvh.bounds[0], ey = r->bvh.bounds[4] - r->bvh.bounds[1], ez = r->bvh.bounds[5] - r->bvh.bounds[2];
+        double face = ex * ey > ey * ez ? ex * ey : ey * ez;
+        if (ex * ez > face) face = ex * ez;
+        const double d2 = 4.0 * r->radius * r->radius;
+        P.rx_coop = (double)r->n_receivers * d2 >= 8.0 * (face > d2 ? face : d2) ? 1 : 0;
+    }
+    P.stack_depth = stack_depth_for(m, P.rx_coop ? nullptr : r);
     P.short_min = 8; // measured flat between 4 and 16 on room.stl (profiles/README.md)
     // DUMP instantiations also accumulate the checksum
     const bool dump = d_hit_tri || d_hit_t || (flags & RFRT_FLAG_CHECKSUM);
     // small scenes: lockstep sweep over the scene staged in shared memory (see closest_hit_small)
     const bool small = m->small && P.n_tris > 0 && !(flags & RFRT_FLAG_FORCE_BVH);
-    if (small) P.stack_depth = r ? stack_depth_for(nullptr, r) : 1;
+    if (small) P.stack_depth = (r && !P.rx_coop) ? stack_depth_for(nullptr, r) : 1;
     const bool lstack = !small && P.stack_depth > 16; // deep tree: local-memory stack (<= 64 entries by construction)
     if (lstack && P.stack_depth > 64) { set_error("rfrt_trace: BVH deeper than 64 levels"); return RFRT_ERR_INVALID; }
     if (lstack) P.stack_depth = 0;
-    const size_t smem = stack_bytes(P.stack_depth) +
+    const size_t smem = stack_bytes(P.stack_depth) + (P.rx_coop ? sizeof(int) * RX_QUEUE_CAP * (TRACE_THREADS / 32) : 0) +
                         (small ? sizeof(float) * small_image_floats(m->small_pairs, (int)P.n_tris) : 0);
     typedef void (*kern_t)(const TraceParams);
     const int variant = small ? (m->small_pairs > 16 ? 2 : 1) : (lstack ? 3 : 0);
-    static const kern_t kerns[4][2] = {
-        {k_trace_env<false, 0, false>, k_trace_env<true, 0, false>},
-        {k_trace_env<false, 1, false>, k_trace_env<true, 1, false>},
-        {k_trace_env<false, 2, false>, k_trace_env<true, 2, false>},
-        {k_trace_env<false, 0, true>, k_trace_env<true, 0, true>},
+    static const kern_t kerns[2][4][2] = {
+        {{k_trace_env<false, 0, false, false>, k_trace_env<true, 0, false, false>},
+         {k_trace_env<false, 1, false, false>, k_trace_env<true, 1, false, false>},
+         {k_trace_env<false, 2, false, false>, k_trace_env<true, 2, false, false>},
+         {k_trace_env<false, 0, true, false>, k_trace_env<true, 0, true, false>}},
+        {{k_trace_env<false, 0, false, true>, k_trace_env<true, 0, false, true>},
+         {k_trace_env<false, 1, false, true>, k_trace_env<true, 1, false, true>},
+         {k_trace_env<false, 2, false, true>, k_trace_env<true, 2, false, true>},
+         {k_trace_env<false, 0, true, true>, k_trace_env<true, 0, true, true>}},
     };
-    const kern_t kern = kerns[variant][dump ? 1 : 0];
+    const kern_t kern = kerns[P.rx_coop ? 1 : 0][variant][dump ? 1 : 0];
     int grid = 0;
     int rc = grid_for((const void *)kern, smem, &grid);
     if (rc) return rc;

@@ -475,6 +475,72 @@ __device__ __forceinline__ bool rx_query(const RxView &rx, const uint8_t *faces,
     return best < max_t;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Warp-cooperative enumeration of the receivers whose (padded) box a segment overlaps.
+// Per-lane enumeration of a dense receiver lattice leaves 5 of 32 lanes busy (each crossing segment walks ~300 nodes
+// of the receiver BVH on its own).  Here the warp takes its lanes' segments one at a time and walks the receiver BVH
+// together: a per-warp node queue in shared memory, every lane pops one node per step (last-in first-out batches of 32,
+// which bounds the queue by ~32 x depth), tests its two child boxes, pushes the internal children (ballot + popc
+// offsets) and hands leaf receivers to `leaf`.  Must be called by all 32 lanes of a converged warp.
+//   want        this lane has a segment (pos, dir, t_limit) to enumerate
+//   leaf(k, src) is called by SOME lane for every receiver k whose box the segment of lane `src` overlaps; it has to
+//               fetch the segment's data with __shfl_sync-free means, so callers broadcast what they need through
+//               `bcast` (called by all lanes with the source lane before the walk of each segment)
+// Returns false if the queue overflowed (results incomplete: the caller counts that in RFRT_CTR_QUEUE_OVERFLOW).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int RX_QUEUE_CAP = 1024; // ints per warp
+
+template <class Bcast, class Leaf>
+__device__ __forceinline__ bool rx_enumerate_coop(const BvhNode *__restrict__ rx_nodes, const int32_t *__restrict__ rx_order,
+                                                  bool want, int *queue, Bcast &&bcast, Leaf &&leaf)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    bool ok = true;
+    unsigned todo = __ballot_sync(FULL, want);
+    while (todo) {
+        const int src = __ffs((int)todo) - 1;
+        todo &= todo - 1u;
+        float3 pos, dir; float t_limit;
+        bcast(src, pos, dir, t_limit); // every lane now holds lane src's segment
+        const SlabRay sr = slab_setup_fast(pos, dir);
+        int n = 1;
+        if (lane == 0) queue[0] = 0;
+        __syncwarp();
+        while (n > 0) {
+            const int batch = n < 32 ? n : 32;
+            int node = -1;
+            if (lane < batch) node = queue[n - 1 - lane];
+            n -= batch;
+            __syncwarp();
+            bool p0 = false, p1 = false;
+            int c0 = 0, c1 = 0;
+            if (node >= 0) {
+                const float4 *np = reinterpret_cast<const float4 *>(rx_nodes + node);
+                const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+                const int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
+                float tn0, tn1;
+                bool h0 = slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_limit, tn0);
+                bool h1 = slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_limit, tn1);
+                c0 = q3.x; c1 = q3.y;
+                if (c1 == c0) h1 = false;
+                p0 = h0 && c0 >= 0; p1 = h1 && c1 >= 0;
+                if (h0 && c0 < 0) leaf(__ldg(rx_order + (~c0)), pos, dir, t_limit);
+                if (h1 && c1 < 0) leaf(__ldg(rx_order + (~c1)), pos, dir, t_limit);
+            }
+            const unsigned b0 = __ballot_sync(FULL, p0), b1 = __ballot_sync(FULL, p1);
+            const int off0 = n + __popc(b0 & lt), off1 = n + __popc(b0) + __popc(b1 & lt);
+            if (p0 && off0 < RX_QUEUE_CAP) queue[off0] = c0;
+            if (p1 && off1 < RX_QUEUE_CAP) queue[off1] = c1;
+            n += __popc(b0) + __popc(b1);
+            if (n > RX_QUEUE_CAP) { n = RX_QUEUE_CAP; ok = false; }
+            __syncwarp();
+        }
+    }
+    return ok;
+}
+
 // Receiver query of the replay kernel, lockstep: the same answer as rx_query (closest exact t in [0, max_t) over all
 // faces of one receiver), but the faces to test are found by the plane / edge-distance filter (see rfrt_small.cu) over
 // the unit shape's face records in shared memory — every lane runs the same n_faces steps, where the unit-BVH walk left

@@ -363,6 +363,8 @@ class Tracer:
                                                     _ptr(counters), _ptr(field), _ptr(ir), _stream_ptr()),
                       "rfrt_trace_physical")
                 c = counters.cpu().numpy()
+                if c[_lib.CTR_QUEUE_OVERFLOW]:
+                    raise RfrtError("receiver-enumeration queue overflowed: results would be incomplete")
                 stats = dict(segments=int(c[_lib.CTR_SEGMENTS]), env_hits=int(c[_lib.CTR_ENV_HITS]),
                              arrivals=int(c[_lib.CTR_RECORDS]))
             finally:
@@ -499,6 +501,8 @@ class TraceJob:
 
     def counters(self):
         c = self.counters_t.cpu().numpy()  # synchronises the stream
+        if c[_lib.CTR_QUEUE_OVERFLOW]:
+            raise RfrtError("receiver-enumeration queue overflowed: results would be incomplete (receiver BVH too deep)")
         return dict(segments=int(c[_lib.CTR_SEGMENTS]), env_hits=int(c[_lib.CTR_ENV_HITS]),
                     candidates=int(c[_lib.CTR_CANDIDATES]), records=int(c[_lib.CTR_RECORDS]))
 
