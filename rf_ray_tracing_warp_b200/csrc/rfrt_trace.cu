@@ -155,7 +155,7 @@ __device__ __forceinline__ unsigned long long segment_hash(uint32_t gid, int bou
 // COOP: dense receiver sets — the warp enumerates its lanes' segments together (rx_enumerate_coop) at a converged point
 //       after the closest hit; otherwise every lane handles its own receivers right where its segment is finished
 template <bool DUMP, int SMALL, bool LSTACK, bool COOP>
-__global__ void __launch_bounds__(TRACE_THREADS, 8) k_trace_env(const TraceParams P)
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P)
 {
     extern __shared__ __align__(16) int s_stack_raw[];
     int l_stack[LSTACK ? 64 : 1];
