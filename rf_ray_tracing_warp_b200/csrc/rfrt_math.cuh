@@ -157,17 +157,11 @@ __device__ __forceinline__ float diff_product(float a, float b, float c, float d
     return __fadd_rn(diff, err);
 }
 
-// returns true and t when the triangle is hit (any sign of t that the reference accepts here:
-// callers apply  t >= 0 && t < best).
-__device__ __forceinline__ bool woop_hit(const WoopRay &r, float3 a, float3 b, float3 c, float &t_out)
+// The test proper, on the vertex offsets already permuted to (kx, ky, kz).  Returns true and t when the triangle is
+// hit (any sign of t that the reference accepts here: callers apply  t >= 0 && t < best).
+__device__ __forceinline__ bool woop_hit_permuted(const WoopRay &r, float Akx, float Aky, float Akz, float Bkx, float Bky,
+                                                  float Bkz, float Ckx, float Cky, float Ckz, float &t_out)
 {
-    float A0 = __fsub_rn(a.x, r.px), A1 = __fsub_rn(a.y, r.py), A2 = __fsub_rn(a.z, r.pz);
-    float B0 = __fsub_rn(b.x, r.px), B1 = __fsub_rn(b.y, r.py), B2 = __fsub_rn(b.z, r.pz);
-    float C0 = __fsub_rn(c.x, r.px), C1 = __fsub_rn(c.y, r.py), C2 = __fsub_rn(c.z, r.pz);
-    float Akx = sel3(A0, A1, A2, r.kx), Aky = sel3(A0, A1, A2, r.ky), Akz = sel3(A0, A1, A2, r.kz);
-    float Bkx = sel3(B0, B1, B2, r.kx), Bky = sel3(B0, B1, B2, r.ky), Bkz = sel3(B0, B1, B2, r.kz);
-    float Ckx = sel3(C0, C1, C2, r.kx), Cky = sel3(C0, C1, C2, r.ky), Ckz = sel3(C0, C1, C2, r.kz);
-
     float Ax = __fsub_rn(Akx, __fmul_rn(r.Sx, Akz));
     float Ay = __fsub_rn(Aky, __fmul_rn(r.Sy, Akz));
     float Bx = __fsub_rn(Bkx, __fmul_rn(r.Sx, Bkz));
@@ -209,6 +203,25 @@ __device__ __forceinline__ bool woop_hit(const WoopRay &r, float3 a, float3 b, f
     float rcp_det = __fdiv_rn(1.0f, det);
     t_out = __fmul_rn(T, rcp_det);
     return true;
+}
+
+__device__ __forceinline__ bool woop_hit(const WoopRay &r, float3 a, float3 b, float3 c, float &t_out)
+{
+    float A0 = __fsub_rn(a.x, r.px), A1 = __fsub_rn(a.y, r.py), A2 = __fsub_rn(a.z, r.pz);
+    float B0 = __fsub_rn(b.x, r.px), B1 = __fsub_rn(b.y, r.py), B2 = __fsub_rn(b.z, r.pz);
+    float C0 = __fsub_rn(c.x, r.px), C1 = __fsub_rn(c.y, r.py), C2 = __fsub_rn(c.z, r.pz);
+    return woop_hit_permuted(r, sel3(A0, A1, A2, r.kx), sel3(A0, A1, A2, r.ky), sel3(A0, A1, A2, r.kz),
+                             sel3(B0, B1, B2, r.kx), sel3(B0, B1, B2, r.ky), sel3(B0, B1, B2, r.kz),
+                             sel3(C0, C1, C2, r.kx), sel3(C0, C1, C2, r.ky), sel3(C0, C1, C2, r.kz), t_out);
+}
+
+// same test with the vertices in memory (3 consecutive floats each): the permuted components are fetched directly
+// (v[k] - p[k] is the same operation whether the permutation is applied before or after the subtraction)
+__device__ __forceinline__ bool woop_hit_mem(const WoopRay &r, const float *a, const float *b, const float *c, float &t_out)
+{
+    return woop_hit_permuted(r, __fsub_rn(__ldg(a + r.kx), r.pkx), __fsub_rn(__ldg(a + r.ky), r.pky), __fsub_rn(__ldg(a + r.kz), r.pkz),
+                             __fsub_rn(__ldg(b + r.kx), r.pkx), __fsub_rn(__ldg(b + r.ky), r.pky), __fsub_rn(__ldg(b + r.kz), r.pkz),
+                             __fsub_rn(__ldg(c + r.kx), r.pkx), __fsub_rn(__ldg(c + r.ky), r.pky), __fsub_rn(__ldg(c + r.kz), r.pkz), t_out);
 }
 
 // normalize(cross(b-a, c-a)); zero vector when degenerate  (normal returned by mesh_query_ray)

@@ -543,8 +543,9 @@ __device__ __forceinline__ bool rx_enumerate_coop(const BvhNode *__restrict__ rx
 
 // Receiver query of the replay kernel, lockstep: the same answer as rx_query (closest exact t in [0, max_t) over all
 // faces of one receiver), but the faces to test are found by the plane / edge-distance filter (see rfrt_small.cu) over
-// the unit shape's face records in shared memory — every lane runs the same n_faces steps, where the unit-BVH walk left
-// 7.7 of 32 lanes active.  The ray is mapped into unit space in fp32, so the tolerance also carries the rounding of
+// the unit shape's face records in shared memory — every lane runs the same n_faces plane steps (stage A), then checks
+// the edge distances of the handful of faces whose plane is crossed inside the receiver's sphere (stage B), where the
+// unit-BVH walk left 7.7 of 32 lanes active.  The ray is mapped into unit space in fp32, so the tolerance also carries the rounding of
 // that mapping (2^-21 * (|c|_1 + |p|_1) / r).
 __device__ __forceinline__ bool rx_query_sweep(const RxView &rx, const float4 *s_recs, const uint8_t *faces, int n_faces,
                                                const WoopRay &wr, float3 pos, float3 dir, float max_t, float &t_out)
@@ -552,56 +553,65 @@ __device__ __forceinline__ bool rx_query_sweep(const RxView &rx, const float4 *s
     const float3 ou = make_float3((pos.x - rx.cx) * rx.inv_r, (pos.y - rx.cy) * rx.inv_r, (pos.z - rx.cz) * rx.inv_r);
     const float3 du = make_float3(dir.x * rx.inv_r, dir.y * rx.inv_r, dir.z * rx.inv_r);
     const float far = fmaxf(fmaxf(fabsf(ou.x), fabsf(ou.y)), fabsf(ou.z));
-    unsigned mask[4] = {0u, 0u, 0u, 0u}; // faces that may be hit (bit f & 31 of word f >> 5)
-    if (!(far <= 8192.0f)) {
-        // origin farther than 8192 radii (or NaN): fp32 unit-space coordinates get too coarse -> every face is tested
-#pragma unroll
-        for (int w = 0; w < 4; ++w) mask[w] = 0xffffffffu;
-    } else {
-        const float dl = (1.0f + fabsf(ou.x) + fabsf(ou.y) + fabsf(ou.z)) * (1.0f / 65536.0f) +
-                         (fabsf(rx.cx) + fabsf(rx.cy) + fabsf(rx.cz) + fabsf(pos.x) + fabsf(pos.y) + fabsf(pos.z)) * rx.inv_r * (1.0f / 2097152.0f);
-        const float dl_h = dl * (sqrt_approx(du.x * du.x + du.y * du.y + du.z * du.z) * 1.001f);
-        const float INF = __int_as_float(0x7f800000);
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const int f0 = 32 * w, cnt = n_faces - f0 < 32 ? n_faces - f0 : 32;
-            if (cnt <= 0) break;
+    const bool all_faces = !(far <= 8192.0f); // origin farther than 8192 radii (or NaN): unit space too coarse
+    const float dl = (1.0f + fabsf(ou.x) + fabsf(ou.y) + fabsf(ou.z)) * (1.0f / 65536.0f) +
+                     (fabsf(rx.cx) + fabsf(rx.cy) + fabsf(rx.cz) + fabsf(pos.x) + fabsf(pos.y) + fabsf(pos.z)) * rx.inv_r * (1.0f / 2097152.0f);
+    const float dd = du.x * du.x + du.y * du.y + du.z * du.z;
+    const float dl_h = dl * (sqrt_approx(dd) * 1.001f);
+    // Stage A works on the chord of the unit sphere inflated by 1 % (+ tolerance): the shape lies inside the unit
+    // sphere, so a face can only be hit where its plane is crossed inside that sphere, and not behind the origin.
+    // (Chord through the closest-approach point: no cancellation for far origins.)
+    const float inv_dd = rcp_approx(dd);
+    const float tc = -(ou.x * du.x + ou.y * du.y + ou.z * du.z) * inv_dd;
+    const float mx = fmaf(tc, du.x, ou.x), my = fmaf(tc, du.y, ou.y), mz = fmaf(tc, du.z, ou.z);
+    const float rho2 = 1.0201f + 4.0f * dl + 1.0e-3f * far * (1.0f / 8192.0f);
+    const float half2 = (rho2 - (mx * mx + my * my + mz * mz)) * inv_dd;
+    float best = max_t;
+    if (all_faces || half2 >= 0.0f || half2 != half2) { // (a line that misses the inflated sphere cannot hit the receiver)
+        const float half = sqrt_approx(half2);
+        const float lo0 = all_faces ? -3.0e38f : fmaxf(tc - half, 0.0f), hi0 = all_faces ? 3.0e38f : tc + half;
+#pragma unroll 1
+        for (int f0 = 0; f0 < n_faces; f0 += 32) {
+            const int cnt = n_faces - f0 < 32 ? n_faces - f0 : 32;
+            // Stage A (lockstep, plane parameter only) for faces f0 .. f0 + cnt - 1
             unsigned dropped = 0u;
             const float4 *rec = s_recs + 4 * (f0 + cnt - 1);
-#pragma unroll 2
+#pragma unroll 4
             for (int k = 0; k < cnt; ++k, rec -= 4) { // backwards: face f0 + j ends up at bit j
-                const float4 P = rec[0], e0 = rec[1], e1 = rec[2], e2 = rec[3];
+                const float4 P = rec[0];
                 const float nd = fmaf(P.x, du.x, fmaf(P.y, du.y, P.z * du.z));
                 const float np = fmaf(P.x, ou.x, fmaf(P.y, ou.y, fmaf(P.z, ou.z, -P.w)));
                 const float r = rcp_approx(nd);
                 const float t = -np * r;
-                const float ar = fabsf(r);
-                const float thr = (t < -(dl * ar)) ? INF : -(dl_h * ar);
-                const float hx = fmaf(t, du.x, ou.x), hy = fmaf(t, du.y, ou.y), hz = fmaf(t, du.z, ou.z);
-                const float d0 = fmaf(e0.x, hx, fmaf(e0.y, hy, fmaf(e0.z, hz, e0.w)));
-                const float d1 = fmaf(e1.x, hx, fmaf(e1.y, hy, fmaf(e1.z, hz, e1.w)));
-                const float d2 = fmaf(e2.x, hx, fmaf(e2.y, hy, fmaf(e2.z, hz, e2.w)));
-                dropped = __funnelshift_l(__float_as_uint(min3f(d0, d1, d2) - thr), dropped, 1);
+                const float kt = dl * fabsf(r);
+                // sign set <=> t + kt < lo0 or t - kt > hi0 (NaN operands are ignored by min: kept)
+                dropped = __funnelshift_l(__float_as_uint(fminf((t + kt) - lo0, hi0 - (t - kt))), dropped, 1);
             }
-            mask[w] = ~dropped & (cnt >= 32 ? 0xffffffffu : (1u << cnt) - 1u);
-        }
-    }
-    float best = max_t;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        unsigned m = mask[w];
-        while (m) {
-            const int b = __ffs((int)m) - 1;
-            m &= m - 1u;
-            const int f = 32 * w + b;
-            if (f >= n_faces) break;
-            const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
-            const float *v = rx.verts;
-            const float3 a = make_float3(__ldg(v + 3 * i0), __ldg(v + 3 * i0 + 1), __ldg(v + 3 * i0 + 2));
-            const float3 bb = make_float3(__ldg(v + 3 * i1), __ldg(v + 3 * i1 + 1), __ldg(v + 3 * i1 + 2));
-            const float3 c = make_float3(__ldg(v + 3 * i2), __ldg(v + 3 * i2 + 1), __ldg(v + 3 * i2 + 2));
-            float t;
-            if (woop_hit(wr, a, bb, c, t) && t < best && t >= 0.0f) best = t;
+            unsigned m = ~dropped & (cnt >= 32 ? 0xffffffffu : (1u << cnt) - 1u);
+            // Stage B + exact test (per lane, the few faces left)
+            while (m) {
+                const int b = __ffs((int)m) - 1;
+                m &= m - 1u;
+                const int f = f0 + b;
+                if (!all_faces) {
+                    const float4 *fr = s_recs + 4 * f;
+                    const float4 P = fr[0], e0 = fr[1], e1 = fr[2], e2 = fr[3];
+                    const float nd = fmaf(P.x, du.x, fmaf(P.y, du.y, P.z * du.z));
+                    const float np = fmaf(P.x, ou.x, fmaf(P.y, ou.y, fmaf(P.z, ou.z, -P.w)));
+                    const float r = rcp_approx(nd);
+                    const float t = -np * r;
+                    const float thr = -(dl_h * fabsf(r));
+                    const float hx = fmaf(t, du.x, ou.x), hy = fmaf(t, du.y, ou.y), hz = fmaf(t, du.z, ou.z);
+                    const float d0 = fmaf(e0.x, hx, fmaf(e0.y, hy, fmaf(e0.z, hz, e0.w)));
+                    const float d1 = fmaf(e1.x, hx, fmaf(e1.y, hy, fmaf(e1.z, hz, e1.w)));
+                    const float d2 = fmaf(e2.x, hx, fmaf(e2.y, hy, fmaf(e2.z, hz, e2.w)));
+                    if (min3f(d0, d1, d2) < thr) continue; // definitely outside the face (false for NaN: tested)
+                }
+                const float *v = rx.verts;
+                float t;
+                if (woop_hit_mem(wr, v + 3 * faces[3 * f], v + 3 * faces[3 * f + 1], v + 3 * faces[3 * f + 2], t) && t < best && t >= 0.0f)
+                    best = t;
+            }
         }
     }
     t_out = best;

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("configs", nargs="*", default=["C2"])
     ap.add_argument("--cpu-rays", type=int, default=1 << 18)
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--reference-at-full-size", action="store_true", help="also time the reference-faithful C3 map at full size (~10 s per run)")
     args = ap.parse_args()
     for cfg in args.configs:
         if cfg == "C2":
@@ -55,8 +56,8 @@ def main():
         ms, cov = timed(lambda: tr.trace_physical(tx, 1.0, rx, 0.1), 3)
         out.update(physical_ms=ms, physical_arrivals=cov["stats"]["arrivals"], physical_segments=cov["stats"]["segments"],
                    physical_max_dbm=float(np.nanmax(np.where(cov["power"] > 0, cov["dbm"], np.nan))))
-        if cfg == "C2" or args.scale <= 0.25:
-            ms, cov = timed(lambda: tr.coverage(tx, 1, rx, 0.1), 2)
+        if cfg == "C2" or args.scale <= 0.25 or args.reference_at_full_size:
+            ms, cov = timed(lambda: tr.coverage(tx, 1, rx, 0.1), 1 if cfg == "C3" else 2)
             out.update(reference_ms=ms, reference_records=cov["stats"]["records"], reference_max_dbm=float(np.nanmax(cov["dbm"])))
         if args.cpu_rays > 0:
             from oracle import cpu, geometry, post
