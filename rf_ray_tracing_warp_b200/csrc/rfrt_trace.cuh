@@ -588,13 +588,13 @@ __device__ __forceinline__ bool rx_query_sweep(const RxView &rx, const float4 *s
                 dropped = __funnelshift_l(__float_as_uint(fminf((t + kt) - lo0, hi0 - (t - kt))), dropped, 1);
             }
             unsigned m = ~dropped & (cnt >= 32 ? 0xffffffffu : (1u << cnt) - 1u);
-            // Stage B + exact test (per lane, the few faces left)
-            while (m) {
-                const int b = __ffs((int)m) - 1;
-                m &= m - 1u;
-                const int f = f0 + b;
-                if (!all_faces) {
-                    const float4 *fr = s_recs + 4 * f;
+            // Stage B (per lane, the few faces left): in-plane edge distances of the plane hit point
+            if (!all_faces) {
+                unsigned mb = m;
+                while (mb) {
+                    const int b = __ffs((int)mb) - 1;
+                    mb &= mb - 1u;
+                    const float4 *fr = s_recs + 4 * (f0 + b);
                     const float4 P = fr[0], e0 = fr[1], e1 = fr[2], e2 = fr[3];
                     const float nd = fmaf(P.x, du.x, fmaf(P.y, du.y, P.z * du.z));
                     const float np = fmaf(P.x, ou.x, fmaf(P.y, ou.y, fmaf(P.z, ou.z, -P.w)));
@@ -605,8 +605,14 @@ __device__ __forceinline__ bool rx_query_sweep(const RxView &rx, const float4 *s
                     const float d0 = fmaf(e0.x, hx, fmaf(e0.y, hy, fmaf(e0.z, hz, e0.w)));
                     const float d1 = fmaf(e1.x, hx, fmaf(e1.y, hy, fmaf(e1.z, hz, e1.w)));
                     const float d2 = fmaf(e2.x, hx, fmaf(e2.y, hy, fmaf(e2.z, hz, e2.w)));
-                    if (min3f(d0, d1, d2) < thr) continue; // definitely outside the face (false for NaN: tested)
+                    if (min3f(d0, d1, d2) < thr) m &= ~(1u << b); // definitely outside the face (false for NaN: kept)
                 }
+            }
+            // exact test on the survivors (a separate loop: the lanes that still hold a face run it together)
+            while (m) {
+                const int b = __ffs((int)m) - 1;
+                m &= m - 1u;
+                const int f = f0 + b;
                 const float *v = rx.verts;
                 float t;
                 if (woop_hit_mem(wr, v + 3 * faces[3 * f], v + 3 * faces[3 * f + 1], v + 3 * faces[3 * f + 2], t) && t < best && t >= 0.0f)
