@@ -313,3 +313,33 @@ def test_material_table_in_reference_mode(torch_cuda, room_stl):
     tr.set_materials(None)
     _, ir5 = tr.compute_cir(tx, 1, rx, r)
     assert np.array_equal(ir5, base_ir)
+
+
+def test_dense_receiver_lattice_uses_cooperative_enumeration(torch_cuda, almost_empty_stl):
+    """A lattice whose spheres overlap heavily (pitch << radius) selects the warp-cooperative receiver enumeration
+    (rx_enumerate_coop) in rfrt_trace and rfrt_trace_physical.  Reference mode: every received path of sampled receivers
+    == oracle; all receivers: record count == sum over per-receiver oracle runs of the sample.  Physical mode: fields of
+    ALL receivers == oracle."""
+    from oracle import cpu, geometry, post
+    from rf_ray_tracing_warp_b200 import load_mesh
+    n, B, tx, r = 1 << 16, 3, [0.4, 0.1, 0.3], 0.1
+    g = (np.arange(40) - 19.5) * 0.03
+    X, Y = np.meshgrid(g, g, indexing="ij")
+    rxs = np.stack([X, Y, np.full_like(X, 0.62)], axis=-1).reshape(-1, 3)  # 1600 receivers over 1.2 m x 1.2 m: ~40-fold overlap
+    assert rxs.shape[0] * 4 * r * r >= 8 * (1.17 + 2 * r) ** 2              # the density rule of rfrt_trace picks the coop path
+    soup = geometry.load_stl_soup(almost_empty_stl)
+    tr = _tracer(load_mesh(almost_empty_stl), B, n, max_candidates=1 << 22, max_records=1 << 22)
+    out = tr.compute_cir_multi(tx, 1, rxs, r, return_paths=True, dense=False)
+    rec = {k: v.cpu().numpy() for k, v in out["records"].items()}
+    assert rec["ray"].shape[0] > 50_000
+    for k in (0, 39, 777, 820, 1599):
+        o = cpu.trace_paths(soup, geometry.rx_soup(rxs[k], r), tx, B, 0, n, instrument=False)
+        o_paths = post.clean_paths(o["received"], o["mask"])
+        sel = rec["rx"] == k
+        assert np.array_equal(rec["ray"][sel].astype(np.uint32), np.nonzero(o["mask"])[0].astype(np.uint32)), k
+        for row, nv, op in zip(rec["paths"][sel], rec["nverts"][sel], o_paths):
+            assert np.array_equal(row[:nv].view(np.uint32), op.view(np.uint32))
+    phys = tr.trace_physical(tx, 1.0, rxs, r, carrier_hz=2.4e9)
+    o = cpu.trace_physical(soup, rxs, r, tx, B, 0, n, n, 2.4e9, C)
+    assert phys["stats"]["arrivals"] == o["arrivals"] > 100_000
+    np.testing.assert_allclose(phys["field"], o["field"], rtol=1e-9, atol=1e-9 * np.abs(o["field"]).max())
