@@ -169,8 +169,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rays", type=int, default=WORKLOAD["rays_per_gpu"], help="rays per GPU per step")
-    ap.add_argument("--ref-rays", type=int, default=1 << 17, help="rays per step of the CPU reference arm")
-    ap.add_argument("--cpu-sample", type=int, default=1 << 18, help="rays of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--ref-rays", type=int, default=1 << 19, help="rays per step of the CPU reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 21, help="rays of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
