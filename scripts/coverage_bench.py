@@ -34,12 +34,17 @@ def main():
     ap.add_argument("--reference-at-full-size", action="store_true", help="also time the reference-faithful C3 map at full size (~10 s per run)")
     args = ap.parse_args()
     for cfg in args.configs:
-        if cfg == "C2":
+        if cfg == "REF":  # the reference's own coverage.py:15-16,38-40 workload (room.stl, tx as main.py:30)
+            from rf_ray_tracing_warp_b200.coverage import reference_lattice
+            mesh, tx, n, B, grid = load_mesh(os.path.join(ROOT, "models/room.stl")), [10, 0, 5], 1_000_000, 2, 16
+            rx = reference_lattice()
+        elif cfg == "C2":
             mesh, tx, n, B, grid, z = load_mesh(os.path.join(ROOT, "models/almost_empty.stl")), [1, 0, 1], 1 << 24, 4, 256, 2.0
         else:
             mesh, tx, n, B, grid, z = synthetic_terrain(1024, 20.0, 17), [10, 0, 4.5], 1 << 26, 6, 1024, 4.8
         n = int(n * args.scale)
-        rx = plane_lattice(grid, grid, z=z)
+        if cfg != "REF":
+            rx = plane_lattice(grid, grid, z=z)
         cap = (1 << 28) if cfg == "C3" else (1 << 26)
         tr = Tracer(mesh, C, 100e9, 100e-9, B, n, max_candidates=cap, max_records=cap)
         out = dict(cfg=cfg, rays=n, bounces=B, receivers=int(rx.shape[0]), triangles=tr.mesh_info()["n_triangles"])
@@ -56,7 +61,7 @@ def main():
         ms, cov = timed(lambda: tr.trace_physical(tx, 1.0, rx, 0.1), 3)
         out.update(physical_ms=ms, physical_arrivals=cov["stats"]["arrivals"], physical_segments=cov["stats"]["segments"],
                    physical_max_dbm=float(np.nanmax(np.where(cov["power"] > 0, cov["dbm"], np.nan))))
-        if cfg == "C2" or args.scale <= 0.25 or args.reference_at_full_size:
+        if cfg in ("C2", "REF") or args.scale <= 0.25 or args.reference_at_full_size:
             ms, cov = timed(lambda: tr.coverage(tx, 1, rx, 0.1), 1 if cfg == "C3" else 2)
             out.update(reference_ms=ms, reference_records=cov["stats"]["records"], reference_max_dbm=float(np.nanmax(cov["dbm"])))
         if args.cpu_rays > 0:
