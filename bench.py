@@ -313,10 +313,11 @@ def main():
     if rank == 0:
         peak, peak_src = load_peaks()
         achieved = seg_step * BYTES_PER_SEGMENT / (k_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, issue_pct = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-                traffic = json.load(f).get("k_trace_env", {}).get("dram_bytes_per_launch")
+                ncu = json.load(f).get("k_trace_env", {})
+                traffic, issue_pct = ncu.get("dram_bytes_per_launch"), ncu.get("issue_active_pct")
             if traffic is not None:
                 traffic = int(traffic * R / (1 << 28))  # captured at 2^28 rays; it is the direction buffer, linear in rays
         except Exception:
@@ -333,7 +334,8 @@ def main():
                              "algorithmic_bytes_per_segment": BYTES_PER_SEGMENT,
                              "note": "the 44-triangle scene is resident in shared memory: HBM traffic is only the direction "
                                      "buffer, the binding limit is instruction issue (profiles/README.md), so frac can exceed 1",
-                             "traffic_note": "ncu dram__bytes_read+write per launch at 268435456 rays (profiles/ncu_summary.json)"},
+                             "traffic_note": "ncu dram__bytes_read+write per launch at 268435456 rays (profiles/ncu_summary.json)",
+                             "issue_active_pct": issue_pct},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches * 1,
                 "kernel_ms": {"k_gen_dirs": g_ms, "k_trace_env": k_ms, "step": total_ms / args.steps}}
         if args.cpu_sample > 0:
