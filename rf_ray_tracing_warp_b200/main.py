@@ -28,6 +28,10 @@ def main(argv=None):
     ap.add_argument("--rays", type=int, default=TX_NUM_RAYS)
     ap.add_argument("--bounces", type=int, default=MAX_BOUNCES)
     ap.add_argument("--out", default=None, help="directory for impulse_response.npy / paths.npz / result.json / scene.glb")
+    ap.add_argument("--mode", default="reference", choices=["reference", "physical"],
+                    help="reference = main.py:36-55; physical = Tracer.trace_physical (free-space loss, Fresnel amplitude, "
+                         "carrier phase, analytic-sphere receiver; complex impulse response)")
+    ap.add_argument("--carrier", type=float, default=2.4e9)              # main.py:46
     ap.add_argument("--scene", default="glb", choices=["glb", "html", "none"],
                     help="scene export written next to the results (replaces viz/visualization.py)")
     args = ap.parse_args(argv)
@@ -35,6 +39,19 @@ def main(argv=None):
     from . import Tracer, load_mesh, to_dbm
     mesh = load_mesh(args.model)
     tracer = Tracer(mesh, LIGHT_SPEED_MPS, SAMPLE_RATE_HZ, SAMPLE_WINDOW_S, args.bounces, args.rays, verbose=True)
+    if args.mode == "physical":
+        out = tracer.trace_physical(np.array(args.tx), args.tx_power, [args.rx], args.rx_radius, carrier_hz=args.carrier,
+                                    want_ir=True)
+        power, dbm = float(out["power"][0]), float(out["dbm"][0])
+        print(f"Signal RX power: {dbm} dBm (physical mode, {out['stats']['arrivals']} arrivals)")
+        result = dict(model=args.model, tx=args.tx, rx=args.rx, rays=args.rays, bounces=args.bounces, mode="physical",
+                      rx_power=power, rx_power_dbm=dbm, **out["stats"])
+        if args.out:
+            os.makedirs(args.out, exist_ok=True)
+            np.save(os.path.join(args.out, "impulse_response_complex.npy"), out["impulse_response"].cpu().numpy()[0])
+            with open(os.path.join(args.out, "result.json"), "w") as f:
+                json.dump(result, f)
+        return result
     paths, impulse_response = tracer.compute_cir(np.array(args.tx), args.tx_power, np.array(args.rx), args.rx_radius)
     out = tracer.compute_cir_multi(np.array(args.tx), args.tx_power, [args.rx], args.rx_radius, dense=False)
     power = float(tracer.rx_power(out["records"], 1).cpu().numpy()[0])   # main.py:46-55
