@@ -396,7 +396,18 @@ __device__ __forceinline__ void literal_trace(const LiteralEnv &E, const RxView 
     float3 dir = ray_direction(tid); // kernel.py:51-52
     float3 pos = tx;                 // :53
     sink.vertex(0, pos);             // :55
+    // A receiver hit at t == 0 leaves the ray where it is with the direction it had (kernel.py:87: pos += dir * 0, no
+    // reflection), so every later iteration evaluates the same two queries on the same values and takes the same branch
+    // — the "stuck" paths of the reference's golden scene.  They are replayed without queries.
+    bool stuck = false;
+    float t_stuck = 0.0f;
     for (int bounce = 0; bounce < max_bounces; ++bounce) {
+        if (stuck) {
+            pos = advance(pos, dir, t_stuck); // :87
+            sink.vertex(bounce + 1, pos);     // :88
+            sink.received(bounce);            // :89-91
+            continue;
+        }
         WoopRay wr = woop_setup(pos, dir);
         SlabRay sr = slab_setup(pos, dir);
         float t_rx = 0.0f;
@@ -412,6 +423,7 @@ __device__ __forceinline__ void literal_trace(const LiteralEnv &E, const RxView 
             pos = advance(pos, dir, t_rx);  // :87
             sink.vertex(bounce + 1, pos);   // :88
             sink.received(bounce);          // :89-91
+            if (t_rx == 0.0f) { stuck = true; t_stuck = t_rx; }
         } else if (maybe_hit_env) {
             pos = advance(pos, dir, h.t);   // :94
             sink.vertex(bounce + 1, pos);   // :95
