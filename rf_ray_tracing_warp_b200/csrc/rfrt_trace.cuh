@@ -567,8 +567,11 @@ __device__ __forceinline__ bool rx_query_sweep(const RxView &rx, const float4 *s
     const float rho2 = 1.0201f + 4.0f * dl + 1.0e-3f * far * (1.0f / 8192.0f);
     const float half2 = (rho2 - (mx * mx + my * my + mz * mz)) * inv_dd;
     float best = max_t;
-    if (all_faces || half2 >= 0.0f || half2 != half2) { // (a line that misses the inflated sphere cannot hit the receiver)
-        const float half = sqrt_approx(half2);
+    const float half = sqrt_approx(half2);
+    // no hit is possible when the line misses the inflated sphere, or when the whole chord lies more than 0.05 radii
+    // behind the origin (hits need t >= 0); NaN falls through to the sweep
+    const bool can_hit = all_faces || !(half2 < 0.0f || (tc + half) * sqrt_approx(dd) < -0.05f);
+    if (can_hit) {
         const float lo0 = all_faces ? -3.0e38f : fmaxf(tc - half, 0.0f), hi0 = all_faces ? 3.0e38f : tc + half;
 #pragma unroll 1
         for (int f0 = 0; f0 < n_faces; f0 += 32) {
