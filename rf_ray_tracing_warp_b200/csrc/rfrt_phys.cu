@@ -140,7 +140,8 @@ __global__ void __launch_bounds__(PHYS_THREADS) k_trace_phys(const PhysParams P)
                     const double dd = __dadd_rn(__dadd_rn(__dmul_rn((double)bd.x, (double)bd.x), __dmul_rn((double)bd.y, (double)bd.y)),
                                                 __dmul_rn((double)bd.z, (double)bd.z));
                     phys_arrival(P, k, bp, bd, dd, dlen_b, bt < 1.0e6f ? (double)bt : 1.0e6, L_b, gamma_b, n_arr);
-                });
+                },
+                [](bool) {});
             if (!ok && lane == 0) atomicAdd(&P.counters[RFRT_CTR_QUEUE_OVERFLOW], 1ull);
         } else if (P.n_rx > 0 && has_ray) {
             // sparse receiver sets: every lane walks the receiver BVH for its own segment

@@ -20,6 +20,8 @@ __constant__ uint8_t c_rx_faces[3 * 128];
 namespace {
 
 constexpr int TRACE_THREADS = 128;
+constexpr int RX_CAND_BUF = 256; // receivers staged per warp between two appends (cooperative enumeration)
+constexpr int RX_COOP_INTS = RX_QUEUE_CAP + RX_CAND_BUF + 4; // per-warp shared memory of the cooperative enumeration
 constexpr int MAX_RECV_BOUNCES = 32;
 
 struct TraceParams {
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
     // SMALL: the whole scene (filter tables + exact-test data) lives in shared memory
     SmallScene S;
     if (SMALL) {
-        float *img = reinterpret_cast<float *>(s_queue_base + (COOP ? RX_QUEUE_CAP * (TRACE_THREADS / 32) : 0));
+        float *img = reinterpret_cast<float *>(s_queue_base + (COOP ? RX_COOP_INTS * (TRACE_THREADS / 32) : 0));
         const int n = (int)P.n_tris, np = P.small_pairs;
         for (int i = threadIdx.x; i < 30 * np + 17 * n; i += TRACE_THREADS) img[i] = __ldg(P.small + i);
         __syncthreads();
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
         S.erode = (float)(2.0 * SMALL_REACH_REL) * P.small_extent;
     }
 
-    int *rx_queue = s_queue_base + (COOP ? RX_QUEUE_CAP * (threadIdx.x >> 5) : 0); // this warp's node queue
+    int *rx_queue = s_queue_base + (COOP ? RX_COOP_INTS * (threadIdx.x >> 5) : 0); // this warp's node queue (+ candidate buffer)
 
     bool has_ray = false;
     bool exhausted = false; // warp-uniform
@@ -278,7 +280,14 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
                           fminf(pos.z, ez) <= P.rx_hi[2] && fmaxf(pos.z, ez) >= P.rx_lo[2];
             }
             if (__any_sync(FULL, near_rx)) {
+                // The receivers that pass the sphere filter are staged per segment in a small shared-memory buffer and
+                // appended in runs (one global atomic per run): consecutive candidates then belong to the same ray, so
+                // the replay kernel's warps work on one ray at a time instead of a mixture of several warps' rays.
                 uint32_t gid_b = 0; int bounce_b = 0;
+                int *cbuf = rx_queue + RX_QUEUE_CAP;        // [RX_CAND_BUF] receiver ids, then the fill count
+                int *ccount = cbuf + RX_CAND_BUF;
+                if (lane == 0) *ccount = 0;
+                __syncwarp();
                 const bool ok = rx_enumerate_coop(
                     P.rx_nodes, P.rx_order, near_rx, rx_queue,
                     [&](int src, float3 &bp, float3 &bd, float &bt) {
@@ -288,7 +297,25 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
                         gid_b = __shfl_sync(FULL, (uint32_t)(P.chunk_begin + ray), src);
                         bounce_b = __shfl_sync(FULL, bounce, src);
                     },
-                    [&](int k, float3 bp, float3 bd, float bt) { rx_filter_and_emit(P, k, bp, bd, bt, gid_b, bounce_b); });
+                    [&](int k, float3 bp, float3 bd, float bt) {
+                        const float cx = (float)__ldg(P.rx_centers + 3 * k), cy = (float)__ldg(P.rx_centers + 3 * k + 1),
+                                    cz = (float)__ldg(P.rx_centers + 3 * k + 2);
+                        if (rx_sphere_filter(bp, bd, cx, cy, cz, P.rx_radius, bt)) cbuf[atomicAdd(ccount, 1)] = k;
+                    },
+                    [&](bool final) {
+                        const int cnt = *ccount; // (every step adds at most 64 entries: the buffer never overflows)
+                        if (cnt >= RX_CAND_BUF - 64 || (final && cnt > 0)) {
+                            unsigned long long base = 0;
+                            if (lane == 0) base = atomicAdd(&P.counters[RFRT_CTR_CANDIDATES], (unsigned long long)cnt);
+                            base = __shfl_sync(FULL, base, 0);
+                            for (int j = lane; j < cnt; j += 32)
+                                if ((int64_t)(base + j) < P.cand_capacity)
+                                    P.candidates[base + j] = make_uint4(gid_b, (uint32_t)cbuf[j], (uint32_t)bounce_b, 0u);
+                            __syncwarp();
+                            if (lane == 0) *ccount = 0;
+                            __syncwarp();
+                        }
+                    });
                 if (!ok && lane == 0) atomicAdd(&P.counters[RFRT_CTR_QUEUE_OVERFLOW], 1ull);
             }
         }
@@ -750,7 +777,7 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     const bool lstack = !small && P.stack_depth > 16; // deep tree: local-memory stack (<= 64 entries by construction)
     if (lstack && P.stack_depth > 64) { set_error("rfrt_trace: BVH deeper than 64 levels"); return RFRT_ERR_INVALID; }
     if (lstack) P.stack_depth = 0;
-    const size_t smem = stack_bytes(P.stack_depth) + (P.rx_coop ? sizeof(int) * RX_QUEUE_CAP * (TRACE_THREADS / 32) : 0) +
+    const size_t smem = stack_bytes(P.stack_depth) + (P.rx_coop ? sizeof(int) * RX_COOP_INTS * (TRACE_THREADS / 32) : 0) +
                         (small ? sizeof(float) * small_image_floats(m->small_pairs, (int)P.n_tris) : 0);
     typedef void (*kern_t)(const TraceParams);
     const int variant = small ? (m->small_pairs > 16 ? 2 : 1) : (lstack ? 3 : 0);

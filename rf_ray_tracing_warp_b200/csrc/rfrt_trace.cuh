@@ -490,9 +490,11 @@ __device__ __forceinline__ bool rx_query(const RxView &rx, const uint8_t *faces,
 // ---------------------------------------------------------------------------------------------------------
 constexpr int RX_QUEUE_CAP = 1024; // ints per warp
 
-template <class Bcast, class Leaf>
+//   flush(final) is called by all lanes at converged points: after every step of a walk (final = false) and after the
+//               last step of a segment (final = true) — the place to drain what `leaf` has staged for this segment
+template <class Bcast, class Leaf, class Flush>
 __device__ __forceinline__ bool rx_enumerate_coop(const BvhNode *__restrict__ rx_nodes, const int32_t *__restrict__ rx_order,
-                                                  bool want, int *queue, Bcast &&bcast, Leaf &&leaf)
+                                                  bool want, int *queue, Bcast &&bcast, Leaf &&leaf, Flush &&flush)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -536,6 +538,7 @@ __device__ __forceinline__ bool rx_enumerate_coop(const BvhNode *__restrict__ rx
             n += __popc(b0) + __popc(b1);
             if (n > RX_QUEUE_CAP) { n = RX_QUEUE_CAP; ok = false; }
             __syncwarp();
+            flush(n == 0);
         }
     }
     return ok;
