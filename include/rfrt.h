@@ -22,7 +22,10 @@
  *   - every function returns 0 on success or a negative rfrt_status; rfrt_last_error() gives the
  *     message of the last failure on the calling thread.  No C++ exception crosses this boundary.
  *   - the library owns only what lives behind a handle (BVH nodes, re-ordered triangles, receiver
- *     vertices) and frees it in *_destroy.
+ *     vertices, the ray-sort workspace of big scenes) and frees it in *_destroy.
+ *   - concurrency: calls on DIFFERENT environment handles may run on different streams at the same time; calls that
+ *     share an environment handle, and replay / compat calls whose receiver sets have different face tables (the
+ *     table lives in __constant__ memory), must be stream-ordered.
  */
 #ifndef RFRT_H
 #define RFRT_H

@@ -795,7 +795,7 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     int grid = 0;
     int rc = grid_for((const void *)kern, smem, &grid);
     if (rc) return rc;
-    if (r) { rc = upload_faces(r, stream); if (rc) return rc; }
+    // (the face table in __constant__ memory is only read by the replay / compat kernels)
 
     // BVH scenes: trace the rays of a chunk in direction-coherent order (workspace cached with the mesh)
     const bool sorted = !small && !(flags & RFRT_FLAG_NO_RAY_SORT) && n >= 4096;
