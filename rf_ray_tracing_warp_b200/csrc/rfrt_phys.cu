@@ -40,6 +40,10 @@ struct PhysParams {
     int64_t n_bins;
     int32_t stack_depth;
     int32_t rx_coop; // dense receiver sets: warp-cooperative enumeration (see rfrt_trace.cu)
+    const float *small;  // small scenes: shared-memory image of the lockstep sweep (rfrt_small.cu), else NULL
+    const float *face_normals; // [n_tris*3] original order
+    int32_t small_pairs;
+    float small_extent;
 };
 
 // one receiver against one segment: fp64 closest-approach test + field accumulation
@@ -72,7 +76,9 @@ __device__ __forceinline__ void phys_arrival(const PhysParams &P, int64_t k, flo
     ++n_arr;
 }
 
-template <bool LSTACK>
+// SMALL: 0 = BVH walk, 1 = lockstep sweep of <= 16 triangle pairs, 2 = of <= 32 pairs (closest_hit_small with the
+//        triangle just left excluded from the exact tests)
+template <bool LSTACK, int SMALL>
 __global__ void __launch_bounds__(PHYS_THREADS) k_trace_phys(const PhysParams P)
 {
     extern __shared__ __align__(16) int s_stack_raw[];
@@ -84,6 +90,14 @@ __global__ void __launch_bounds__(PHYS_THREADS) k_trace_phys(const PhysParams P)
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     int *rx_queue = s_stack_raw + 2 * P.stack_depth * PHYS_THREADS + RX_QUEUE_CAP * (threadIdx.x >> 5); // this warp's node queue
+    SmallScene S;
+    if (SMALL) { // the scene image lives behind the stacks and (dense receiver sets) the node queues
+        float *img = reinterpret_cast<float *>(s_stack_raw + 2 * P.stack_depth * PHYS_THREADS + (P.rx_coop ? RX_QUEUE_CAP * (PHYS_THREADS / 32) : 0));
+        const int n = (int)P.n_tris, np = P.small_pairs;
+        for (int i = threadIdx.x; i < 30 * np + 17 * n; i += PHYS_THREADS) img[i] = __ldg(P.small + i);
+        __syncthreads();
+        S = small_scene_view(img, np, n, P.small_extent, 0.0f, 0.0f);
+    }
 
     bool has_ray = false, exhausted = false;
     float3 pos = make_float3(0.f, 0.f, 0.f), dir = make_float3(0.f, 0.f, 1.f);
@@ -116,8 +130,12 @@ __global__ void __launch_bounds__(PHYS_THREADS) k_trace_phys(const PhysParams P)
         float dlen_f = 1.0f;
         if (has_ray) {
             const WoopRay wr = woop_setup(pos, dir);
-            const SlabRay sr = slab_setup(pos, dir);
-            closest_hit(P.nodes, P.tris, P.n_tris, wr, sr, stack, stack_t, STRIDE, h, prev);
+            if (SMALL) {
+                closest_hit_small<SMALL == 2>(S, pos, dir, wr, h, prev);
+            } else {
+                const SlabRay sr = slab_setup(pos, dir);
+                closest_hit(P.nodes, P.tris, P.n_tris, wr, sr, stack, stack_t, STRIDE, h, prev);
+            }
             ++n_seg;
             dlen_f = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dir.x, dir.x), __fmul_rn(dir.y, dir.y)), __fmul_rn(dir.z, dir.z)));
         }
@@ -176,8 +194,13 @@ __global__ void __launch_bounds__(PHYS_THREADS) k_trace_phys(const PhysParams P)
         if (has_ray) {
             if (hit) {
                 ++n_hit;
-                const float4 n4 = __ldg(P.normals + h.slot);
-                const float3 nrm = make_float3(n4.x, n4.y, n4.z);
+                float3 nrm; // normalize(cross(b-a, c-a)) of the hit triangle, precomputed at build time
+                if (SMALL) {
+                    nrm = make_float3(S.normals[3 * h.face], S.normals[3 * h.face + 1], S.normals[3 * h.face + 2]);
+                } else {
+                    const float4 n4 = __ldg(P.normals + h.slot);
+                    nrm = make_float3(n4.x, n4.y, n4.z);
+                }
                 const float dn = __fadd_rn(__fadd_rn(__fmul_rn(dir.x, nrm.x), __fmul_rn(dir.y, nrm.y)), __fmul_rn(dir.z, nrm.z));
                 const double nmat = P.materials ? (double)__ldg(P.materials + h.face) : 5.0;
                 double ci = __ddiv_rn(fabs((double)dn), dlen);
@@ -248,6 +271,8 @@ extern "C" int rfrt_trace_physical(rfrt_handle env_mesh, rfrt_handle rxset, cons
 
     PhysParams P;
     P.nodes = m->bvh.nodes; P.tris = m->tris; P.normals = m->normals; P.n_tris = m->bvh.n_prims;
+    P.small = (m->small && m->bvh.n_prims > 0) ? m->small : nullptr; P.face_normals = m->face_normals;
+    P.small_pairs = m->small_pairs; P.small_extent = m->small_extent;
     P.materials = d_materials;
     P.rx_nodes = r ? r->bvh.nodes : nullptr; P.rx_order = r ? r->bvh.prim_order : nullptr;
     P.rx_centers = r ? r->centers : nullptr; P.n_rx = r ? r->n_receivers : 0;
@@ -271,7 +296,7 @@ extern "C" int rfrt_trace_physical(rfrt_handle env_mesh, rfrt_handle rxset, cons
         const double d2 = 4.0 * r->radius * r->radius;
         P.rx_coop = (double)r->n_receivers * d2 >= 8.0 * (face > d2 ? face : d2) ? 1 : 0;
     }
-    int depth = m->bvh.max_depth;
+    int depth = P.small ? 0 : m->bvh.max_depth; // (small scenes: lockstep sweep, the stack only serves the receiver walk)
     if (r && !P.rx_coop && r->bvh.max_depth > depth) depth = r->bvh.max_depth;
     depth += 2;
     if (depth < 8) depth = 8;
@@ -279,8 +304,14 @@ extern "C" int rfrt_trace_physical(rfrt_handle env_mesh, rfrt_handle rxset, cons
     if (lstack && depth > 64) { set_error("rfrt_trace_physical: BVH deeper than 64 levels"); return RFRT_ERR_INVALID; }
     P.stack_depth = lstack ? 0 : depth;
     const size_t smem = (size_t)P.stack_depth * PHYS_THREADS * 2 * sizeof(int) +
-                        (P.rx_coop ? sizeof(int) * RX_QUEUE_CAP * (PHYS_THREADS / 32) : 0);
-    const void *kern = lstack ? (const void *)k_trace_phys<true> : (const void *)k_trace_phys<false>;
+                        (P.rx_coop ? sizeof(int) * RX_QUEUE_CAP * (PHYS_THREADS / 32) : 0) +
+                        (P.small ? sizeof(float) * small_image_floats(m->small_pairs, (int)P.n_tris) : 0);
+    typedef void (*kern_t)(const PhysParams);
+    const int sv = P.small ? (m->small_pairs > 16 ? 2 : 1) : 0;
+    static const kern_t kerns[2][3] = {{k_trace_phys<false, 0>, k_trace_phys<false, 1>, k_trace_phys<false, 2>},
+                                       {k_trace_phys<true, 0>, k_trace_phys<true, 1>, k_trace_phys<true, 2>}};
+    const kern_t kfn = kerns[lstack ? 1 : 0][sv];
+    const void *kern = (const void *)kfn;
     int dev = 0, sms = 0, per_sm = 0;
     RFRT_CUDA(cudaGetDevice(&dev));
     RFRT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -296,8 +327,7 @@ extern "C" int rfrt_trace_physical(rfrt_handle env_mesh, rfrt_handle rxset, cons
         int g = grid;
         const int64_t need = (cn + PHYS_THREADS - 1) / PHYS_THREADS;
         if (need < g) g = (int)need;
-        if (lstack) k_trace_phys<true><<<g, PHYS_THREADS, smem, stream>>>(P);
-        else k_trace_phys<false><<<g, PHYS_THREADS, smem, stream>>>(P);
+        kfn<<<g, PHYS_THREADS, smem, stream>>>(P);
     }
     RFRT_CUDA(cudaGetLastError());
     return RFRT_OK;

@@ -176,14 +176,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
         const int n = (int)P.n_tris, np = P.small_pairs;
         for (int i = threadIdx.x; i < 30 * np + 17 * n; i += TRACE_THREADS) img[i] = __ldg(P.small + i);
         __syncthreads();
-        S.recs = reinterpret_cast<const float4 *>(img);
-        S.nbr = reinterpret_cast<const uint4 *>(img + 28 * np);
-        S.slot_tri = reinterpret_cast<const int *>(img + 28 * np + 4 * n);
-        S.soup = img + 30 * np + 4 * n;
-        S.normals = img + 30 * np + 13 * n;
-        S.tri_slot = reinterpret_cast<const int *>(img + 30 * np + 16 * n);
-        S.n_pairs = np; S.extent = P.small_extent; S.tau = (float)SMALL_TAU_REL * P.small_extent;
-        S.erode = (float)(2.0 * SMALL_REACH_REL) * P.small_extent;
+        S = small_scene_view(img, np, n, P.small_extent, (float)SMALL_TAU_REL * P.small_extent,
+                             (float)(2.0 * SMALL_REACH_REL) * P.small_extent);
     }
 
     int *rx_queue = s_queue_base + (COOP ? RX_COOP_INTS * (threadIdx.x >> 5) : 0); // this warp's node queue (+ candidate buffer)

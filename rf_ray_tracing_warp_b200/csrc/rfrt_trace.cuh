@@ -356,8 +356,10 @@ __device__ __forceinline__ void small_resolve(const SmallScene &S, unsigned lo, 
 }
 
 // WIDE: more than 16 pairs (the candidate mask needs a second word)
+// (skip: a triangle the query ignores — physical mode's "the triangle just left"; -1 = none)
 template <bool WIDE>
-__device__ __forceinline__ void closest_hit_small(const SmallScene &S, float3 pos, float3 dir, const WoopRay &wr, Hit &h)
+__device__ __forceinline__ void closest_hit_small(const SmallScene &S, float3 pos, float3 dir, const WoopRay &wr, Hit &h,
+                                                  int skip = -1)
 {
     // ---- phase 1: lockstep candidate filter ------------------------------------------------------------------
     // tolerance (metres) = 2^-16 * (extent + |p|_1) / sin(angle between ray and plane); see rfrt_small.cu
@@ -368,7 +370,22 @@ __device__ __forceinline__ void closest_hit_small(const SmallScene &S, float3 po
     const unsigned hi = WIDE ? sweep_pairs(S.recs + 7 * 16, n_hi, pos, dir, dl, dl_h) : 0u;
     // ---- phase 2 ---------------------------------------------------------------------------------------------
     const SmallExact X = small_exact_setup(S, wr);
-    small_resolve<false>(S, lo, hi, pos, dir, dl, X, wr, -1, h);
+    if (skip >= 0) small_resolve<true>(S, lo, hi, pos, dir, dl, X, wr, skip, h);
+    else small_resolve<false>(S, lo, hi, pos, dir, dl, X, wr, -1, h);
+}
+
+// pointers into the small-scene image staged at `img` (layout: rfrt_internal.h)
+__device__ __forceinline__ SmallScene small_scene_view(const float *img, int n_pairs, int n_tris, float extent, float tau, float erode)
+{
+    SmallScene S;
+    S.recs = reinterpret_cast<const float4 *>(img);
+    S.nbr = reinterpret_cast<const uint4 *>(img + 28 * n_pairs);
+    S.slot_tri = reinterpret_cast<const int *>(img + 28 * n_pairs + 4 * n_tris);
+    S.soup = img + 30 * n_pairs + 4 * n_tris;
+    S.normals = img + 30 * n_pairs + 13 * n_tris;
+    S.tri_slot = reinterpret_cast<const int *>(img + 30 * n_pairs + 16 * n_tris);
+    S.n_pairs = n_pairs; S.extent = extent; S.tau = tau; S.erode = erode;
+    return S;
 }
 
 // Self-re-hit shortcut.  The reference never offsets a reflected ray (kernel.py:94-96), so most segments that start on
