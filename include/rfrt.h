@@ -109,10 +109,11 @@ RFRT_API int rfrt_mesh_export(rfrt_handle mesh, float *d_nodes, int32_t *d_tri_o
  *   plane (n.xyz, d) + 2 x 3 edge functions (m.xyz, c)), h_slot_tri [64] (slot -> triangle), *n_pairs,
  *   *extent (max |coordinate|), h_nbr [n*4] or NULL (neighbour pair masks of the self-re-hit shortcut: interior,
  *   boundary, and both restricted to lower triangle indices; bit k = pair k holds another triangle within
- *   1e-3 * extent of this one).  RFRT_ERR_INVALID when the scene needs more than 64 slots (it then takes the BVH path).
- *   Layout and tolerance: csrc/rfrt_small.cu. */
+ *   1e-3 * extent of this one), h_class_begin [5] or NULL (pairs are ordered general / x- / y- / z-aligned planes;
+ *   class c = pairs [h_class_begin[c], h_class_begin[c+1])).  RFRT_ERR_INVALID when the scene needs more than 64 slots
+ *   (it then takes the BVH path).  Layout and tolerance: csrc/rfrt_small.cu. */
 RFRT_API int rfrt_small_scene_tables(const float *h_soup, int32_t n_triangles, float *h_recs, int32_t *h_slot_tri,
-                            int32_t *n_pairs, float *extent, uint32_t *h_nbr);
+                            int32_t *n_pairs, float *extent, uint32_t *h_nbr, int32_t *h_class_begin);
 
 /* ---------------------------------------------------------------------------------------------
  * Receiver set.  Replaces Tracer._generate_rx_mesh (tracer.py:26-30), batched over R receivers:

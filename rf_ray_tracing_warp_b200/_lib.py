@@ -35,7 +35,7 @@ SIGNATURES = {
                                       ctypes.POINTER(c_i32), ctypes.POINTER(c_f)]),
     "rfrt_mesh_export": (ctypes.c_int, [c_u64, c_void_p, c_void_p, c_void_p]),
     "rfrt_small_scene_tables": (ctypes.c_int, [c_void_p, c_i32, c_void_p, c_void_p, ctypes.POINTER(c_i32),
-                                               ctypes.POINTER(c_f), c_void_p]),
+                                               ctypes.POINTER(c_f), c_void_p, c_void_p]),
     "rfrt_rxset_create": (ctypes.c_int, [c_void_p, c_i64, c_d, ctypes.POINTER(c_d), c_i32, ctypes.POINTER(c_i32),
                                          c_i32, c_void_p, ctypes.POINTER(c_u64)]),
     "rfrt_rxset_destroy": (ctypes.c_int, [c_u64]),

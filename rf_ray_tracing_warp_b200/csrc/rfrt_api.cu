@@ -179,7 +179,7 @@ extern "C" int rfrt_mesh_create(const float *d_vertices_xyz, int64_t n_vertices,
             RFRT_CUDA(cudaMemcpy(soup.data(), m->soup, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost));
             RFRT_CUDA(cudaMemcpy(fnorm.data(), m->face_normals, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
             int32_t n_pairs = 0;
-            if (small_scene_tables(soup.data(), n, recs.data(), slot_tri.data(), &n_pairs, &m->small_extent) == RFRT_OK) {
+            if (small_scene_tables(soup.data(), n, recs.data(), slot_tri.data(), &n_pairs, &m->small_extent, m->small_class) == RFRT_OK) {
                 m->small_pairs = n_pairs;
                 std::vector<float> image(small_image_floats(n_pairs, n));
                 float *w = image.data();

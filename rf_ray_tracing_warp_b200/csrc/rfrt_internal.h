@@ -47,6 +47,7 @@ struct Mesh {
     // recs[28*pairs] | nbr[4*n] | slot_tri[2*pairs] | soup[9*n] | face_normals[3*n] | tri_slot[n]   (first two: 16-byte rows)
     float *small = nullptr;
     int32_t small_pairs = 0;
+    int32_t small_class[5] = {0, 0, 0, 0, 0}; // pair ranges of the plane classes (general, x-, y-, z-aligned)
     float small_extent = 0.0f;
     float build_ms = 0.0f;
     float *materials = nullptr;  // [n] refractive index per triangle (rfrt_mesh_set_materials) or NULL = 5.0 everywhere
@@ -86,7 +87,8 @@ void keep_pool_memory();
 int64_t sort_hist_blocks(int64_t n);
 uint64_t *radix_sort_u64(uint64_t *a, uint64_t *b, uint32_t *hist, int64_t n, int shift, int passes, cudaStream_t stream);
 
-int small_scene_tables(const float *soup, int n_tris, float *recs, int32_t *slot_tri, int32_t *n_pairs, float *extent);
+int small_scene_tables(const float *soup, int n_tris, float *recs, int32_t *slot_tri, int32_t *n_pairs, float *extent,
+                       int32_t *class_begin);
 void small_scene_neighbours(const float *soup, int n_tris, const int32_t *slot_tri, int n_pairs, double reach, uint32_t *nbr,
                             int32_t *tri_slot);
 inline size_t small_image_floats(int n_pairs, int n_tris) { return 30 * (size_t)n_pairs + 17 * (size_t)n_tris; }

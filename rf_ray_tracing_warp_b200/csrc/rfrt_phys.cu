@@ -43,6 +43,7 @@ struct PhysParams {
     const float *small;  // small scenes: shared-memory image of the lockstep sweep (rfrt_small.cu), else NULL
     const float *face_normals; // [n_tris*3] original order
     int32_t small_pairs;
+    int32_t small_class[5];
     float small_extent;
 };
 
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(PHYS_THREADS) k_trace_phys(const PhysParams P)
         const int n = (int)P.n_tris, np = P.small_pairs;
         for (int i = threadIdx.x; i < 30 * np + 17 * n; i += PHYS_THREADS) img[i] = __ldg(P.small + i);
         __syncthreads();
-        S = small_scene_view(img, np, n, P.small_extent, 0.0f, 0.0f);
+        S = small_scene_view(img, np, n, P.small_class, P.small_extent, 0.0f, 0.0f);
     }
 
     bool has_ray = false, exhausted = false;
@@ -273,6 +274,7 @@ extern "C" int rfrt_trace_physical(rfrt_handle env_mesh, rfrt_handle rxset, cons
     P.nodes = m->bvh.nodes; P.tris = m->tris; P.normals = m->normals; P.n_tris = m->bvh.n_prims;
     P.small = (m->small && m->bvh.n_prims > 0) ? m->small : nullptr; P.face_normals = m->face_normals;
     P.small_pairs = m->small_pairs; P.small_extent = m->small_extent;
+    for (int c = 0; c < 5; ++c) P.small_class[c] = m->small_class[c];
     P.materials = d_materials;
     P.rx_nodes = r ? r->bvh.nodes : nullptr; P.rx_order = r ? r->bvh.prim_order : nullptr;
     P.rx_centers = r ? r->centers : nullptr; P.n_rx = r ? r->n_receivers : 0;

@@ -157,7 +157,11 @@ void small_scene_neighbours(const float *soup, int n_tris, const int32_t *slot_t
 // duplicate candidate is harmless).  A degenerate triangle (no usable normal) gets n = 0: every lane then computes
 // NaN and keeps it as a candidate, so the exact test alone decides (it never accepts a zero-area triangle, but a
 // sliver might be hit).  Returns RFRT_ERR_INVALID when the scene needs more than RFRT_SMALL_MAX_TRIS slots.
-int small_scene_tables(const float *soup, int n_tris, float *recs, int32_t *slot_tri, int32_t *n_pairs, float *extent)
+// class_begin[5]: the pairs are ordered by the class of their plane — general (incl. degenerate) first, then planes
+// normal to x, y, z — and class c occupies pairs [class_begin[c], class_begin[c+1]).  The device sweeps axis-aligned
+// planes with the zero terms of the general formulas left out (same values, two thirds of the instructions).
+int small_scene_tables(const float *soup, int n_tris, float *recs, int32_t *slot_tri, int32_t *n_pairs, float *extent,
+                       int32_t *class_begin)
 {
     if (n_tris < 0 || n_tris > RFRT_SMALL_MAX_TRIS) return RFRT_ERR_INVALID;
     struct Pl {
@@ -209,8 +213,19 @@ int small_scene_tables(const float *soup, int n_tris, float *recs, int32_t *slot
     int need = 0;
     for (const Pl &p : pls) need += ((int)p.tris.size() + 1) / 2;
     if (2 * need > RFRT_SMALL_MAX_TRIS) return RFRT_ERR_INVALID;
+    auto plane_class = [](const Pl &p) {
+        if (p.degenerate) return 0;
+        const bool zx = p.n.x == 0.0, zy = p.n.y == 0.0, zz = p.n.z == 0.0;
+        if (zy && zz && p.n.x == 1.0) return 1;
+        if (zx && zz && p.n.y == 1.0) return 2;
+        if (zx && zy && p.n.z == 1.0) return 3;
+        return 0;
+    };
     int pair = 0;
-    for (const Pl &p : pls) {
+    for (int cls = 0; cls < 4; ++cls) {
+      if (class_begin) class_begin[cls] = pair;
+      for (const Pl &p : pls) {
+        if (plane_class(p) != cls) continue;
         for (size_t j = 0; j < p.tris.size(); j += 2) {
             float *R = recs + 28 * pair;
             R[0] = (float)p.n.x; R[1] = (float)p.n.y; R[2] = (float)p.n.z; R[3] = (float)p.d;
@@ -236,7 +251,9 @@ int small_scene_tables(const float *soup, int n_tris, float *recs, int32_t *slot
             }
             ++pair;
         }
+      }
     }
+    if (class_begin) class_begin[4] = pair;
     *n_pairs = pair;
     *extent = (float)ext;
     return RFRT_OK;
@@ -275,13 +292,13 @@ void unit_face_records(const double *unit_v, const int32_t *faces, int n_faces, 
 } // namespace rfrt
 
 extern "C" int rfrt_small_scene_tables(const float *h_soup, int32_t n_triangles, float *h_recs, int32_t *h_slot_tri,
-                                       int32_t *n_pairs, float *extent, uint32_t *h_nbr)
+                                       int32_t *n_pairs, float *extent, uint32_t *h_nbr, int32_t *h_class_begin)
 {
     if (!h_soup || !h_recs || !h_slot_tri || !n_pairs || !extent) {
         rfrt::set_error("rfrt_small_scene_tables: null argument");
         return RFRT_ERR_INVALID;
     }
-    int rc = rfrt::small_scene_tables(h_soup, n_triangles, h_recs, h_slot_tri, n_pairs, extent);
+    int rc = rfrt::small_scene_tables(h_soup, n_triangles, h_recs, h_slot_tri, n_pairs, extent, h_class_begin);
     if (rc) { rfrt::set_error("rfrt_small_scene_tables: the scene does not fit 64 filter slots"); return rc; }
     if (h_nbr)
         rfrt::small_scene_neighbours(h_soup, n_triangles, h_slot_tri, *n_pairs, rfrt::SMALL_REACH_REL * (double)*extent, h_nbr, nullptr);

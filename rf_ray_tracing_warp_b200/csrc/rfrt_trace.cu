@@ -30,6 +30,7 @@ struct TraceParams {
     const float4 *normals;      // [n_tris] sorted order
     const float *small;         // small scenes: shared-memory image (rfrt_internal.h), else NULL
     int32_t small_pairs;
+    int32_t small_class[5];
     float small_extent;
     int64_t n_tris;
     // receivers
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
         const int n = (int)P.n_tris, np = P.small_pairs;
         for (int i = threadIdx.x; i < 30 * np + 17 * n; i += TRACE_THREADS) img[i] = __ldg(P.small + i);
         __syncthreads();
-        S = small_scene_view(img, np, n, P.small_extent, (float)SMALL_TAU_REL * P.small_extent,
+        S = small_scene_view(img, np, n, P.small_class, P.small_extent, (float)SMALL_TAU_REL * P.small_extent,
                              (float)(2.0 * SMALL_REACH_REL) * P.small_extent);
     }
 
@@ -732,6 +733,7 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     P.nodes = m->bvh.nodes; P.tris = m->tris; P.n_tris = m->bvh.n_prims;
     P.normals = m->normals;
     P.small = m->small; P.small_pairs = m->small_pairs; P.small_extent = m->small_extent;
+    for (int c = 0; c < 5; ++c) P.small_class[c] = m->small_class[c];
     P.rx_nodes = r ? r->bvh.nodes : nullptr; P.rx_order = r ? r->bvh.prim_order : nullptr;
     P.rx_verts = r ? r->verts : nullptr; P.rx_centers = r ? r->centers : nullptr;
     P.n_rx = r ? r->n_receivers : 0; P.n_unit = r ? r->n_unit : 0; P.n_faces = r ? r->n_faces : 0;

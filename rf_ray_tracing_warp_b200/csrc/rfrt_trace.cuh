@@ -172,6 +172,7 @@ struct SmallScene {
     const uint4 *nbr;     // [n] neighbour pair masks of triangle f: interior, boundary, interior & lower index, boundary & lower
     const int *tri_slot;  // [n] a filter slot of triangle f
     int n_pairs;
+    int cls[5];           // pair ranges of the plane classes (general, x-, y-, z-aligned)
     float extent;         // max |coordinate| of the scene
     float tau;            // self-re-hit shortcut: path-length bound
     float erode;          // ... clearance that rules out the boundary neighbours (2 * reach)
@@ -255,14 +256,61 @@ __device__ __forceinline__ unsigned pair_shift_in(const float4 *rec, float3 pos,
     return dropped;
 }
 
-// phase 1 over n_pairs records (walked backwards, so that slot s ends up at mask bit s): the candidate mask
-__device__ __forceinline__ unsigned sweep_pairs(const float4 *recs, int n_pairs, float3 pos, float3 dir, float dl, float dl_h)
+// The same filter for pairs whose plane is normal to axis K (n = +e_K exactly, so the edge normals have no K
+// component): the zero terms of pair_shift_in are left out — identical values, 32 instead of 46 instructions per pair.
+// r, kt, thr0: 1 / dir[K], dl * |r|, -dl_h * |r| (constant for the whole class).
+template <int K>
+__device__ __forceinline__ unsigned pair_shift_in_axis(const float4 *rec, float3 pos, float3 dir, float r, float kt, float thr0,
+                                                       unsigned dropped)
 {
-    unsigned dropped = 0u;
-    const float4 *rec = recs + 7 * (n_pairs - 1);
+    const float pk = K == 0 ? pos.x : (K == 1 ? pos.y : pos.z);
+    const float pi = K == 0 ? pos.y : pos.x, pj = K == 2 ? pos.y : pos.z; // the two in-plane axes, in x < y < z order
+    const float di = K == 0 ? dir.y : dir.x, dj = K == 2 ? dir.y : dir.z;
+    const float np = pk - rec[0].w;
+    const float t = -np * r;
+    const float thr = (t < -kt) ? __int_as_float(0x7f800000) : thr0;
+    const float hi = fmaf(t, di, pi), hj = fmaf(t, dj, pj);
+#pragma unroll
+    for (int j = 1; j >= 0; --j) {
+        const float4 e0 = rec[1 + 3 * j], e1 = rec[2 + 3 * j], e2 = rec[3 + 3 * j];
+        const float d0 = fmaf(K == 0 ? e0.y : e0.x, hi, fmaf(K == 2 ? e0.y : e0.z, hj, e0.w));
+        const float d1 = fmaf(K == 0 ? e1.y : e1.x, hi, fmaf(K == 2 ? e1.y : e1.z, hj, e1.w));
+        const float d2 = fmaf(K == 0 ? e2.y : e2.x, hi, fmaf(K == 2 ? e2.y : e2.z, hj, e2.w));
+        dropped = __funnelshift_l(__float_as_uint(min3f(d0, d1, d2) - thr), dropped, 1);
+    }
+    return dropped;
+}
+
+template <int K>
+__device__ __forceinline__ unsigned sweep_axis_range(const float4 *recs, int b, int e, float3 pos, float3 dir, float dl, float dl_h,
+                                                     unsigned dropped)
+{
+    if (e <= b) return dropped;
+    const float r = rcp_approx(K == 0 ? dir.x : (K == 1 ? dir.y : dir.z));
+    const float ar = fabsf(r), kt = dl * ar, thr0 = -(dl_h * ar);
+    const float4 *rec = recs + 7 * (e - 1);
 #pragma unroll 2
-    for (int k = 0; k < n_pairs; ++k, rec -= 7) dropped = pair_shift_in(rec, pos, dir, dl, dl_h, dropped);
-    return ~dropped & (n_pairs >= 16 ? 0xffffffffu : (1u << (2 * n_pairs)) - 1u);
+    for (int k = e - 1; k >= b; --k, rec -= 7) dropped = pair_shift_in_axis<K>(rec, pos, dir, r, kt, thr0, dropped);
+    return dropped;
+}
+
+// phase 1 over the pairs [first, first + count) (walked backwards, so that slot s ends up at mask bit s - 2 * first):
+// the candidate mask.  cls[0..4]: pair ranges of the plane classes general / x / y / z (rfrt_small.cu).
+__device__ __forceinline__ unsigned sweep_pairs(const float4 *recs, const int *cls, int first, int count, float3 pos, float3 dir,
+                                                float dl, float dl_h)
+{
+    const int last = first + count;
+    unsigned dropped = 0u;
+    dropped = sweep_axis_range<2>(recs, max(first, cls[3]), min(last, cls[4]), pos, dir, dl, dl_h, dropped);
+    dropped = sweep_axis_range<1>(recs, max(first, cls[2]), min(last, cls[3]), pos, dir, dl, dl_h, dropped);
+    dropped = sweep_axis_range<0>(recs, max(first, cls[1]), min(last, cls[2]), pos, dir, dl, dl_h, dropped);
+    {
+        const int b = max(first, cls[0]), e = min(last, cls[1]);
+        const float4 *rec = recs + 7 * (e - 1);
+#pragma unroll 2
+        for (int k = e - 1; k >= b; --k, rec -= 7) dropped = pair_shift_in(rec, pos, dir, dl, dl_h, dropped);
+    }
+    return ~dropped & (count >= 16 ? 0xffffffffu : (1u << (2 * count)) - 1u);
 }
 
 // per-ray constants of the exact test against the shared-memory soup
@@ -366,8 +414,8 @@ __device__ __forceinline__ void closest_hit_small(const SmallScene &S, float3 po
     const float dl = (S.extent + fabsf(pos.x) + fabsf(pos.y) + fabsf(pos.z)) * (1.0f / 65536.0f);
     const float dl_h = dl * (sqrt_approx(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z) * 1.001f);
     const int n_lo = WIDE ? 16 : S.n_pairs, n_hi = WIDE ? S.n_pairs - 16 : 0;
-    const unsigned lo = sweep_pairs(S.recs, n_lo, pos, dir, dl, dl_h);
-    const unsigned hi = WIDE ? sweep_pairs(S.recs + 7 * 16, n_hi, pos, dir, dl, dl_h) : 0u;
+    const unsigned lo = sweep_pairs(S.recs, S.cls, 0, n_lo, pos, dir, dl, dl_h);
+    const unsigned hi = WIDE ? sweep_pairs(S.recs, S.cls, 16, n_hi, pos, dir, dl, dl_h) : 0u;
     // ---- phase 2 ---------------------------------------------------------------------------------------------
     const SmallExact X = small_exact_setup(S, wr);
     if (skip >= 0) small_resolve<true>(S, lo, hi, pos, dir, dl, X, wr, skip, h);
@@ -375,9 +423,12 @@ __device__ __forceinline__ void closest_hit_small(const SmallScene &S, float3 po
 }
 
 // pointers into the small-scene image staged at `img` (layout: rfrt_internal.h)
-__device__ __forceinline__ SmallScene small_scene_view(const float *img, int n_pairs, int n_tris, float extent, float tau, float erode)
+__device__ __forceinline__ SmallScene small_scene_view(const float *img, int n_pairs, int n_tris, const int *cls, float extent,
+                                                       float tau, float erode)
 {
     SmallScene S;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) S.cls[c] = cls[c];
     S.recs = reinterpret_cast<const float4 *>(img);
     S.nbr = reinterpret_cast<const uint4 *>(img + 28 * n_pairs);
     S.slot_tri = reinterpret_cast<const int *>(img + 28 * n_pairs + 4 * n_tris);

@@ -20,9 +20,11 @@ def _tables(soup):
     slot_tri = np.zeros(64, dtype=np.int32)
     n_pairs, extent = ctypes.c_int32(), ctypes.c_float()
     nbr = np.zeros((max(soup.shape[0], 1), 4), dtype=np.uint32)
+    cls = np.zeros(5, dtype=np.int32)
     rc = lib.rfrt_small_scene_tables(soup.ctypes.data, soup.shape[0], recs.ctypes.data, slot_tri.ctypes.data,
-                                     ctypes.byref(n_pairs), ctypes.byref(extent), nbr.ctypes.data)
+                                     ctypes.byref(n_pairs), ctypes.byref(extent), nbr.ctypes.data, cls.ctypes.data)
     _tables.nbr = nbr[:soup.shape[0]]
+    _tables.class_begin = cls
     return rc, recs[:n_pairs.value], slot_tri[:2 * n_pairs.value], extent.value
 
 
@@ -80,6 +82,11 @@ def test_filter_keeps_every_oracle_hit(name, tx, repo_root):
     soup = geometry.load_stl_soup(f"{repo_root}/models/{name}.stl")
     rc, recs, slot_tri, extent = _tables(soup)
     assert rc == 0 and sorted(set(slot_tri.tolist())) == list(range(soup.reshape(-1, 9).shape[0]))
+    cls = _tables.class_begin  # both shipped scenes are all axis-aligned walls: no general-class pair
+    assert cls[0] == 0 and cls[1] == 0 and cls[4] == recs.shape[0] and np.all(np.diff(cls) >= 0)
+    for c, axis in ((1, 0), (2, 1), (3, 2)):
+        n = recs[cls[c]:cls[c + 1], :3]
+        assert np.all(n[:, axis] == 1.0) and np.all(np.delete(n, axis, axis=1) == 0.0)
     pos, dirs, face = _segments(soup, tx, 8, 200_000)
     keep = _candidates(recs, slot_tri, extent, pos, dirs)
     hit = face >= 0
