@@ -61,7 +61,6 @@ struct TraceParams {
     int32_t stack_depth;
     int32_t fetch_block; // rays a warp claims per atomic (32..256, sized so that every warp sees >= 64 blocks)
     int32_t rx_coop;   // dense receiver sets: the warp enumerates its lanes' segments together (rx_enumerate_coop)
-    int32_t short_min; // small scenes: run a self-re-hit trip when at least this many lanes stand on a surface
 };
 
 __global__ void k_gen_dirs(int64_t ray_begin, int64_t n, float4 *__restrict__ dirs)
@@ -142,6 +141,98 @@ __device__ __forceinline__ void rx_filter_and_emit(const TraceParams &P, int k, 
     if ((int64_t)slot < P.cand_capacity) P.candidates[slot] = make_uint4(gid, (uint32_t)k, (uint32_t)bounce, 0u);
 }
 
+// Receivers of one finished segment, per lane (sparse receiver sets): the segment's own box against the bounds of all
+// receivers (no division: most segments of a sparse set stop here), then this lane walks the receiver BVH with its
+// column of the shared-memory stack.
+__device__ __forceinline__ void receivers_lane(const TraceParams &P, float3 pos, float3 dir, float t_limit, uint32_t gid,
+                                               int bounce, int *stack, int stride)
+{
+    if (P.n_rx == 1) {
+        rx_filter_and_emit(P, 0, pos, dir, t_limit, gid, bounce);
+        return;
+    }
+    const float ex = fmaf(dir.x, t_limit, pos.x), ey = fmaf(dir.y, t_limit, pos.y), ez = fmaf(dir.z, t_limit, pos.z);
+    const bool near_rx = fminf(pos.x, ex) <= P.rx_hi[0] && fmaxf(pos.x, ex) >= P.rx_lo[0] &&
+                         fminf(pos.y, ey) <= P.rx_hi[1] && fmaxf(pos.y, ey) >= P.rx_lo[1] &&
+                         fminf(pos.z, ez) <= P.rx_hi[2] && fmaxf(pos.z, ez) >= P.rx_lo[2];
+    const SlabRay sr = slab_setup_fast(pos, dir);
+    int sp = 0;
+    int node = near_rx ? 0 : -1;
+    while (node >= 0) {
+        const float4 *np = reinterpret_cast<const float4 *>(P.rx_nodes + node);
+        float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+        int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
+        float tn0, tn1;
+        bool h0 = slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_limit, tn0);
+        bool h1 = slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_limit, tn1);
+        int c0 = q3.x, c1 = q3.y;
+        if (c1 == c0) h1 = false;
+        if (h0) {
+            if (c0 < 0) rx_filter_and_emit(P, __ldg(P.rx_order + (~c0)), pos, dir, t_limit, gid, bounce);
+            else { stack[sp * stride] = c0; ++sp; }
+        }
+        if (h1) {
+            if (c1 < 0) rx_filter_and_emit(P, __ldg(P.rx_order + (~c1)), pos, dir, t_limit, gid, bounce);
+            else { stack[sp * stride] = c1; ++sp; }
+        }
+        node = -1;
+        if (sp > 0) { --sp; node = stack[sp * stride]; }
+    }
+}
+
+// Dense receiver sets: the warp enumerates the receivers of its lanes' finished segments together (converged call).
+__device__ __forceinline__ void receivers_coop(const TraceParams &P, bool seg_done, float3 pos, float3 dir, float t_limit,
+                                               uint32_t gid, int bounce, int *rx_queue, int lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    // first the segment's own box against the bounds of all receivers, then the warp enumerates together
+    bool near_rx = false;
+    if (seg_done) {
+        const float ex = fmaf(dir.x, t_limit, pos.x), ey = fmaf(dir.y, t_limit, pos.y), ez = fmaf(dir.z, t_limit, pos.z);
+        near_rx = fminf(pos.x, ex) <= P.rx_hi[0] && fmaxf(pos.x, ex) >= P.rx_lo[0] &&
+                  fminf(pos.y, ey) <= P.rx_hi[1] && fmaxf(pos.y, ey) >= P.rx_lo[1] &&
+                  fminf(pos.z, ez) <= P.rx_hi[2] && fmaxf(pos.z, ez) >= P.rx_lo[2];
+    }
+    if (!__any_sync(FULL, near_rx)) return;
+    // The receivers that pass the sphere filter are staged per segment in a small shared-memory buffer and
+    // appended in runs (one global atomic per run): consecutive candidates then belong to the same ray, so
+    // the replay kernel's warps work on one ray at a time instead of a mixture of several warps' rays.
+    uint32_t gid_b = 0; int bounce_b = 0;
+    int *cbuf = rx_queue + RX_QUEUE_CAP;        // [RX_CAND_BUF] receiver ids, then the fill count
+    int *ccount = cbuf + RX_CAND_BUF;
+    if (lane == 0) *ccount = 0;
+    __syncwarp();
+    const bool ok = rx_enumerate_coop(
+        P.rx_nodes, P.rx_order, near_rx, rx_queue,
+        [&](int src, float3 &bp, float3 &bd, float &bt) {
+            bp.x = __shfl_sync(FULL, pos.x, src); bp.y = __shfl_sync(FULL, pos.y, src); bp.z = __shfl_sync(FULL, pos.z, src);
+            bd.x = __shfl_sync(FULL, dir.x, src); bd.y = __shfl_sync(FULL, dir.y, src); bd.z = __shfl_sync(FULL, dir.z, src);
+            bt = __shfl_sync(FULL, t_limit, src);
+            gid_b = __shfl_sync(FULL, gid, src);
+            bounce_b = __shfl_sync(FULL, bounce, src);
+        },
+        [&](int k, float3 bp, float3 bd, float bt) {
+            const float cx = (float)__ldg(P.rx_centers + 3 * k), cy = (float)__ldg(P.rx_centers + 3 * k + 1),
+                        cz = (float)__ldg(P.rx_centers + 3 * k + 2);
+            if (rx_sphere_filter(bp, bd, cx, cy, cz, P.rx_radius, bt)) cbuf[atomicAdd(ccount, 1)] = k;
+        },
+        [&](bool final) {
+            const int cnt = *ccount; // (every step adds at most 64 entries: the buffer never overflows)
+            if (cnt >= RX_CAND_BUF - 64 || (final && cnt > 0)) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&P.counters[RFRT_CTR_CANDIDATES], (unsigned long long)cnt);
+                base = __shfl_sync(FULL, base, 0);
+                for (int j = lane; j < cnt; j += 32)
+                    if ((int64_t)(base + j) < P.cand_capacity)
+                        P.candidates[base + j] = make_uint4(gid_b, (uint32_t)cbuf[j], (uint32_t)bounce_b, 0u);
+                __syncwarp();
+                if (lane == 0) *ccount = 0;
+                __syncwarp();
+            }
+        });
+    if (!ok && lane == 0) atomicAdd(&P.counters[RFRT_CTR_QUEUE_OVERFLOW], 1ull);
+}
+
 // LSTACK: deep trees (big meshes) keep the traversal stack in per-thread local memory (L1-cached) instead of
 // shared memory, whose depth x 1 KiB per CTA would otherwise cap the occupancy of this latency-bound case.
 __device__ __forceinline__ unsigned long long segment_hash(uint32_t gid, int bounce, int face, float t)
@@ -154,10 +245,10 @@ __device__ __forceinline__ unsigned long long segment_hash(uint32_t gid, int bou
     return z ^ (z >> 31);
 }
 
-// SMALL: 0 = BVH walk, 1 = lockstep sweep of <= 16 triangle pairs, 2 = of <= 32 pairs
+// BVH scenes.  LSTACK: see above.
 // COOP: dense receiver sets — the warp enumerates its lanes' segments together (rx_enumerate_coop) at a converged point
 //       after the closest hit; otherwise every lane handles its own receivers right where its segment is finished
-template <bool DUMP, int SMALL, bool LSTACK, bool COOP>
+template <bool DUMP, bool LSTACK, bool COOP>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P)
 {
     extern __shared__ __align__(16) int s_stack_raw[];
@@ -168,27 +259,14 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
     constexpr int STRIDE = LSTACK ? 1 : TRACE_THREADS;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    // behind the stacks: the warps' receiver-enumeration queues, then (SMALL) the scene image
-    int *s_queue_base = s_stack_raw + 2 * P.stack_depth * TRACE_THREADS;
-    // SMALL: the whole scene (filter tables + exact-test data) lives in shared memory
-    SmallScene S;
-    if (SMALL) {
-        float *img = reinterpret_cast<float *>(s_queue_base + (COOP ? RX_COOP_INTS * (TRACE_THREADS / 32) : 0));
-        const int n = (int)P.n_tris, np = P.small_pairs;
-        for (int i = threadIdx.x; i < 30 * np + 17 * n; i += TRACE_THREADS) img[i] = __ldg(P.small + i);
-        __syncthreads();
-        S = small_scene_view(img, np, n, P.small_class, P.small_extent, (float)SMALL_TAU_REL * P.small_extent,
-                             (float)(2.0 * SMALL_REACH_REL) * P.small_extent);
-    }
-
-    int *rx_queue = s_queue_base + (COOP ? RX_COOP_INTS * (threadIdx.x >> 5) : 0); // this warp's node queue (+ candidate buffer)
+    // behind the stacks: this warp's receiver-enumeration queue (+ candidate buffer)
+    int *rx_queue = s_stack_raw + 2 * P.stack_depth * TRACE_THREADS + (COOP ? RX_COOP_INTS * (threadIdx.x >> 5) : 0);
 
     bool has_ray = false;
     bool exhausted = false; // warp-uniform
     float3 pos = make_float3(0.f, 0.f, 0.f), dir = make_float3(0.f, 0.f, 1.f);
     int bounce = 0;
-    int on_face = -1; // SMALL: the triangle the ray stands on (its previous hit); -1 at the transmitter
-    bool entered = false; // BVH variants: the current segment is known to enter the scene's bounding box
+    bool entered = false; // the current segment is known to enter the scene's bounding box
     int64_t ray = 0;
     unsigned int n_seg = 0, n_hit = 0;
     unsigned long long csum = 0ull;
@@ -218,7 +296,6 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
                     dir = make_float3(d4.x, d4.y, d4.z);
                     pos = P.tx;
                     bounce = 0;
-                    on_face = -1;
                     entered = false;
                     ray = r;
                     has_ray = true;
@@ -228,165 +305,224 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
             idle = __ballot_sync(FULL, !has_ray);
         }
         if (!__any_sync(FULL, has_ray)) break;
-        // SMALL: a trip is either a self-re-hit trip (only the lanes standing on a surface work; cheap) or a full
-        // sweep (every lane with a ray).  The full sweep is always valid, so the vote is purely a scheduling choice.
-        bool shortcut = false;
-        if (SMALL) shortcut = __popc(__ballot_sync(FULL, has_ray && on_face >= 0)) >= P.short_min;
-        // BVH variants: a trip is either a box trip (the lanes whose segment has not been tested against the scene's
-        // bounding box do just that: a miss finishes the segment at once and frees the lane for the next refill) or a
-        // walk.  Without it the many rays that leave the scene immediately (half of them above an open terrain) would
-        // sit idle in warps whose other lanes walk 50 nodes (measured: 5.6 of 32 lanes active).
-        bool boxtrip = false;
-        if (!SMALL) boxtrip = __any_sync(FULL, has_ray && !entered);
+        // A trip is either a box trip (the lanes whose segment has not been tested against the scene's bounding box do
+        // just that: a miss finishes the segment at once and frees the lane for the next refill) or a walk.  Without it
+        // the many rays that leave the scene immediately (half of them above an open terrain) would sit idle in warps
+        // whose other lanes walk 50 nodes (measured: 5.6 of 32 lanes active).
+        const bool boxtrip = __any_sync(FULL, has_ray && !entered);
         // ---- one bounce iteration (kernel.py:57-98, environment branch) -----------------------
         Hit h;
         h.t = 1.0e6f; h.face = -1; h.slot = -1;
         bool seg_done = false; // this lane finished a segment in this trip (h = its closest hit)
-        if (has_ray && (SMALL ? (!shortcut || on_face >= 0) : (!boxtrip || !entered))) {
+        if (has_ray && (!boxtrip || !entered)) {
             bool resolved = true;
-            if (SMALL) {
-                const WoopRay wr = woop_setup(pos, dir);
-                if (shortcut) resolved = small_self_rehit(S, on_face, pos, dir, wr, h);
-                else closest_hit_small<SMALL == 2>(S, pos, dir, wr, h);
-                if (!resolved) on_face = -1; // not a self re-hit: this segment goes through the next full sweep
+            const SlabRay sr_env = slab_setup(pos, dir);
+            if (boxtrip) {
+                float tn;
+                entered = slab_hit(sr_env, P.env_lo[0], P.env_lo[1], P.env_lo[2], P.env_hi[0], P.env_hi[1], P.env_hi[2], 1.0e6f, tn);
+                resolved = !entered; // outside the box: a miss (h stays empty)
             } else {
-                const SlabRay sr_env = slab_setup(pos, dir);
-                if (boxtrip) {
-                    float tn;
-                    entered = slab_hit(sr_env, P.env_lo[0], P.env_lo[1], P.env_lo[2], P.env_hi[0], P.env_hi[1], P.env_hi[2], 1.0e6f, tn);
-                    resolved = !entered; // outside the box: a miss (h stays empty)
-                } else {
-                    const WoopRay wr = woop_setup(pos, dir);
-                    closest_hit(P.nodes, P.tris, P.n_tris, wr, sr_env, stack, stack_t, STRIDE, h);
-                }
+                const WoopRay wr = woop_setup(pos, dir);
+                closest_hit(P.nodes, P.tris, P.n_tris, wr, sr_env, stack, stack_t, STRIDE, h);
             }
             seg_done = resolved;
         }
 
         // ---- receivers hit strictly before the environment, or at all if it is missed (kernel.py:71,85) ----
-        if (COOP) {
-            // first the segment's own box against the bounds of all receivers, then the warp enumerates together
-            const float t_limit = h.face >= 0 ? h.t : 1.0e6f;
-            bool near_rx = false;
-            if (seg_done) {
-                const float ex = fmaf(dir.x, t_limit, pos.x), ey = fmaf(dir.y, t_limit, pos.y), ez = fmaf(dir.z, t_limit, pos.z);
-                near_rx = fminf(pos.x, ex) <= P.rx_hi[0] && fmaxf(pos.x, ex) >= P.rx_lo[0] &&
-                          fminf(pos.y, ey) <= P.rx_hi[1] && fmaxf(pos.y, ey) >= P.rx_lo[1] &&
-                          fminf(pos.z, ez) <= P.rx_hi[2] && fmaxf(pos.z, ez) >= P.rx_lo[2];
-            }
-            if (__any_sync(FULL, near_rx)) {
-                // The receivers that pass the sphere filter are staged per segment in a small shared-memory buffer and
-                // appended in runs (one global atomic per run): consecutive candidates then belong to the same ray, so
-                // the replay kernel's warps work on one ray at a time instead of a mixture of several warps' rays.
-                uint32_t gid_b = 0; int bounce_b = 0;
-                int *cbuf = rx_queue + RX_QUEUE_CAP;        // [RX_CAND_BUF] receiver ids, then the fill count
-                int *ccount = cbuf + RX_CAND_BUF;
-                if (lane == 0) *ccount = 0;
-                __syncwarp();
-                const bool ok = rx_enumerate_coop(
-                    P.rx_nodes, P.rx_order, near_rx, rx_queue,
-                    [&](int src, float3 &bp, float3 &bd, float &bt) {
-                        bp.x = __shfl_sync(FULL, pos.x, src); bp.y = __shfl_sync(FULL, pos.y, src); bp.z = __shfl_sync(FULL, pos.z, src);
-                        bd.x = __shfl_sync(FULL, dir.x, src); bd.y = __shfl_sync(FULL, dir.y, src); bd.z = __shfl_sync(FULL, dir.z, src);
-                        bt = __shfl_sync(FULL, t_limit, src);
-                        gid_b = __shfl_sync(FULL, (uint32_t)(P.chunk_begin + ray), src);
-                        bounce_b = __shfl_sync(FULL, bounce, src);
-                    },
-                    [&](int k, float3 bp, float3 bd, float bt) {
-                        const float cx = (float)__ldg(P.rx_centers + 3 * k), cy = (float)__ldg(P.rx_centers + 3 * k + 1),
-                                    cz = (float)__ldg(P.rx_centers + 3 * k + 2);
-                        if (rx_sphere_filter(bp, bd, cx, cy, cz, P.rx_radius, bt)) cbuf[atomicAdd(ccount, 1)] = k;
-                    },
-                    [&](bool final) {
-                        const int cnt = *ccount; // (every step adds at most 64 entries: the buffer never overflows)
-                        if (cnt >= RX_CAND_BUF - 64 || (final && cnt > 0)) {
-                            unsigned long long base = 0;
-                            if (lane == 0) base = atomicAdd(&P.counters[RFRT_CTR_CANDIDATES], (unsigned long long)cnt);
-                            base = __shfl_sync(FULL, base, 0);
-                            for (int j = lane; j < cnt; j += 32)
-                                if ((int64_t)(base + j) < P.cand_capacity)
-                                    P.candidates[base + j] = make_uint4(gid_b, (uint32_t)cbuf[j], (uint32_t)bounce_b, 0u);
-                            __syncwarp();
-                            if (lane == 0) *ccount = 0;
-                            __syncwarp();
-                        }
-                    });
-                if (!ok && lane == 0) atomicAdd(&P.counters[RFRT_CTR_QUEUE_OVERFLOW], 1ull);
-            }
-        }
+        if (COOP)
+            receivers_coop(P, seg_done, pos, dir, h.face >= 0 ? h.t : 1.0e6f, (uint32_t)(P.chunk_begin + ray), bounce, rx_queue, lane);
 
         if (seg_done) {
-        const bool hit_env = h.face >= 0;
-        ++n_seg;
+            const bool hit_env = h.face >= 0;
+            ++n_seg;
 
-        if (!COOP && P.n_rx > 0) {
-            const float t_limit = hit_env ? h.t : 1.0e6f;
-            const uint32_t gid = (uint32_t)(P.chunk_begin + ray);
-            if (P.n_rx == 1) {
-                rx_filter_and_emit(P, 0, pos, dir, t_limit, gid, bounce);
+            if (!COOP && P.n_rx > 0)
+                receivers_lane(P, pos, dir, hit_env ? h.t : 1.0e6f, (uint32_t)(P.chunk_begin + ray), bounce, stack, STRIDE);
+
+            if (DUMP) {
+                int64_t row = (P.chunk_begin + ray - P.dump_begin) * P.max_bounces + bounce;
+                if (P.hit_tri) P.hit_tri[row] = hit_env ? h.face : -1;
+                if (P.hit_t) P.hit_t[row] = hit_env ? h.t : 0.0f;
+                csum += segment_hash((uint32_t)(P.chunk_begin + ray), bounce, hit_env ? h.face : -1, hit_env ? h.t : 0.0f);
+            }
+
+            if (hit_env) {
+                ++n_hit;
+                pos = advance(pos, dir, h.t);                 // kernel.py:94
+                const float4 n4 = __ldg(P.normals + h.slot);  // normalize(cross(b-a, c-a)), precomputed at build time
+                dir = reflect(dir, make_float3(n4.x, n4.y, n4.z)); // kernel.py:96
+                entered = false;
+                ++bounce;
+                if (bounce >= P.max_bounces) has_ray = false;
             } else {
-                // the segment's own box against the bounds of all receivers (no division: most segments of a sparse
-                // receiver set stop here), then this lane walks the receiver BVH
-                const float ex = fmaf(dir.x, t_limit, pos.x), ey = fmaf(dir.y, t_limit, pos.y), ez = fmaf(dir.z, t_limit, pos.z);
-                const bool near_rx = fminf(pos.x, ex) <= P.rx_hi[0] && fmaxf(pos.x, ex) >= P.rx_lo[0] &&
-                                     fminf(pos.y, ey) <= P.rx_hi[1] && fmaxf(pos.y, ey) >= P.rx_lo[1] &&
-                                     fminf(pos.z, ez) <= P.rx_hi[2] && fmaxf(pos.z, ez) >= P.rx_lo[2];
-                const SlabRay sr = slab_setup_fast(pos, dir);
-                int sp = 0;
-                int node = near_rx ? 0 : -1;
-                while (node >= 0) {
-                    const float4 *np = reinterpret_cast<const float4 *>(P.rx_nodes + node);
-                    float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-                    int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
-                    float tn0, tn1;
-                    bool h0 = slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_limit, tn0);
-                    bool h1 = slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_limit, tn1);
-                    int c0 = q3.x, c1 = q3.y;
-                    if (c1 == c0) h1 = false;
-                    if (h0) {
-                        if (c0 < 0) rx_filter_and_emit(P, __ldg(P.rx_order + (~c0)), pos, dir, t_limit, gid, bounce);
-                        else { stack[sp * STRIDE] = c0; ++sp; }
-                    }
-                    if (h1) {
-                        if (c1 < 0) rx_filter_and_emit(P, __ldg(P.rx_order + (~c1)), pos, dir, t_limit, gid, bounce);
-                        else { stack[sp * STRIDE] = c1; ++sp; }
-                    }
-                    node = -1;
-                    if (sp > 0) { --sp; node = stack[sp * STRIDE]; }
-                }
+                has_ray = false; // a miss repeats forever in the reference (kernel.py:97-98): nothing more to do
             }
         }
-
-        if (DUMP) {
-            int64_t row = (P.chunk_begin + ray - P.dump_begin) * P.max_bounces + bounce;
-            if (P.hit_tri) P.hit_tri[row] = hit_env ? h.face : -1;
-            if (P.hit_t) P.hit_t[row] = hit_env ? h.t : 0.0f;
-            csum += segment_hash((uint32_t)(P.chunk_begin + ray), bounce, hit_env ? h.face : -1, hit_env ? h.t : 0.0f);
-        }
-
-        if (hit_env) {
-            ++n_hit;
-            pos = advance(pos, dir, h.t);                 // kernel.py:94
-            float3 nrm; // normalize(cross(b-a, c-a)) of the hit triangle, precomputed at build time
-            if (SMALL) {
-                const float *v = S.normals + 3 * h.face;
-                nrm = make_float3(v[0], v[1], v[2]);
-            } else {
-                float4 n4 = __ldg(P.normals + h.slot);
-                nrm = make_float3(n4.x, n4.y, n4.z);
-            }
-            dir = reflect(dir, nrm);                      // kernel.py:96
-            on_face = h.face;
-            entered = false;
-            ++bounce;
-            if (bounce >= P.max_bounces) has_ray = false;
-        } else {
-            has_ray = false; // a miss repeats forever in the reference (kernel.py:97-98): nothing more to do
-        }
-        } // seg_done
     }
 
     // warp-reduced counters
+    for (int o = 16; o > 0; o >>= 1) {
+        n_seg += __shfl_xor_sync(FULL, n_seg, o);
+        n_hit += __shfl_xor_sync(FULL, n_hit, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&P.counters[RFRT_CTR_SEGMENTS], (unsigned long long)n_seg);
+        atomicAdd(&P.counters[RFRT_CTR_ENV_HITS], (unsigned long long)n_hit);
+    }
+    if (DUMP) {
+        for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(FULL, csum, o);
+        if (lane == 0) atomicAdd(&P.counters[RFRT_CTR_CHECKSUM], csum);
+    }
+}
+
+// ---- small scenes (<= 64 filter slots): lockstep sweep, several rays per lane ------------------------------------
+// The scene image (rfrt_small.cu) lives in shared memory.  A trip of the warp is one of two kinds: a self-re-hit trip
+// (cheap: the lanes whose ray stands on a triangle test whether it hits that triangle again at t ~ 0 —
+// small_self_rehit; 3/4 of room.stl's segments) or a full sweep (closest_hit_small, ~3x the instructions).  With one
+// ray per lane a self-re-hit trip finds only about half the lanes eligible (measured 17 of 32).  So every lane owns
+// SMALL_SLOTS rays whose states live in its own column of shared memory (two 128-bit words per ray, conflict-free):
+// the trip is the kind that more lanes can take part in, and each lane contributes whichever of its rays fits
+// (28 of 32 lanes in both kinds; -10 % warp instructions, +13 % segments/s on room.stl).  The per-segment functions
+// are those of the BVH path's parity tests, so the segments are the same; only the schedule differs.
+//   word A = (pos.xyz, dir.x)   word B = (dir.y, dir.z, ray index in chunk, bounce << 8 | (triangle stood on + 1))
+//   SMALL: 1 = <= 16 triangle pairs (one 32-bit candidate mask), 2 = <= 32 pairs
+constexpr int SMALL_SLOTS = 5;       // rays per lane     (measured on room.stl: 2: 28e9, 3: 33.6e9, 4: 34.5e9, 5: 35.1e9
+constexpr int SMALL_REFILL_MIN = 16; // lanes with an empty slot that make a refill pass worth its instructions (8 / 16 / 24: 34.6 / 35.1 / 35.2e9)
+
+template <bool DUMP, int SMALL, bool COOP>
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_small(const TraceParams P)
+{
+    extern __shared__ __align__(16) int s_raw[];
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    // shared memory: ray slots | scene image | receiver stacks (one int column per thread) | cooperative queues
+    float4 *slots = reinterpret_cast<float4 *>(s_raw) + threadIdx.x; // [2 * SMALL_SLOTS][TRACE_THREADS]
+    float *img = reinterpret_cast<float *>(s_raw) + 8 * SMALL_SLOTS * TRACE_THREADS;
+    const int n = (int)P.n_tris, np = P.small_pairs;
+    const int img_floats = 30 * np + 17 * n;
+    for (int i = threadIdx.x; i < img_floats; i += TRACE_THREADS) img[i] = __ldg(P.small + i);
+    __syncthreads();
+    const SmallScene S = small_scene_view(img, np, n, P.small_class, P.small_extent, (float)SMALL_TAU_REL * P.small_extent,
+                                          (float)(2.0 * SMALL_REACH_REL) * P.small_extent);
+    int *stack = reinterpret_cast<int *>(img + img_floats) + threadIdx.x;
+    int *rx_queue = reinterpret_cast<int *>(img + img_floats) + P.stack_depth * TRACE_THREADS + (COOP ? RX_COOP_INTS * (threadIdx.x >> 5) : 0);
+
+    unsigned valid = 0u;  // bit k: slot k holds a ray
+    unsigned onface = 0u; // bit k: that ray stands on a triangle and has not failed the self-re-hit test there
+    bool exhausted = false; // warp-uniform
+    unsigned int n_seg = 0, n_hit = 0;
+    unsigned long long csum = 0ull;
+    const int FETCH_BLOCK = P.fetch_block;
+    uint32_t blk_next = 0u; // warp-uniform: next ray of the warp's block (index in the chunk) and how many are left
+    int blk_left = 0;
+    constexpr unsigned ALL_SLOTS = (1u << SMALL_SLOTS) - 1u;
+
+    for (;;) {
+        // ---- refill: one empty slot per lane and trip (rays are handed out in blocks per warp: one atomic per block;
+        //      second pass: the block ran out in the middle of the refill) ----
+        {
+            const int ke = __ffs((int)(~valid & ALL_SLOTS)) - 1; // -1: no empty slot
+            unsigned idle = __ballot_sync(FULL, ke >= 0);
+            bool filled = false;
+            // (with several slots per lane a few empty ones can wait: refill when it pays for the pass)
+#pragma unroll 1
+            for (int pass = 0; pass < 2 && __popc(idle) >= (pass == 0 ? SMALL_REFILL_MIN : 1) && !exhausted; ++pass) {
+                if (blk_left == 0) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(&P.counters[RFRT_CTR_NEXT_RAY], (unsigned long long)FETCH_BLOCK);
+                    base = __shfl_sync(FULL, base, 0);
+                    if ((int64_t)base >= P.chunk_n) {
+                        exhausted = true;
+                    } else {
+                        blk_next = (uint32_t)base;
+                        blk_left = P.chunk_n - (int64_t)base < FETCH_BLOCK ? (int)(P.chunk_n - (int64_t)base) : FETCH_BLOCK;
+                    }
+                }
+                const int rank = __popc(idle & ((1u << lane) - 1u));
+                if (ke >= 0 && !filled && rank < blk_left) {
+                    const uint32_t r = blk_next + (uint32_t)rank;
+                    const float4 d4 = __ldg(P.dirs + r);
+                    slots[(2 * ke) * TRACE_THREADS] = make_float4(P.tx.x, P.tx.y, P.tx.z, d4.x);
+                    slots[(2 * ke + 1) * TRACE_THREADS] = make_float4(d4.y, d4.z, __uint_as_float(r), __int_as_float(0));
+                    valid |= 1u << ke;
+                    filled = true;
+                }
+                const int took = __popc(idle) < blk_left ? __popc(idle) : blk_left;
+                blk_next += (uint32_t)took;
+                blk_left -= took;
+                idle = __ballot_sync(FULL, ke >= 0 && !filled);
+            }
+        }
+        if (!__any_sync(FULL, valid != 0u)) break;
+
+        // ---- pick the trip: the kind that more lanes can take part in (a full sweep is always valid) ----
+        const unsigned wants_sweep = valid & ~onface;
+        const int n_r = __popc(__ballot_sync(FULL, onface != 0u));
+        const int n_s = __popc(__ballot_sync(FULL, wants_sweep != 0u));
+        const bool shortcut = n_r > 0 && n_r >= n_s; // (a bias of +-2..4 lanes either way: no difference)
+        const unsigned pick = shortcut ? onface : wants_sweep;
+        const bool act = pick != 0u;
+        const int k = __ffs((int)pick) - 1;
+
+        float3 pos = make_float3(0.f, 0.f, 0.f), dir = make_float3(0.f, 0.f, 1.f);
+        Hit h;
+        h.t = 1.0e6f; h.face = -1; h.slot = -1;
+        bool seg_done = false;
+        if (act) {
+            const float4 A = slots[(2 * k) * TRACE_THREADS], B = slots[(2 * k + 1) * TRACE_THREADS];
+            pos = make_float3(A.x, A.y, A.z);
+            dir = make_float3(A.w, B.x, B.y);
+            const WoopRay wr = woop_setup(pos, dir);
+            bool resolved = true;
+            if (shortcut) resolved = small_self_rehit(S, (__float_as_int(B.w) & 0xff) - 1, pos, dir, wr, h);
+            else closest_hit_small<SMALL == 2>(S, pos, dir, wr, h);
+            if (!resolved) onface &= ~(1u << k); // not a self re-hit: this segment goes through a full sweep
+            seg_done = resolved;
+        }
+        // (ray id and bounce are read back from the slot only now: they need not live through the sweep)
+        uint32_t ray = 0u;
+        int bounce = 0;
+        if (seg_done) {
+            const float4 B = slots[(2 * k + 1) * TRACE_THREADS];
+            ray = __float_as_uint(B.z);
+            bounce = __float_as_int(B.w) >> 8;
+        }
+
+        // ---- receivers hit strictly before the environment, or at all if it is missed (kernel.py:71,85) ----
+        const float t_limit = h.face >= 0 ? h.t : 1.0e6f;
+        const uint32_t gid = (uint32_t)(P.chunk_begin + ray);
+        if (COOP) receivers_coop(P, seg_done, pos, dir, t_limit, gid, bounce, rx_queue, lane);
+
+        if (seg_done) {
+            const bool hit_env = h.face >= 0;
+            ++n_seg;
+            if (!COOP && P.n_rx > 0) receivers_lane(P, pos, dir, t_limit, gid, bounce, stack, TRACE_THREADS);
+            if (DUMP) {
+                int64_t row = (P.chunk_begin + ray - P.dump_begin) * P.max_bounces + bounce;
+                if (P.hit_tri) P.hit_tri[row] = hit_env ? h.face : -1;
+                if (P.hit_t) P.hit_t[row] = hit_env ? h.t : 0.0f;
+                csum += segment_hash(gid, bounce, hit_env ? h.face : -1, hit_env ? h.t : 0.0f);
+            }
+            bool alive = false;
+            if (hit_env) {
+                ++n_hit;
+                pos = advance(pos, dir, h.t);                 // kernel.py:94
+                const float *v = S.normals + 3 * h.face;
+                dir = reflect(dir, make_float3(v[0], v[1], v[2])); // kernel.py:96
+                ++bounce;
+                alive = bounce < P.max_bounces;
+            } // (a miss repeats forever in the reference, kernel.py:97-98: nothing more to do)
+            if (alive) {
+                slots[(2 * k) * TRACE_THREADS] = make_float4(pos.x, pos.y, pos.z, dir.x);
+                slots[(2 * k + 1) * TRACE_THREADS] = make_float4(dir.y, dir.z, __uint_as_float(ray), __int_as_float((bounce << 8) | (h.face + 1)));
+                onface |= 1u << k;
+            } else {
+                valid &= ~(1u << k);
+                onface &= ~(1u << k);
+            }
+        }
+    }
+
     for (int o = 16; o > 0; o >>= 1) {
         n_seg += __shfl_xor_sync(FULL, n_seg, o);
         n_hit += __shfl_xor_sync(FULL, n_hit, o);
@@ -670,12 +806,15 @@ int stack_depth_for(const Mesh *m, const RxSet *r)
 
 size_t stack_bytes(int depth) { return (size_t)depth * TRACE_THREADS * 2 * sizeof(int); }
 
-int grid_for(const void *kernel, size_t smem, int *out_grid)
+// all_smem: the kernel keeps its whole working set in shared memory (small scenes) — ask for the largest carve-out, so
+// that the resident CTAs per SM are what the occupancy query below says and not what the driver's L1/shared split leaves
+int grid_for(const void *kernel, size_t smem, int *out_grid, bool all_smem = false)
 {
     int dev = 0, sms = 0, per_sm = 0;
     RFRT_CUDA(cudaGetDevice(&dev));
     RFRT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (smem > 48 * 1024) RFRT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (all_smem) RFRT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     RFRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRACE_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     *out_grid = sms * per_sm;
@@ -764,7 +903,6 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
         P.rx_coop = (double)r->n_receivers * d2 >= 8.0 * (face > d2 ? face : d2) ? 1 : 0;
     }
     P.stack_depth = stack_depth_for(m, P.rx_coop ? nullptr : r);
-    P.short_min = 8; // measured flat between 4 and 16 on room.stl (profiles/README.md)
     // DUMP instantiations also accumulate the checksum
     const bool dump = d_hit_tri || d_hit_t || (flags & RFRT_FLAG_CHECKSUM);
     // small scenes: lockstep sweep over the scene staged in shared memory (see closest_hit_small)
@@ -773,23 +911,30 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     const bool lstack = !small && P.stack_depth > 16; // deep tree: local-memory stack (<= 64 entries by construction)
     if (lstack && P.stack_depth > 64) { set_error("rfrt_trace: BVH deeper than 64 levels"); return RFRT_ERR_INVALID; }
     if (lstack) P.stack_depth = 0;
-    const size_t smem = stack_bytes(P.stack_depth) + (P.rx_coop ? sizeof(int) * RX_COOP_INTS * (TRACE_THREADS / 32) : 0) +
-                        (small ? sizeof(float) * small_image_floats(m->small_pairs, (int)P.n_tris) : 0);
+    size_t smem = stack_bytes(P.stack_depth) + (P.rx_coop ? sizeof(int) * RX_COOP_INTS * (TRACE_THREADS / 32) : 0);
     typedef void (*kern_t)(const TraceParams);
-    const int variant = small ? (m->small_pairs > 16 ? 2 : 1) : (lstack ? 3 : 0);
-    static const kern_t kerns[2][4][2] = {
-        {{k_trace_env<false, 0, false, false>, k_trace_env<true, 0, false, false>},
-         {k_trace_env<false, 1, false, false>, k_trace_env<true, 1, false, false>},
-         {k_trace_env<false, 2, false, false>, k_trace_env<true, 2, false, false>},
-         {k_trace_env<false, 0, true, false>, k_trace_env<true, 0, true, false>}},
-        {{k_trace_env<false, 0, false, true>, k_trace_env<true, 0, false, true>},
-         {k_trace_env<false, 1, false, true>, k_trace_env<true, 1, false, true>},
-         {k_trace_env<false, 2, false, true>, k_trace_env<true, 2, false, true>},
-         {k_trace_env<false, 0, true, true>, k_trace_env<true, 0, true, true>}},
-    };
-    const kern_t kern = kerns[P.rx_coop ? 1 : 0][variant][dump ? 1 : 0];
+    kern_t kern;
+    if (small) {
+        // several rays per lane: ray slots | scene image | one int column per thread for the receiver walk | queues
+        if (max_bounces >= (1 << 23)) { set_error("rfrt_trace: max_bounces too large"); return RFRT_ERR_INVALID; }
+        smem = sizeof(float4) * 2 * SMALL_SLOTS * TRACE_THREADS + sizeof(float) * small_image_floats(m->small_pairs, (int)P.n_tris) +
+               sizeof(int) * P.stack_depth * TRACE_THREADS + (P.rx_coop ? sizeof(int) * RX_COOP_INTS * (TRACE_THREADS / 32) : 0);
+        static const kern_t small_kerns[2][2][2] = {
+            {{k_trace_small<false, 1, false>, k_trace_small<true, 1, false>}, {k_trace_small<false, 2, false>, k_trace_small<true, 2, false>}},
+            {{k_trace_small<false, 1, true>, k_trace_small<true, 1, true>}, {k_trace_small<false, 2, true>, k_trace_small<true, 2, true>}},
+        };
+        kern = small_kerns[P.rx_coop ? 1 : 0][m->small_pairs > 16 ? 1 : 0][dump ? 1 : 0];
+    } else {
+        static const kern_t kerns[2][2][2] = {
+            {{k_trace_env<false, false, false>, k_trace_env<true, false, false>},
+             {k_trace_env<false, true, false>, k_trace_env<true, true, false>}},
+            {{k_trace_env<false, false, true>, k_trace_env<true, false, true>},
+             {k_trace_env<false, true, true>, k_trace_env<true, true, true>}},
+        };
+        kern = kerns[P.rx_coop ? 1 : 0][lstack ? 1 : 0][dump ? 1 : 0];
+    }
     int grid = 0;
-    int rc = grid_for((const void *)kern, smem, &grid);
+    int rc = grid_for((const void *)kern, smem, &grid, small);
     if (rc) return rc;
     // (the face table in __constant__ memory is only read by the replay / compat kernels)
 
