@@ -316,7 +316,7 @@ def main():
         traffic, issue_pct = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-                ncu = json.load(f).get("k_trace_env", {})
+                ncu = json.load(f).get("k_trace_small", {})
                 traffic, issue_pct = ncu.get("dram_bytes_per_launch"), ncu.get("issue_active_pct")
             if traffic is not None:
                 traffic = int(traffic * R / (1 << 28))  # captured at 2^28 rays; it is the direction buffer, linear in rays
@@ -330,14 +330,14 @@ def main():
                            "l2": "256 MiB flush between timed steps; the 4 GiB direction buffer streamed by every step exceeds the 126 MB L2",
                            "parallelism": f"ray-range sharding x{world}, BVH replicated, sparse record all-gather"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "kernel": "k_trace_env", "kernel_ms": k_ms, "peak_source": peak_src,
+                             "traffic": traffic, "kernel": "k_trace_small", "kernel_ms": k_ms, "peak_source": peak_src,
                              "algorithmic_bytes_per_segment": BYTES_PER_SEGMENT,
                              "note": "the 44-triangle scene is resident in shared memory: HBM traffic is only the direction "
                                      "buffer, the binding limit is instruction issue (profiles/README.md), so frac can exceed 1",
                              "traffic_note": "ncu dram__bytes_read+write per launch at 268435456 rays (profiles/ncu_summary.json)",
                              "issue_active_pct": issue_pct},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches * 1,
-                "kernel_ms": {"k_gen_dirs": g_ms, "k_trace_env": k_ms, "step": total_ms / args.steps}}
+                "kernel_ms": {"k_gen_dirs": g_ms, "k_trace_small": k_ms, "step": total_ms / args.steps}}
         if args.cpu_sample > 0:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
         print(json.dumps(line), flush=True)
