@@ -143,6 +143,7 @@ RFRT_API int rfrt_ray_directions(int64_t ray_begin, int64_t ray_end, float *d_di
  * that hits receiver k before the environment appends the candidate (ray id, k, bounce); candidates
  * are later replayed literally by rfrt_trace_receive (which drops repeats of a (ray, k) pair).  No N x (B+1) array is ever materialised.
  *   h_tx_pos        : 3 floats (host)
+ *   max_bounces     : bounce iterations per ray (kernel.py:57), 0 <= max_bounces < 2^23
  *   d_dir_scratch   : [min(chunk, n)*4] float32 workspace (directions of the chunk in flight)
  *   chunk_rays      : rays generated per wave (0 = default 2^24)
  *   d_counters      : [RFRT_CTR_COUNT] uint64, zeroed by the CALLER before the first call of a job;

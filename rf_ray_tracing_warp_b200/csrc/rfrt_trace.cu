@@ -1,10 +1,13 @@
 // rfrt_trace.cu — the trace kernels (sm_100a) and their C-ABI launchers.
 //
 //   k_gen_dirs      kernel.py:51-52  directions of a chunk of rays (fp64 deterministic math, no divergence)
-//   k_trace_env     kernel.py:57-98  persistent wavefront kernel: every lane owns one ray, runs one bounce
-//                                    iteration per loop trip and is refilled with a fresh ray (warp-
-//                                    aggregated fetch: ballot + popc + one atomic per warp) as soon as its
-//                                    ray misses the environment or exhausts its bounces
+//   k_trace_small   kernel.py:57-98  scenes of <= 64 filter slots, staged in shared memory: persistent kernel, every
+//                                    lane owns several rays and runs one bounce iteration of one of them per loop
+//                                    trip (lockstep sweep or self-re-hit test, whichever more lanes can join)
+//   k_trace_env     kernel.py:57-98  BVH scenes: persistent kernel, every lane owns one ray, runs one bounce
+//                                    iteration per loop trip and is refilled with a fresh ray (warp-aggregated
+//                                    fetch: ballot + popc + one atomic per block of rays) as soon as its ray
+//                                    misses the environment or exhausts its bounces
 //   k_trace_receive kernel.py:38-98  literal replay for the rare (ray, receiver) candidates + the per-path
 //                                    post-processing of tracer.py:102-115
 //   k_trace_compat  kernel.py:38-98  the reference kernel's dense contract (tracer.py:75-79)
@@ -859,8 +862,8 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
         if (!d_candidates || cand_capacity <= 0) { set_error("rfrt_trace: candidate buffer required with receivers"); return RFRT_ERR_INVALID; }
     }
     int64_t n = ray_end - ray_begin;
-    if (!h_tx_pos || !d_counters || max_bounces < 0 || n < 0 || ray_end > (1ll << 32) || ray_begin < 0) {
-        set_error("rfrt_trace: bad arguments (need tx_pos, counters, 0 <= ray ids <= 2^32)");
+    if (!h_tx_pos || !d_counters || max_bounces < 0 || max_bounces >= (1 << 23) || n < 0 || ray_end > (1ll << 32) || ray_begin < 0) {
+        set_error("rfrt_trace: bad arguments (need tx_pos, counters, 0 <= ray ids <= 2^32, max_bounces < 2^23)");
         return RFRT_ERR_INVALID;
     }
     if (n == 0 || max_bounces == 0) return RFRT_OK;
@@ -916,7 +919,6 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     kern_t kern;
     if (small) {
         // several rays per lane: ray slots | scene image | one int column per thread for the receiver walk | queues
-        if (max_bounces >= (1 << 23)) { set_error("rfrt_trace: max_bounces too large"); return RFRT_ERR_INVALID; }
         smem = sizeof(float4) * 2 * SMALL_SLOTS * TRACE_THREADS + sizeof(float) * small_image_floats(m->small_pairs, (int)P.n_tris) +
                sizeof(int) * P.stack_depth * TRACE_THREADS + (P.rx_coop ? sizeof(int) * RX_COOP_INTS * (TRACE_THREADS / 32) : 0);
         static const kern_t small_kerns[2][2][2] = {
