@@ -89,6 +89,39 @@ __global__ void k_rx_vertices(const double *__restrict__ centers, int64_t n_rx, 
     hi[k] = make_float4(h[0], h[1], h[2], 0.f);
 }
 
+// Device memory of a mesh / receiver set (also the clean-up of a half-built one: every pointer starts as NULL)
+void release_mesh(Mesh *m)
+{
+    free_bvh(&m->bvh);
+    if (m->tris) cudaFree(m->tris);
+    if (m->soup) cudaFree(m->soup);
+    if (m->normals) cudaFree(m->normals);
+    if (m->face_normals) cudaFree(m->face_normals);
+    if (m->small) cudaFree(m->small);
+    if (m->materials) cudaFree(m->materials);
+    if (m->ray_keys[0]) cudaFree(m->ray_keys[0]);
+    if (m->ray_keys[1]) cudaFree(m->ray_keys[1]);
+    if (m->ray_hist) cudaFree(m->ray_hist);
+    *m = Mesh();
+}
+
+void release_rxset(RxSet *r)
+{
+    free_bvh(&r->bvh);
+    free_bvh(&r->unit_bvh);
+    if (r->verts) cudaFreeAsync(r->verts, 0);
+    if (r->centers) cudaFreeAsync(r->centers, 0);
+    if (r->unit_recs) cudaFreeAsync(r->unit_recs, 0);
+    r->verts = nullptr; r->centers = nullptr; r->unit_recs = nullptr;
+}
+
+struct MeshDeleter {
+    void operator()(Mesh *m) const { release_mesh(m); delete m; }
+};
+struct RxSetDeleter {
+    void operator()(RxSet *r) const { release_rxset(r); delete r; }
+};
+
 } // namespace
 
 Mesh *get_mesh(rfrt_handle h)
@@ -136,18 +169,24 @@ extern "C" int rfrt_mesh_create(const float *d_vertices_xyz, int64_t n_vertices,
         set_error("rfrt_mesh_create: bad arguments");
         return RFRT_ERR_INVALID;
     }
-    std::unique_ptr<Mesh> m(new Mesh());
+    std::unique_ptr<Mesh, MeshDeleter> m(new Mesh());
+    Temporaries tmp;
     cudaEvent_t e0, e1;
     RFRT_CUDA(cudaEventCreate(&e0));
+    tmp.events.push_back(e0);
     RFRT_CUDA(cudaEventCreate(&e1));
+    tmp.events.push_back(e1);
     RFRT_CUDA(cudaEventRecord(e0, stream));
     if (n_triangles > 0) {
         float4 *lo = nullptr, *hi = nullptr;
         int *bad = nullptr;
         RFRT_CUDA(cudaMalloc(&m->soup, sizeof(float) * 9 * n_triangles));
         RFRT_CUDA(cudaMalloc(&lo, sizeof(float4) * n_triangles));
+        tmp.sync_ptrs.push_back(lo);
         RFRT_CUDA(cudaMalloc(&hi, sizeof(float4) * n_triangles));
+        tmp.sync_ptrs.push_back(hi);
         RFRT_CUDA(cudaMalloc(&bad, sizeof(int)));
+        tmp.sync_ptrs.push_back(bad);
         RFRT_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), stream));
         const int T = 256;
         const unsigned nb = (unsigned)((n_triangles + T - 1) / T);
@@ -156,12 +195,11 @@ extern "C" int rfrt_mesh_create(const float *d_vertices_xyz, int64_t n_vertices,
         RFRT_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
         RFRT_CUDA(cudaStreamSynchronize(stream));
         if (h_bad) {
-            cudaFree(lo); cudaFree(hi); cudaFree(bad); cudaFree(m->soup);
             set_error("rfrt_mesh_create: face index out of range");
             return RFRT_ERR_INVALID;
         }
         int rc = build_lbvh(lo, hi, n_triangles, stream, &m->bvh);
-        if (rc) { cudaFree(lo); cudaFree(hi); cudaFree(bad); cudaFree(m->soup); return rc; }
+        if (rc) return rc;
         RFRT_CUDA(cudaMalloc(&m->tris, sizeof(BvhTri) * n_triangles));
         RFRT_CUDA(cudaMalloc(&m->normals, sizeof(float4) * n_triangles));
         RFRT_CUDA(cudaMalloc(&m->face_normals, sizeof(float) * 3 * n_triangles));
@@ -170,7 +208,6 @@ extern "C" int rfrt_mesh_create(const float *d_vertices_xyz, int64_t n_vertices,
         RFRT_CUDA(cudaEventRecord(e1, stream));
         RFRT_CUDA(cudaStreamSynchronize(stream));
         RFRT_CUDA(cudaEventElapsedTime(&m->build_ms, e0, e1));
-        cudaFree(lo); cudaFree(hi); cudaFree(bad);
         if (n_triangles <= RFRT_SMALL_MAX_TRIS) {
             // small scene: the shared-memory image of the lockstep sweep (candidate-filter tables + exact-test data)
             const int n = (int)n_triangles;
@@ -198,8 +235,6 @@ extern "C" int rfrt_mesh_create(const float *d_vertices_xyz, int64_t n_vertices,
             } // else: too many distinct planes for 64 slots -> BVH path
         }
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     std::lock_guard<std::mutex> lock(g_mutex);
     rfrt_handle h = g_next_handle++;
     g_meshes[h] = m.release();
@@ -217,16 +252,7 @@ extern "C" int rfrt_mesh_destroy(rfrt_handle mesh)
         m = it->second;
         g_meshes.erase(it);
     }
-    free_bvh(&m->bvh);
-    if (m->tris) cudaFree(m->tris);
-    if (m->soup) cudaFree(m->soup);
-    if (m->normals) cudaFree(m->normals);
-    if (m->face_normals) cudaFree(m->face_normals);
-    if (m->small) cudaFree(m->small);
-    if (m->materials) cudaFree(m->materials);
-    if (m->ray_keys[0]) cudaFree(m->ray_keys[0]);
-    if (m->ray_keys[1]) cudaFree(m->ray_keys[1]);
-    if (m->ray_hist) cudaFree(m->ray_hist);
+    release_mesh(m);
     delete m;
     return RFRT_OK;
 }
@@ -286,7 +312,8 @@ extern "C" int rfrt_rxset_create(const double *d_centers_xyz, int64_t n_receiver
         return RFRT_ERR_INVALID;
     }
     keep_pool_memory();
-    std::unique_ptr<RxSet> r(new RxSet());
+    std::unique_ptr<RxSet, RxSetDeleter> r(new RxSet());
+    Temporaries tmp;
     r->n_receivers = n_receivers; r->n_unit = n_unit_vertices; r->n_faces = n_faces; r->radius = radius;
     for (int i = 0; i < 3 * n_faces; ++i) {
         if (h_faces[i] < 0 || h_faces[i] >= n_unit_vertices) { set_error("rfrt_rxset_create: face index out of range"); return RFRT_ERR_INVALID; }
@@ -295,10 +322,13 @@ extern "C" int rfrt_rxset_create(const double *d_centers_xyz, int64_t n_receiver
     double *d_unit = nullptr;
     float4 *lo = nullptr, *hi = nullptr;
     RFRT_CUDA(cudaMallocAsync(&d_unit, sizeof(double) * 3 * n_unit_vertices, stream));
+    tmp.async_ptrs.push_back({d_unit, stream});
     RFRT_CUDA(cudaMallocAsync(&r->centers, sizeof(double) * 3 * n_receivers, stream));
     RFRT_CUDA(cudaMallocAsync(&r->verts, sizeof(float) * 3 * n_unit_vertices * n_receivers, stream));
     RFRT_CUDA(cudaMallocAsync(&lo, sizeof(float4) * n_receivers, stream));
+    tmp.async_ptrs.push_back({lo, stream});
     RFRT_CUDA(cudaMallocAsync(&hi, sizeof(float4) * n_receivers, stream));
+    tmp.async_ptrs.push_back({hi, stream});
     RFRT_CUDA(cudaMemcpyAsync(d_unit, h_unit_vertices, sizeof(double) * 3 * n_unit_vertices, cudaMemcpyHostToDevice, stream));
     RFRT_CUDA(cudaMemcpyAsync(r->centers, d_centers_xyz, sizeof(double) * 3 * n_receivers, cudaMemcpyDeviceToDevice, stream));
     const int T = 128;
@@ -306,8 +336,7 @@ extern "C" int rfrt_rxset_create(const double *d_centers_xyz, int64_t n_receiver
                                                                            n_unit_vertices, r->verts, lo, hi);
     RFRT_CUDA(cudaGetLastError());
     int rc = build_lbvh(lo, hi, n_receivers, stream, &r->bvh);
-    cudaFreeAsync(d_unit, stream); cudaFreeAsync(lo, stream); cudaFreeAsync(hi, stream);
-    if (rc) { cudaFreeAsync(r->centers, stream); cudaFreeAsync(r->verts, stream); return rc; }
+    if (rc) return rc;
     {
         // BVH over the unit icosphere's faces, used (after mapping the ray into unit space) to prune the exact
         // per-receiver triangle tests.  Boxes are inflated: the mapping (o - c) / r is only approximate in fp32.
@@ -325,12 +354,13 @@ extern "C" int rfrt_rxset_create(const double *d_centers_xyz, int64_t n_receiver
         }
         float4 *dlo = nullptr, *dhi = nullptr;
         RFRT_CUDA(cudaMallocAsync(&dlo, sizeof(float4) * n_faces, stream));
+        tmp.async_ptrs.push_back({dlo, stream});
         RFRT_CUDA(cudaMallocAsync(&dhi, sizeof(float4) * n_faces, stream));
+        tmp.async_ptrs.push_back({dhi, stream});
         RFRT_CUDA(cudaMemcpyAsync(dlo, ulo.data(), sizeof(float4) * n_faces, cudaMemcpyHostToDevice, stream));
         RFRT_CUDA(cudaMemcpyAsync(dhi, uhi.data(), sizeof(float4) * n_faces, cudaMemcpyHostToDevice, stream));
         rc = build_lbvh(dlo, dhi, n_faces, stream, &r->unit_bvh); // synchronises the stream
-        cudaFreeAsync(dlo, stream); cudaFreeAsync(dhi, stream);
-        if (rc) { cudaFreeAsync(r->centers, stream); cudaFreeAsync(r->verts, stream); free_bvh(&r->bvh); return rc; }
+        if (rc) return rc;
     }
     {
         std::vector<float> recs(16 * (size_t)n_faces);
@@ -356,11 +386,7 @@ extern "C" int rfrt_rxset_destroy(rfrt_handle rxset)
         r = it->second;
         g_rxsets.erase(it);
     }
-    free_bvh(&r->bvh);
-    free_bvh(&r->unit_bvh);
-    if (r->verts) cudaFreeAsync(r->verts, 0);
-    if (r->centers) cudaFreeAsync(r->centers, 0);
-    if (r->unit_recs) cudaFreeAsync(r->unit_recs, 0);
+    release_rxset(r);
     delete r;
     return RFRT_OK;
 }

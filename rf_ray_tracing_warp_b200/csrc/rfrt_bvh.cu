@@ -362,16 +362,17 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
     int2 *children = nullptr;
     const int64_t n_nodes = n > 1 ? n - 1 : 1;
 
-    RFRT_CUDA(cudaMallocAsync(&keys_a, sizeof(uint64_t) * n, stream));
-    RFRT_CUDA(cudaMallocAsync(&keys_b, sizeof(uint64_t) * n, stream));
-    RFRT_CUDA(cudaMallocAsync(&ghist, sizeof(uint32_t) * 256 * ((size_t)nblocks + 1), stream));
-    RFRT_CUDA(cudaMallocAsync(&bounds_enc, sizeof(int) * 8, stream));
-    RFRT_CUDA(cudaMallocAsync(&d_bounds, sizeof(float) * 8, stream));
-    RFRT_CUDA(cudaMallocAsync(&node_parent, sizeof(int) * n_nodes, stream));
-    RFRT_CUDA(cudaMallocAsync(&leaf_parent, sizeof(int) * n, stream));
-    RFRT_CUDA(cudaMallocAsync(&arrive, sizeof(int) * n_nodes, stream));
-    RFRT_CUDA(cudaMallocAsync(&children, sizeof(int2) * n_nodes, stream));
-    RFRT_CUDA(cudaMallocAsync(&d_depth, sizeof(int), stream));
+    Temporaries tmp; // (out->nodes / out->prim_order belong to the caller's Bvh: free_bvh)
+    RFRT_CUDA(tmp.alloc_async(&keys_a, sizeof(uint64_t) * n, stream));
+    RFRT_CUDA(tmp.alloc_async(&keys_b, sizeof(uint64_t) * n, stream));
+    RFRT_CUDA(tmp.alloc_async(&ghist, sizeof(uint32_t) * 256 * ((size_t)nblocks + 1), stream));
+    RFRT_CUDA(tmp.alloc_async(&bounds_enc, sizeof(int) * 8, stream));
+    RFRT_CUDA(tmp.alloc_async(&d_bounds, sizeof(float) * 8, stream));
+    RFRT_CUDA(tmp.alloc_async(&node_parent, sizeof(int) * n_nodes, stream));
+    RFRT_CUDA(tmp.alloc_async(&leaf_parent, sizeof(int) * n, stream));
+    RFRT_CUDA(tmp.alloc_async(&arrive, sizeof(int) * n_nodes, stream));
+    RFRT_CUDA(tmp.alloc_async(&children, sizeof(int2) * n_nodes, stream));
+    RFRT_CUDA(tmp.alloc_async(&d_depth, sizeof(int), stream));
     RFRT_CUDA(cudaMallocAsync(&out->nodes, sizeof(BvhNode) * n_nodes, stream));
     RFRT_CUDA(cudaMallocAsync(&out->prim_order, sizeof(int32_t) * n, stream));
 
@@ -414,8 +415,6 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
     RFRT_CUDA(cudaStreamSynchronize(stream));
     RFRT_CUDA(cudaGetLastError());
 
-    cudaFreeAsync(keys_a, stream); cudaFreeAsync(keys_b, stream); cudaFreeAsync(ghist, stream); cudaFreeAsync(bounds_enc, stream); cudaFreeAsync(d_bounds, stream);
-    cudaFreeAsync(node_parent, stream); cudaFreeAsync(leaf_parent, stream); cudaFreeAsync(arrive, stream); cudaFreeAsync(children, stream); cudaFreeAsync(d_depth, stream);
     return RFRT_OK;
 }
 

@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/rfrt.h"
 
@@ -78,6 +80,29 @@ int cuda_fail(cudaError_t e, const char *what);
         cudaError_t _e = (call);                                         \
         if (_e != cudaSuccess) return ::rfrt::cuda_fail(_e, #call);      \
     } while (0)
+
+// Device temporaries of a constructor: released when the scope ends, on success and on every early error return alike.
+struct Temporaries {
+    std::vector<void *> sync_ptrs;                           // from cudaMalloc
+    std::vector<std::pair<void *, cudaStream_t>> async_ptrs; // from cudaMallocAsync (freed in stream order)
+    std::vector<cudaEvent_t> events;
+    Temporaries() = default;
+    Temporaries(const Temporaries &) = delete;
+    Temporaries &operator=(const Temporaries &) = delete;
+    ~Temporaries()
+    {
+        for (void *q : sync_ptrs) cudaFree(q);
+        for (auto &q : async_ptrs) cudaFreeAsync(q.first, q.second);
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+    }
+    template <class T>
+    cudaError_t alloc_async(T **p, size_t bytes, cudaStream_t stream)
+    {
+        cudaError_t e = cudaMallocAsync(p, bytes, stream);
+        if (e == cudaSuccess) async_ptrs.push_back({*p, stream});
+        return e;
+    }
+};
 
 // Builds a BVH over n axis-aligned boxes (device arrays lo/hi as float4 per primitive, w ignored).
 // Allocates bvh.nodes / bvh.prim_order.  Synchronises the stream.
