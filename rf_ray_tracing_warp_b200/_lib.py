@@ -20,7 +20,7 @@ c_d = ctypes.c_double
 
 CTR_SEGMENTS, CTR_CANDIDATES, CTR_RECORDS, CTR_ENV_HITS, CTR_NEXT_RAY, CTR_NEXT_CAND, CTR_CHECKSUM, CTR_QUEUE_OVERFLOW, CTR_COUNT = \
     0, 1, 2, 3, 4, 5, 6, 7, 8
-FLAG_DIRS_READY, FLAG_FORCE_BVH, FLAG_CHECKSUM = 1, 2, 8
+FLAG_NONE, FLAG_DIRS_READY, FLAG_FORCE_BVH, FLAG_CHECKSUM, FLAG_NO_RAY_SORT = 0, 1, 2, 8, 16
 SMALL_MAX_TRIS = 64
 
 # name -> (restype, argtypes); mirrors include/rfrt.h one to one

@@ -38,6 +38,16 @@ def test_binding_table_matches_header(repo_root):
         assert n == len(argtypes), name
 
 
+def test_binding_constants_match_header(repo_root):
+    """Every RFRT_FLAG_* / RFRT_CTR_* / RFRT_SMALL_MAX_TRIS of include/rfrt.h has the same value in the ctypes mirror."""
+    from rf_ray_tracing_warp_b200 import _lib
+    text = open(os.path.join(repo_root, "include", "rfrt.h")).read()
+    defines = dict(re.findall(r"#define\s+RFRT_((?:FLAG|CTR)_\w+|SMALL_MAX_TRIS)\s+(\d+)u?\b", text))
+    assert len(defines) >= 14
+    for name, value in defines.items():
+        assert getattr(_lib, name) == int(value), name
+
+
 def test_error_path_without_gpu(repo_root):
     """Error behaviour: bad arguments return a negative status and set a message; nothing throws."""
     from rf_ray_tracing_warp_b200 import _lib
