@@ -22,7 +22,8 @@
  *   - every function returns 0 on success or a negative rfrt_status; rfrt_last_error() gives the
  *     message of the last failure on the calling thread.  No C++ exception crosses this boundary.
  *   - the library owns only what lives behind a handle (BVH nodes, re-ordered triangles, receiver
- *     vertices, the ray-sort workspace of big scenes) and frees it in *_destroy.
+ *     vertices, the ray-sort workspace of big scenes) and frees it in *_destroy.  *_destroy frees in the order of the
+ *     stream the object was created on: work that uses the handle on OTHER streams must have finished.
  *   - concurrency: calls on DIFFERENT environment handles may run on different streams at the same time; calls that
  *     share an environment handle, and replay / compat calls whose receiver sets have different face tables (the
  *     table lives in __constant__ memory), must be stream-ordered.
@@ -91,6 +92,9 @@ RFRT_API int rfrt_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_
 RFRT_API int rfrt_mesh_create(const float *d_vertices_xyz, int64_t n_vertices, const int32_t *d_indices,
                      int64_t n_triangles, void *stream, rfrt_handle *out_mesh);
 RFRT_API int rfrt_mesh_destroy(rfrt_handle mesh);
+/* Sizes the mesh's ray-order workspace (BVH scenes trace each wave in direction-coherent order: 16 B per ray of the
+ * largest wave) so that rfrt_trace never allocates; without it the first rfrt_trace call of a larger wave allocates. */
+RFRT_API int rfrt_mesh_reserve_rays(rfrt_handle mesh, int64_t max_chunk_rays);
 /* Material table for the reference-mode amplitude: tracer.py:43 hard-codes the refractive index n_1 = 5.0 in
  * _bounce_amplitude; with a table the triangle of each path vertex supplies n_1 (receiver vertices keep 5.0).
  *   d_refractive_index : [n_triangles] float32 (device; copied), or NULL to restore the reference's constant. */
@@ -190,6 +194,49 @@ RFRT_API int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const f
 RFRT_API int rfrt_bin_ir(const int32_t *d_rec_rx, const int64_t *d_rec_bin, const double *d_rec_amp, int64_t n_records,
                 const uint64_t *d_n_records, int64_t n_receivers, int64_t n_bins, int32_t deterministic,
                 double *d_ir, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Received-record pipeline (tracer.py:84-87 compaction order, tracer.py:101-117 binning) — the library's own
+ * radix sort and run sums; the Python layer only allocates.
+ *
+ * SEGMENT = fixed-capacity, self-describing block of received records, the unit of the multi-GPU exchange: every
+ * rank packs its records into one segment of the same capacity and the ranks all-gather them (one collective; the
+ * counts ride in the headers, so no host round trip is needed).  Layout (sections 16-byte aligned, cap = capacity):
+ *   u64 header[16] : [0] records produced (> [1] means overflow), [1] records that fit, [2..9] the job's counter block
+ *   u32 ray[cap] | i32 rx[cap] | i32 nverts[cap] | i64 bin[cap] | f64 amp[cap] | f64 dist[cap] | f32 paths[cap*path_floats]
+ * rfrt_record_segment_bytes / rfrt_records_workspace_bytes are host-only size queries.
+ * ------------------------------------------------------------------------------------------- */
+RFRT_API int rfrt_record_segment_bytes(int64_t capacity, int32_t path_floats, int64_t *out_bytes);
+RFRT_API int rfrt_records_workspace_bytes(int64_t n_slots, int64_t *out_bytes);
+/* Packs the records rfrt_trace_receive appended (count = d_counters[RFRT_CTR_RECORDS]) into d_segment.
+ *   d_rec_paths may be NULL (then the segment's path section stays unwritten); path_floats = (max_bounces+1)*3 */
+RFRT_API int rfrt_records_pack(const uint64_t *d_counters, const uint32_t *d_rec_ray, const int32_t *d_rec_rx,
+                      const int32_t *d_rec_nverts, const int64_t *d_rec_bin, const double *d_rec_amp,
+                      const double *d_rec_dist, const float *d_rec_paths, int64_t rec_capacity, int32_t path_floats,
+                      void *d_segment, int64_t seg_capacity, void *stream);
+/* Merges n_segments consecutive segments (stride = rfrt_record_segment_bytes) into records sorted by
+ * (receiver, ray id) — per receiver the reference's own order (tracer.py:87,102).
+ *   outputs: arrays of n_segments*seg_capacity entries (d_paths may be NULL); the first d_summary[0] are valid
+ *   d_summary [16] u64: [0] records stored, [1] segments that overflowed, [2..9] counter block summed over segments,
+ *                       [10] max records produced by one segment, [11] max candidates of one segment
+ *   d_workspace: rfrt_records_workspace_bytes(n_segments*seg_capacity) bytes */
+RFRT_API int rfrt_records_sort(const void *d_segments, int64_t n_segments, int64_t seg_capacity, int32_t path_floats,
+                      int64_t n_receivers, uint32_t *d_ray, int32_t *d_rx, int32_t *d_nverts, int64_t *d_bin,
+                      double *d_amp, double *d_dist, float *d_paths, uint64_t *d_summary, void *d_workspace,
+                      int64_t workspace_bytes, void *stream);
+/* Arrival sums of (receiver, ray id)-ordered records: every (receiver, bin) run is added sequentially in ray-id order,
+ * exactly like `impulse_response[delay_samples] += amplitude` (tracer.py:116-117) — bit-reproducible, independent of
+ * the GPU count, parallel over records.  Records with bin outside [0, n_bins) are skipped (tracer.py:116); runs that
+ * sum to exactly 0 are dropped from the arrival list.
+ *   n_slots / d_n_records : as rfrt_bin_ir (d_n_records may point at d_summary[0])
+ *   d_arr_offsets [n_receivers+1] int64, d_arr_bin [n_slots] int32, d_arr_amp [n_slots] float64: CSR for rfrt_rx_power
+ *                 (all three NULL to skip)
+ *   d_ir : NULL or [n_receivers*n_bins] float64 zeroed by the caller: ir[rx][bin] = the run's sum
+ *   d_workspace: rfrt_records_workspace_bytes(n_slots) bytes */
+RFRT_API int rfrt_arrivals_build(const int32_t *d_rec_rx, const int64_t *d_rec_bin, const double *d_rec_amp, int64_t n_slots,
+                        const uint64_t *d_n_records, int64_t n_receivers, int64_t n_bins, int64_t *d_arr_offsets,
+                        int32_t *d_arr_bin, double *d_arr_amp, double *d_ir, void *d_workspace, int64_t workspace_bytes,
+                        void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * RX power of main.py:39,46-55 / coverage.py:45-55 for each receiver, from its SPARSE arrivals

@@ -22,6 +22,8 @@ CTR_SEGMENTS, CTR_CANDIDATES, CTR_RECORDS, CTR_ENV_HITS, CTR_NEXT_RAY, CTR_NEXT_
     0, 1, 2, 3, 4, 5, 6, 7, 8
 FLAG_NONE, FLAG_DIRS_READY, FLAG_FORCE_BVH, FLAG_CHECKSUM, FLAG_NO_RAY_SORT = 0, 1, 2, 8, 16
 SMALL_MAX_TRIS = 64
+# d_summary of rfrt_records_sort (u64[16])
+SUM_RECORDS, SUM_OVERFLOWED, SUM_COUNTERS, SUM_MAX_RECORDS, SUM_MAX_CANDIDATES, SUM_COUNT = 0, 1, 2, 10, 11, 16
 
 # name -> (restype, argtypes); mirrors include/rfrt.h one to one
 SIGNATURES = {
@@ -48,6 +50,13 @@ SIGNATURES = {
                                           c_void_p, c_i64, c_void_p]),
     "rfrt_bin_ir": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_i32, c_void_p,
                                    c_void_p]),
+    "rfrt_mesh_reserve_rays": (ctypes.c_int, [c_u64, c_i64]),
+    "rfrt_record_segment_bytes": (ctypes.c_int, [c_i64, c_i32, ctypes.POINTER(c_i64)]),
+    "rfrt_records_workspace_bytes": (ctypes.c_int, [c_i64, ctypes.POINTER(c_i64)]),
+    "rfrt_records_pack": (ctypes.c_int, [c_void_p] * 8 + [c_i64, c_i32, c_void_p, c_i64, c_void_p]),
+    "rfrt_records_sort": (ctypes.c_int, [c_void_p, c_i64, c_i64, c_i32, c_i64] + [c_void_p] * 9 + [c_i64, c_void_p]),
+    "rfrt_arrivals_build": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "rfrt_rx_power": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_d, c_d, c_void_p, c_void_p,
                                      c_void_p]),
     "rfrt_rx_power_dense": (ctypes.c_int, [c_void_p, c_i64, c_i64, c_d, c_d, c_void_p, c_void_p]),

@@ -107,11 +107,12 @@ void release_mesh(Mesh *m)
 
 void release_rxset(RxSet *r)
 {
+    const cudaStream_t stream = r->stream; // the creating stream: frees are ordered after the work enqueued on it
     free_bvh(&r->bvh);
     free_bvh(&r->unit_bvh);
-    if (r->verts) cudaFreeAsync(r->verts, 0);
-    if (r->centers) cudaFreeAsync(r->centers, 0);
-    if (r->unit_recs) cudaFreeAsync(r->unit_recs, 0);
+    if (r->verts) cudaFreeAsync(r->verts, stream);
+    if (r->centers) cudaFreeAsync(r->centers, stream);
+    if (r->unit_recs) cudaFreeAsync(r->unit_recs, stream);
     r->verts = nullptr; r->centers = nullptr; r->unit_recs = nullptr;
 }
 
@@ -266,10 +267,6 @@ extern "C" int rfrt_mesh_set_materials(rfrt_handle mesh, const float *d_refracti
         m->materials = nullptr;
         return RFRT_OK;
     }
-    if (m->bvh.n_prims >= 32768) {
-        set_error("rfrt_mesh_set_materials: the reference-mode material table supports fewer than 32768 triangles");
-        return RFRT_ERR_INVALID;
-    }
     if (!m->materials) RFRT_CUDA(cudaMalloc(&m->materials, sizeof(float) * (size_t)(m->bvh.n_prims > 0 ? m->bvh.n_prims : 1)));
     RFRT_CUDA(cudaMemcpyAsync(m->materials, d_refractive_index, sizeof(float) * (size_t)m->bvh.n_prims, cudaMemcpyDeviceToDevice,
                               (cudaStream_t)stream_));
@@ -315,6 +312,7 @@ extern "C" int rfrt_rxset_create(const double *d_centers_xyz, int64_t n_receiver
     std::unique_ptr<RxSet, RxSetDeleter> r(new RxSet());
     Temporaries tmp;
     r->n_receivers = n_receivers; r->n_unit = n_unit_vertices; r->n_faces = n_faces; r->radius = radius;
+    r->stream = stream;
     for (int i = 0; i < 3 * n_faces; ++i) {
         if (h_faces[i] < 0 || h_faces[i] >= n_unit_vertices) { set_error("rfrt_rxset_create: face index out of range"); return RFRT_ERR_INVALID; }
         r->faces[i] = (uint8_t)h_faces[i];

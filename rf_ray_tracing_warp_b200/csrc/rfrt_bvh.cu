@@ -320,11 +320,12 @@ __global__ void k_prim_order(const uint64_t *__restrict__ keys, int64_t n, int32
 
 } // namespace
 
-// (stream-ordered frees on the legacy default stream: no device-wide synchronisation as with cudaFree)
+// (stream-ordered frees on the stream the hierarchy was built on — no device-wide synchronisation as with cudaFree, and
+// ordered after the work the caller enqueued on that stream; work on OTHER streams must be finished by the caller)
 void free_bvh(Bvh *b)
 {
-    if (b->nodes) cudaFreeAsync(b->nodes, 0);
-    if (b->prim_order) cudaFreeAsync(b->prim_order, 0);
+    if (b->nodes) cudaFreeAsync(b->nodes, b->stream);
+    if (b->prim_order) cudaFreeAsync(b->prim_order, b->stream);
     b->nodes = nullptr;
     b->prim_order = nullptr;
 }
@@ -349,6 +350,7 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
     keep_pool_memory();
     *out = Bvh();
     out->n_prims = n;
+    out->stream = stream;
     if (n <= 0) return RFRT_OK;
     if (n >= (1ll << 31)) {
         set_error("build_lbvh: more than 2^31-1 primitives");

@@ -37,6 +37,7 @@ struct Bvh {
     int32_t max_depth = 0;
     float bounds[6] = {0, 0, 0, 0, 0, 0};
     float pad = 0.0f;
+    cudaStream_t stream = nullptr; // the stream the hierarchy was allocated on: free_bvh frees in its order
 };
 
 struct Mesh {
@@ -70,6 +71,7 @@ struct RxSet {
     double radius = 0.0;
     double *centers = nullptr; // [R*3] device copy
     float *unit_recs = nullptr; // [n_faces*16] unit-space face records of the receiver-query filter (rfrt_small.cu)
+    cudaStream_t stream = nullptr; // creating stream (stream-ordered frees in rfrt_rxset_destroy)
 };
 
 void set_error(const std::string &msg);

@@ -1,8 +1,10 @@
 // rfrt_math.cuh — device arithmetic of the hot path (sm_100a).
 //
 // Everything here that decides WHICH triangle a ray hits is written as an explicit sequence of IEEE
-// fp32 operations (the library is compiled with -fmad=false, so the only fused operations are the
-// fmaf() calls written out below).  The sequence restates:
+// fp32 operations through the __f*_rn intrinsics, which nvcc never contracts (the library is built with the default
+// -fmad=true: pruning code such as the slab tests and the candidate filters may fuse freely, parity-critical code
+// may not, so it never uses plain * and +); the only fused parity-critical operations are the __fmaf_rn calls
+// written out below.  The sequence restates:
 //   kernel.py:51-52  wp.rand_init / wp.sample_unit_sphere_surface   (PCG hash, 24-bit randf)
 //   kernel.py:71,82  wp.mesh_query_ray -> intersect_ray_tri_woop    (watertight test)
 //   kernel.py:6-8    reflect

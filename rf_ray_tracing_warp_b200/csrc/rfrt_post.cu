@@ -23,27 +23,48 @@ __global__ void k_bin_atomic(const int32_t *__restrict__ rx, const int64_t *__re
     }
 }
 
-// Privatised variant for few receivers / many records: each CTA owns a contiguous slice of the records,
-// accumulates the bins that fall into its shared-memory window with shared atomics and flushes the
-// non-zero bins with one global atomic each.  Used when one receiver's histogram fits in shared memory.
-__global__ void k_bin_privatised(const int32_t *__restrict__ rx, const int64_t *__restrict__ bin,
-                                 const double *__restrict__ amp, int64_t n, const unsigned long long *d_n, int64_t n_rx,
-                                 int64_t n_bins, double *ir, int64_t per_block)
+// Privatised variant for few receivers / many records (one receiver's histogram fits in shared memory): each CTA owns
+// a contiguous slice of the records and, receiver by receiver, accumulates them into its shared-memory window, then
+// flushes the window's non-zero bins with one global atomic each.  The shared-memory adds are WARP-AGGREGATED: lanes
+// whose records fall into the same bin (__match_any_sync) are summed by their lowest lane in lane order and that lane
+// issues the one atomic — fp64 shared atomics are compare-and-swap loops, and the arrivals of a receiver cluster in a
+// few bins (every line-of-sight ray of a receiver has the same delay), so same-address conflicts are the common case.
+__global__ void __launch_bounds__(512)
+k_bin_privatised(const int32_t *__restrict__ rx, const int64_t *__restrict__ bin, const double *__restrict__ amp, int64_t n,
+                 const unsigned long long *d_n, int64_t n_rx, int64_t n_bins, double *ir, int64_t per_block)
 {
     extern __shared__ double s_hist[];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     if (d_n && (int64_t)*d_n < n) n = (int64_t)*d_n;
     const int64_t begin = blockIdx.x * per_block;
     const int64_t end = begin + per_block < n ? begin + per_block : n;
+    if (begin >= end) return;
     for (int64_t k = 0; k < n_rx; ++k) {
         for (int64_t b = threadIdx.x; b < n_bins; b += blockDim.x) s_hist[b] = 0.0;
         __syncthreads();
-        for (int64_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
-            int64_t b = bin[i];
-            if (rx[i] == k && b >= 0 && b < n_bins) atomicAdd(&s_hist[b], amp[i]);
+        // warp-uniform trip count: every lane takes part in the votes of every trip
+        for (int64_t base = begin + (threadIdx.x & ~31); base < end; base += blockDim.x) {
+            const int64_t i = base + lane;
+            int64_t b = -1;
+            double a = 0.0;
+            if (i < end && rx[i] == k) { b = bin[i]; a = amp[i]; }
+            const bool valid = b >= 0 && b < n_bins;
+            const int tag = valid ? (int)b : -1 - lane; // lanes without a record match nobody
+            const unsigned peers = __match_any_sync(FULL, tag);
+            const int iters = __reduce_max_sync(FULL, (unsigned)__popc(peers));
+            unsigned rest = peers;
+            double sum = 0.0;
+            for (int it = 0; it < iters; ++it) { // lane order: the group's sum does not depend on the schedule
+                const int src = rest ? __ffs((int)rest) - 1 : lane;
+                const double v = __shfl_sync(FULL, a, src);
+                if (rest) { sum += v; rest &= rest - 1u; }
+            }
+            if (valid && lane == __ffs((int)peers) - 1) atomicAdd(&s_hist[b], sum);
         }
         __syncthreads();
         for (int64_t b = threadIdx.x; b < n_bins; b += blockDim.x) {
-            double v = s_hist[b];
+            const double v = s_hist[b];
             if (v != 0.0) atomicAdd(&ir[k * n_bins + b], v);
         }
         __syncthreads();
@@ -69,9 +90,10 @@ __global__ void k_bin_ordered(const int32_t *__restrict__ rx, const int64_t *__r
     }
 }
 
-// same result with one CTA per receiver: thread j owns the bins b with b % blockDim == j; the receiver's records are
-// staged tile by tile in shared memory (coalesced) and every thread walks the tile in order, so every bin still sees
-// its additions in ray-id order (few receivers, many records each)
+// same result with gridDim.y CTAs per receiver: CTA s owns the 256-bin blocks j with j % gridDim.y == s and its thread t
+// the bins b of those blocks with b % 256 == t; the receiver's records are staged tile by tile in shared memory
+// (coalesced) and every thread walks the tile in order, so every bin still sees its additions in ray-id order (few
+// receivers, many records each).  (rfrt_arrivals_build is the scalable ordered path; this one needs no workspace.)
 __global__ void __launch_bounds__(256) k_bin_ordered_cta(const int32_t *__restrict__ rx, const int64_t *__restrict__ bin,
                                                          const double *__restrict__ amp, int64_t n,
                                                          const unsigned long long *d_n, int64_t n_bins, double *ir)
@@ -99,7 +121,8 @@ __global__ void __launch_bounds__(256) k_bin_ordered_cta(const int32_t *__restri
         const int cnt = (int)(end - base < 256 ? end - base : 256);
         for (int j = 0; j < cnt; ++j) {
             const int64_t b = s_bin[j];
-            if (b >= 0 && b < n_bins && (int)(b & 255) == (int)threadIdx.x) row[b] = __dadd_rn(row[b], s_amp[j]);
+            if (b >= 0 && b < n_bins && (int)(b & 255) == (int)threadIdx.x && (int)((b >> 8) % gridDim.y) == (int)blockIdx.y)
+                row[b] = __dadd_rn(row[b], s_amp[j]);
         }
         __syncthreads();
     }
@@ -304,9 +327,15 @@ extern "C" int rfrt_bin_ir(const int32_t *d_rec_rx, const int64_t *d_rec_bin, co
     }
     if (n_records == 0 || n_bins == 0) return RFRT_OK;
     if (deterministic) {
-        if (n_receivers <= 2048 && n_records >= 8 * n_receivers)
-            k_bin_ordered_cta<<<(unsigned)n_receivers, 256, 0, stream>>>(d_rec_rx, d_rec_bin, d_rec_amp, n_records, d_n,
-                                                                          n_bins, d_ir);
+        if (n_receivers <= 2048 && n_records >= 8 * n_receivers) {
+            int64_t split = 296 / n_receivers; // ~2 CTAs per SM in flight
+            const int64_t blocks256 = (n_bins + 255) / 256;
+            if (split > blocks256) split = blocks256;
+            if (split > 16) split = 16;
+            if (split < 1) split = 1;
+            k_bin_ordered_cta<<<dim3((unsigned)n_receivers, (unsigned)split), 256, 0, stream>>>(d_rec_rx, d_rec_bin, d_rec_amp,
+                                                                                              n_records, d_n, n_bins, d_ir);
+        }
         else
             k_bin_ordered<<<(unsigned)((n_receivers + 127) / 128), 128, 0, stream>>>(d_rec_rx, d_rec_bin, d_rec_amp,
                                                                                      n_records, d_n, n_receivers, n_bins, d_ir);
@@ -317,9 +346,11 @@ extern "C" int rfrt_bin_ir(const int32_t *d_rec_rx, const int64_t *d_rec_bin, co
             RFRT_CUDA(cudaGetDevice(&dev));
             RFRT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
             RFRT_CUDA(cudaFuncSetAttribute((const void *)k_bin_privatised, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int64_t per_block = (n_records + sms - 1) / sms;
-            k_bin_privatised<<<sms, 512, smem, stream>>>(d_rec_rx, d_rec_bin, d_rec_amp, n_records, d_n, n_receivers,
-                                                        n_bins, d_ir, per_block);
+            const int ctas = smem <= 100 * 1024 ? 2 * sms : sms; // two resident CTAs per SM when the window allows it
+            int64_t per_block = (n_records + ctas - 1) / ctas;
+            per_block = (per_block + 31) & ~(int64_t)31;
+            k_bin_privatised<<<ctas, 512, smem, stream>>>(d_rec_rx, d_rec_bin, d_rec_amp, n_records, d_n, n_receivers,
+                                                         n_bins, d_ir, per_block);
         } else {
             int64_t nb = (n_records + 255) / 256;
             if (nb > 4096) nb = 4096;

@@ -105,7 +105,10 @@ __global__ void k_dir_keys(const float4 *__restrict__ dirs, int64_t n, uint64_t 
 
 // Conservative sphere filter in front of the exact 80-triangle receiver query: can the segment
 // [0, t_limit] of the ray come within the receiver's bounding sphere?  (Approximate reciprocal / square root: the
-// 1 % inflation of the radius is five orders of magnitude above their 2-ulp error.)
+// 1 % inflation of the radius is five orders of magnitude above their 2-ulp error.)  The perpendicular distance is
+// taken from the closest-approach VECTOR m = (c - p) - tc * d: |c - p|^2 - tc * ((c - p) . d) cancels two terms of
+// size D^2 and loses the 1e-2 m^2 that matter once the receiver is D > ~50 m away (every rounding of m is ~D * 2^-24,
+// far inside the 1e-5 * D slack on the radius).
 __device__ __forceinline__ bool rx_sphere_filter(float3 p, float3 d, float cx, float cy, float cz, float radius,
                                                  float t_limit)
 {
@@ -119,7 +122,8 @@ __device__ __forceinline__ bool rx_sphere_filter(float3 p, float3 d, float cx, f
     float inv_dd = rcp_approx(dd);
     float tc = od * inv_dd;
     if (tc < 0.0f) return false;
-    float perp2 = oo - tc * od;
+    float mx = fmaf(-tc, d.x, ox), my = fmaf(-tc, d.y, oy), mz = fmaf(-tc, d.z, oz);
+    float perp2 = mx * mx + my * my + mz * mz;
     if (perp2 > r2 * 1.01f + 1.0e-12f) return false;
     float half = sqrt_approx(fmaxf(r2 * 1.01f - perp2, 0.0f) * inv_dd);
     return tc - half * 1.0001f <= t_limit * 1.0001f + 1.0e-6f;
@@ -615,9 +619,11 @@ struct CompatSink {
 };
 
 __global__ void __launch_bounds__(TRACE_THREADS)
-k_trace_compat(LiteralEnv E, RxView rx, int has_rx, int n_faces, float3 tx, int max_bounces, int64_t ray_begin, int64_t n_rays,
-               float *traced, float *received, uint32_t *mask, int stack_depth)
+k_trace_compat(LiteralEnv E, RxView rx, const double *rx_center, int n_faces, float3 tx, int max_bounces, int64_t ray_begin,
+               int64_t n_rays, float *traced, float *received, uint32_t *mask, int stack_depth)
 {
+    const int has_rx = rx_center != nullptr;
+    if (has_rx) { rx.cx = (float)__ldg(rx_center); rx.cy = (float)__ldg(rx_center + 1); rx.cz = (float)__ldg(rx_center + 2); }
     extern __shared__ int s_stack_raw[];
     int *stack = s_stack_raw + threadIdx.x;
     float *stack_t = reinterpret_cast<float *>(s_stack_raw + stack_depth * TRACE_THREADS) + threadIdx.x;
@@ -631,11 +637,11 @@ k_trace_compat(LiteralEnv E, RxView rx, int has_rx, int n_faces, float3 tx, int 
 
 struct RecordSink {
     float path[3 * (MAX_RECV_BOUNCES + 1)];
-    short face[MAX_RECV_BOUNCES + 1]; // triangle of an environment vertex, -1 for tx / receiver vertices (materials)
+    int face[MAX_RECV_BOUNCES + 1]; // triangle of an environment vertex, -1 for tx / receiver vertices (materials)
     int last_rx_bounce;
     int first_rx_bounce;
     bool want_faces;
-    __device__ __forceinline__ void env_face(int i, int f) { if (want_faces) face[i] = (short)f; }
+    __device__ __forceinline__ void env_face(int i, int f) { if (want_faces) face[i] = f; }
     __device__ __forceinline__ void vertex(int i, float3 p)
     {
         path[3 * i] = p.x; path[3 * i + 1] = p.y; path[3 * i + 2] = p.z;
@@ -652,18 +658,20 @@ __device__ __forceinline__ float norm3_f32(float x, float y, float z)
     return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
 }
 
-// tracer.py:34-61
+// tracer.py:34-61.  Explicit _rn operations: nvcc would otherwise contract n_2*cos(theta_i) -/+ n_1*cos(theta) into
+// FMAs, which CPython's float arithmetic never does (asin / sin / cos themselves are libdevice vs libm: <= 1e-15).
 __device__ __forceinline__ double bounce_amplitude(double angle_between, double n_1 = 5.0)
 {
     if (isnan(angle_between)) return 0.0;
     const double PI = 3.141592653589793;
-    double theta = PI / 2 - angle_between / 2;
+    double theta = __dsub_rn(__ddiv_rn(PI, 2.0), __ddiv_rn(angle_between, 2.0));
     const double n_2 = 1.0;
-    double theta_i = asin((n_2 * sin(theta)) / n_1);
-    double num = n_2 * cos(theta_i) - n_1 * cos(theta);
-    double denom = n_2 * cos(theta_i) + n_1 * cos(theta);
-    double q = num / denom;
-    double amp = -(q * q);
+    double theta_i = asin(__ddiv_rn(__dmul_rn(n_2, sin(theta)), n_1));
+    double a = __dmul_rn(n_2, cos(theta_i)), b = __dmul_rn(n_1, cos(theta));
+    double num = __dsub_rn(a, b);
+    double denom = __dadd_rn(a, b);
+    double q = __ddiv_rn(num, denom);
+    double amp = -__dmul_rn(q, q);
     if (amp < -1) amp = -1;
     if (isnan(amp)) return 0.0;
     return -amp;
@@ -752,7 +760,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_receive(const ReceivePa
                 // tracer.py:43 hard-codes n_1 = 5; with a material table the vertex's triangle decides
                 double n_1 = 5.0;
                 if (P.materials && sink.face[v + 1] >= 0) n_1 = (double)__ldg(P.materials + sink.face[v + 1]);
-                amplitude *= bounce_amplitude((double)angle, n_1);
+                amplitude = __dmul_rn(amplitude, bounce_amplitude((double)angle, n_1));
                 distance = __dadd_rn(distance, (double)l1);
             }
             const float *u = p + 3 * (nverts - 2), *w = p + 3 * (nverts - 1);
@@ -824,6 +832,21 @@ int grid_for(const void *kernel, size_t smem, int *out_grid, bool all_smem = fal
     return RFRT_OK;
 }
 
+// workspace of the direction-coherent ray order (BVH scenes): two key buffers + the sort's histograms
+int reserve_ray_sort(Mesh *m, int64_t cap)
+{
+    if (m->ray_cap >= cap) return RFRT_OK;
+    if (m->ray_keys[0]) cudaFree(m->ray_keys[0]);
+    if (m->ray_keys[1]) cudaFree(m->ray_keys[1]);
+    if (m->ray_hist) cudaFree(m->ray_hist);
+    m->ray_keys[0] = m->ray_keys[1] = nullptr; m->ray_hist = nullptr; m->ray_cap = 0;
+    RFRT_CUDA(cudaMalloc(&m->ray_keys[0], sizeof(uint64_t) * cap));
+    RFRT_CUDA(cudaMalloc(&m->ray_keys[1], sizeof(uint64_t) * cap));
+    RFRT_CUDA(cudaMalloc(&m->ray_hist, sizeof(uint32_t) * 256 * ((size_t)sort_hist_blocks(cap) + 1)));
+    m->ray_cap = cap;
+    return RFRT_OK;
+}
+
 int upload_faces(const RxSet *r, cudaStream_t stream)
 {
     RFRT_CUDA(cudaMemcpyToSymbolAsync(c_rx_faces, r->faces, sizeof(uint8_t) * 3 * (size_t)r->n_faces, 0,
@@ -844,6 +867,15 @@ extern "C" int rfrt_ray_directions(int64_t ray_begin, int64_t ray_end, float *d_
     k_gen_dirs<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ray_begin, n, (float4 *)d_dirs);
     RFRT_CUDA(cudaGetLastError());
     return RFRT_OK;
+}
+
+extern "C" int rfrt_mesh_reserve_rays(rfrt_handle mesh, int64_t max_chunk_rays)
+{
+    Mesh *m = get_mesh(mesh);
+    if (!m) { set_error("rfrt_mesh_reserve_rays: unknown mesh handle"); return RFRT_ERR_HANDLE; }
+    if (max_chunk_rays < 0) { set_error("rfrt_mesh_reserve_rays: bad arguments"); return RFRT_ERR_INVALID; }
+    if (m->small || max_chunk_rays == 0) return RFRT_OK; // small scenes are swept, not walked: no ray order needed
+    return reserve_ray_sort(m, max_chunk_rays);
 }
 
 extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *h_tx_pos, int32_t max_bounces,
@@ -943,17 +975,10 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     // BVH scenes: trace the rays of a chunk in direction-coherent order (workspace cached with the mesh)
     const bool sorted = !small && !(flags & RFRT_FLAG_NO_RAY_SORT) && n >= 4096;
     if (sorted) {
-        const int64_t cap = n < chunk_rays ? n : chunk_rays;
-        if (m->ray_cap < cap) {
-            if (m->ray_keys[0]) cudaFree(m->ray_keys[0]);
-            if (m->ray_keys[1]) cudaFree(m->ray_keys[1]);
-            if (m->ray_hist) cudaFree(m->ray_hist);
-            m->ray_keys[0] = m->ray_keys[1] = nullptr; m->ray_hist = nullptr; m->ray_cap = 0;
-            RFRT_CUDA(cudaMalloc(&m->ray_keys[0], sizeof(uint64_t) * cap));
-            RFRT_CUDA(cudaMalloc(&m->ray_keys[1], sizeof(uint64_t) * cap));
-            RFRT_CUDA(cudaMalloc(&m->ray_hist, sizeof(uint32_t) * 256 * ((size_t)sort_hist_blocks(cap) + 1)));
-            m->ray_cap = cap;
-        }
+        // (sized once by rfrt_mesh_reserve_rays, which the Python layer calls when it builds a BVH scene; a caller that
+        // did not reserve pays for the allocation here, on the first wave only)
+        const int rc2 = reserve_ray_sort(m, n < chunk_rays ? n : chunk_rays);
+        if (rc2) return rc2;
     }
 
     for (int64_t c0 = ray_begin; c0 < ray_end; c0 += chunk_rays) {
@@ -999,7 +1024,7 @@ extern "C" int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const
     }
     ReceiveParams P;
     P.env.nodes = m->bvh.nodes; P.env.tris = m->tris; P.env.n_tris = m->bvh.n_prims;
-    P.materials = (m->materials && m->bvh.n_prims < 32768) ? m->materials : nullptr;
+    P.materials = m->materials;
     P.rx_verts = r->verts; P.n_unit = r->n_unit; P.n_faces = r->n_faces;
     P.rx_centers = r->centers; P.unit_nodes = r->unit_bvh.nodes; P.unit_order = r->unit_bvh.prim_order;
     P.unit_recs = r->unit_recs;
@@ -1054,19 +1079,16 @@ extern "C" int rfrt_trace_paths_compat(rfrt_handle env_mesh, const float *h_tx_p
     int rc = grid_for((const void *)k_trace_compat, smem, &grid);
     RxView rxv{};
     if (r) {
-        double c[3];
-        RFRT_CUDA(cudaMemcpyAsync(c, r->centers + 3 * rx_index, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream));
-        RFRT_CUDA(cudaStreamSynchronize(stream));
         rxv.verts = r->verts + rx_index * r->n_unit * 3;
         rxv.unit_nodes = r->unit_bvh.nodes; rxv.unit_order = r->unit_bvh.prim_order;
-        rxv.cx = (float)c[0]; rxv.cy = (float)c[1]; rxv.cz = (float)c[2]; rxv.inv_r = (float)(1.0 / r->radius);
+        rxv.inv_r = (float)(1.0 / r->radius); // (centre: read by the kernel from r->centers — no host round trip)
     }
     if (rc) return rc;
     int64_t need = (n_rays + TRACE_THREADS - 1) / TRACE_THREADS;
     if (need < grid) grid = (int)need;
     if (r) { rc = upload_faces(r, stream); if (rc) return rc; }
     k_trace_compat<<<grid, TRACE_THREADS, smem, stream>>>(
-        E, rxv, r ? 1 : 0, r ? r->n_faces : 0, make_float3(h_tx_pos[0], h_tx_pos[1], h_tx_pos[2]), max_bounces, ray_begin, n_rays,
+        E, rxv, r ? r->centers + 3 * rx_index : nullptr, r ? r->n_faces : 0, make_float3(h_tx_pos[0], h_tx_pos[1], h_tx_pos[2]), max_bounces, ray_begin, n_rays,
         d_traced_paths, d_received_paths, d_row_mask, depth);
     RFRT_CUDA(cudaGetLastError());
     return RFRT_OK;

@@ -46,13 +46,15 @@ class Tracer:
       shard         split rays across torch.distributed ranks and combine the received records
       chunk_rays    rays generated per wave
       max_candidates / max_records   initial capacities of the device work lists (grown on overflow)
+      exchange_records   initial capacity of the record segment every rank contributes to the exchange (grown on overflow)
       verbose       print the reference's progress line (tracer.py:119)
       force_bvh     walk the BVH even for scenes of <= 64 triangles (default: lockstep sweep for those)
     """
 
     def __init__(self, environment_trimesh, light_speed_mps, sample_rate_hz, sample_window_s, max_bounces,
                  tx_num_rays, *, device=None, ray_range=None, shard=False, chunk_rays=1 << 26,
-                 max_candidates=1 << 20, max_records=1 << 20, verbose=False, force_bvh=False):
+                 max_candidates=1 << 20, max_records=1 << 20, exchange_records=1 << 16, verbose=False,
+                 force_bvh=False):
         if not torch.cuda.is_available():
             raise RfrtError("rf_ray_tracing_warp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self._lib = _lib.load()
@@ -65,6 +67,7 @@ class Tracer:
         self.chunk_rays = int(chunk_rays)
         self.max_candidates = int(max_candidates)
         self.max_records = int(max_records)
+        self.exchange_records = int(exchange_records)
         self.verbose = verbose
         self.trace_flags = _lib.FLAG_FORCE_BVH if force_bvh else 0
         self.shard = bool(shard)
@@ -85,6 +88,9 @@ class Tracer:
             check(self._lib.rfrt_mesh_create(_ptr(self._d_vertices), vertices.shape[0], _ptr(self._d_faces),
                                              faces.shape[0] // 3, _stream_ptr(), handle), "rfrt_mesh_create")
         self._env = handle.value
+        # BVH scenes trace each wave in direction-coherent order: size that workspace now, not on the hot path
+        check(self._lib.rfrt_mesh_reserve_rays(self._env, min(self.chunk_rays, max(self.ray_range[1] - self.ray_range[0], 1))),
+              "rfrt_mesh_reserve_rays")
         self._unit_v, self._unit_f = unit_icosphere(1)  # tracer.py:27 (subdivisions=1)
         self._materials = None
         self._dir_scratch = None
@@ -160,48 +166,71 @@ class Tracer:
         return TraceJob(self, rx_positions, rx_radius, want_paths, cand_capacity or self.max_candidates,
                         rec_capacity or self.max_records)
 
-    def _trace_records(self, tx_pos, tx_power, centers, rx_radius, want_paths):
-        """trace + literal replay for this process's ray range -> unsorted device record arrays."""
-        cand_cap, rec_cap = self.max_candidates, self.max_records
-        while True:
-            job = TraceJob(self, centers, rx_radius, want_paths, cand_cap, rec_cap)
-            try:
-                job.enqueue(tx_pos, tx_power)
-                c = job.counters()  # synchronises
-            finally:
-                job.close()
-            n_cand, n_rec = c["candidates"], c["records"]
-            if n_cand <= cand_cap and n_rec <= rec_cap:
-                break
-            cand_cap = max(cand_cap, int(n_cand * 1.25) + 1)  # overflow is reported, never silent: retry
-            rec_cap = max(rec_cap, int(n_cand * 1.25) + 1)
-        self.max_candidates, self.max_records = cand_cap, rec_cap
-        rec = {k: (v[:n_rec] if v is not None else None) for k, v in job.rec.items()}
-        return rec, c
-
-    def _gather_records(self, rec, stats):
-        """Multi-GPU exchange step: every rank ends up with ALL received records (they are sparse), so the
-        ordered binning below gives bit-identical results for any GPU count."""
-        if self._world == 1:
-            return rec, stats
-        return sharding.gather_records(rec), sharding.sum_stats(stats, self.device)
-
-    def _records(self, tx_pos, tx_power, rx_positions, rx_radius, want_paths):
+    def _records(self, tx_pos, tx_power, rx_positions, rx_radius, want_paths, ir=None):
+        """trace + literal replay of this process's ray range, then the record exchange: every rank packs its records
+        into one fixed-size segment, ONE all-gather moves the segments (NCCL; counts and counters ride in the headers),
+        and the library sorts them by (receiver, ray id) — the reference's own order (tracer.py:87,102) — so that
+        everything downstream is bit-identical for any GPU count.  The only host round trip is the read of the
+        16-word summary at the end.  ``ir``: optional (R, L) float64 tensor to fill with the ordered impulse responses
+        in the same submission.  Returns (records dict of device tensors, n_receivers)."""
         centers = np.ascontiguousarray(np.asarray(rx_positions, dtype=np.float64).reshape(-1, 3))
+        cand_cap, rec_cap, seg_cap = self.max_candidates, self.max_records, min(self.exchange_records, self.max_records)
         with torch.cuda.device(self.device):
-            rec, stats = self._trace_records(tx_pos, tx_power, centers, rx_radius, want_paths)
-            rec, stats = self._gather_records(rec, stats)
-            rec = sharding.sort_records(rec)
-        self.last_stats = stats
+            job, traced = None, False
+            try:
+                while True:
+                    if job is None:
+                        job = TraceJob(self, centers, rx_radius, want_paths, cand_cap, rec_cap)
+                        traced = False
+                    if not traced:
+                        job.enqueue(tx_pos, tx_power)
+                        traced = True
+                    rec, summary = job.collect(seg_cap, ir=ir)
+                    c = summary.cpu().numpy()  # the one synchronisation
+                    if c[_lib.SUM_COUNTERS + _lib.CTR_QUEUE_OVERFLOW]:
+                        raise RfrtError("receiver-enumeration queue overflowed: results would be incomplete (receiver BVH too deep)")
+                    max_rec, max_cand = int(c[_lib.SUM_MAX_RECORDS]), int(c[_lib.SUM_MAX_CANDIDATES])
+                    # overflow is reported, never silent: grow and retry (every rank sees the same summary, so all
+                    # ranks take the same branch with the same capacities)
+                    if max_cand > cand_cap or max_rec > rec_cap:
+                        cand_cap = max(cand_cap, int(max_cand * 1.25) + 1)
+                        rec_cap = max(rec_cap, int(max_cand * 1.25) + 1)
+                        job.close()
+                        job = None
+                        continue
+                    if c[_lib.SUM_OVERFLOWED]:
+                        seg_cap = min(rec_cap, max(2 * seg_cap, int(max_rec * 1.25) + 1))
+                        continue  # the records are still in the job's lists: only the exchange is repeated
+                    break
+            finally:
+                if job is not None:
+                    job.close()
+        self.max_candidates, self.max_records, self.exchange_records = cand_cap, rec_cap, seg_cap
+        n = int(c[_lib.SUM_RECORDS])
+        self.last_stats = dict(segments=int(c[_lib.SUM_COUNTERS + _lib.CTR_SEGMENTS]),
+                               env_hits=int(c[_lib.SUM_COUNTERS + _lib.CTR_ENV_HITS]),
+                               candidates=int(c[_lib.SUM_COUNTERS + _lib.CTR_CANDIDATES]), records=n)
+        rec = {k: (v[:n] if v is not None else None) for k, v in rec.items()}
         return rec, centers.shape[0]
 
-    def _dense_ir(self, rec, n_rx):
+    def _workspace(self, n_slots):
+        need = c_i64(0)
+        check(self._lib.rfrt_records_workspace_bytes(int(n_slots), need), "rfrt_records_workspace_bytes")
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() < need.value:
+            self._ws = ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+        return ws
+
+    def _dense_ir(self, rec, n_rx, out=None):
+        """tracer.py:101,116-117 per receiver from (receiver, ray id)-ordered records: ordered run sums (library)."""
         L = int(self.sample_window_s * self.sample_rate_hz)  # tracer.py:101
-        ir = torch.zeros((n_rx, L), dtype=torch.float64, device=self.device)
+        ir = torch.zeros((n_rx, L), dtype=torch.float64, device=self.device) if out is None else out.zero_()
         n = rec["ray"].shape[0]
         if n and L:
-            check(self._lib.rfrt_bin_ir(_ptr(rec["rx"]), _ptr(rec["bin"]), _ptr(rec["amp"]), n, None, n_rx, L, 1,
-                                        _ptr(ir), _stream_ptr()), "rfrt_bin_ir")
+            ws = self._workspace(n)
+            check(self._lib.rfrt_arrivals_build(_ptr(rec["rx"]), _ptr(rec["bin"]), _ptr(rec["amp"]), n, None, n_rx, L, None,
+                                                None, None, _ptr(ir), _ptr(ws), ws.numel(), _stream_ptr()),
+                  "rfrt_arrivals_build")
         return ir
 
     # ------------------------------------------------------------------------------------------
@@ -223,11 +252,16 @@ class Tracer:
         """Batched compute_cir: ONE trace for R receivers, identical per receiver to R separate compute_cir calls.
         Returns dict(impulse_response (R,L) float64 tensor if dense, records=dict of device tensors sorted by
         (receiver, ray id): ray, rx, nverts, bin, amp, dist[, paths])."""
-        rec, n_rx = self._records(tx_pos, tx_power, rx_positions, rx_radius, return_paths)
+        ir = None
+        if dense:
+            n_rx = np.asarray(rx_positions).reshape(-1, 3).shape[0]
+            L = int(self.sample_window_s * self.sample_rate_hz)
+            with torch.cuda.device(self.device):
+                ir = torch.empty((n_rx, L), dtype=torch.float64, device=self.device)
+        rec, n_rx = self._records(tx_pos, tx_power, rx_positions, rx_radius, return_paths, ir=ir)
         out = dict(records=rec, n_receivers=n_rx, stats=dict(self.last_stats))
         if dense:
-            with torch.cuda.device(self.device):
-                out["impulse_response"] = self._dense_ir(rec, n_rx)
+            out["impulse_response"] = ir
         return out
 
     def rx_power(self, rec, n_rx, carrier_hz=2.4e9):
@@ -236,24 +270,18 @@ class Tracer:
         L = int(self.sample_window_s * self.sample_rate_hz)
         dev = self.device
         with torch.cuda.device(dev):
-            keep = (rec["bin"] >= 0) & (rec["bin"] < L)
-            rx = rec["rx"][keep].to(torch.int64)
-            b = rec["bin"][keep]
-            amp = rec["amp"][keep]
-            key = rx * L + b
-            order = torch.argsort(key, stable=True)  # keeps ray-id order inside one (receiver, bin)
-            key, amp = key[order], amp[order]
-            ukey, inverse = torch.unique_consecutive(key, return_inverse=True)
-            aamp = torch.zeros(ukey.shape[0], dtype=torch.float64, device=dev).index_add_(0, inverse, amp)
-            nz = aamp != 0  # np.convolve sees the summed impulse response: exact zeros contribute nothing
-            ukey, aamp = ukey[nz], aamp[nz]
-            arx = torch.div(ukey, L, rounding_mode="floor")
-            abin = (ukey - arx * L).to(torch.int32).contiguous()
+            n = rec["ray"].shape[0]
             offsets = torch.zeros(n_rx + 1, dtype=torch.int64, device=dev)
-            offsets[1:] = torch.cumsum(torch.bincount(arx, minlength=n_rx), 0)
+            abin = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            aamp = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+            if n:
+                ws = self._workspace(n)
+                check(self._lib.rfrt_arrivals_build(_ptr(rec["rx"]), _ptr(rec["bin"]), _ptr(rec["amp"]), n, None, n_rx, L,
+                                                    _ptr(offsets), _ptr(abin), _ptr(aamp), None, _ptr(ws), ws.numel(),
+                                                    _stream_ptr()), "rfrt_arrivals_build")
             power = torch.empty(n_rx, dtype=torch.float64, device=dev)
             table = torch.empty(max(L, 1), dtype=torch.float64, device=dev)
-            check(self._lib.rfrt_rx_power(_ptr(offsets), _ptr(abin), _ptr(aamp.contiguous()), n_rx, L,
+            check(self._lib.rfrt_rx_power(_ptr(offsets), _ptr(abin), _ptr(aamp), n_rx, L,
                                           float(self.sample_window_s), float(carrier_hz), _ptr(table), _ptr(power),
                                           _stream_ptr()), "rfrt_rx_power")
         return power
@@ -332,10 +360,9 @@ class Tracer:
         if mat.shape[0] != self.mesh_info()["n_triangles"]:
             raise ValueError("set_materials: need one refractive index per triangle")
         self._materials = torch.from_numpy(mat).to(self.device)
-        if mat.shape[0] < 32768:  # reference mode keeps per-vertex triangle ids as 16-bit
-            with torch.cuda.device(self.device):
-                check(self._lib.rfrt_mesh_set_materials(self._env, _ptr(self._materials), _stream_ptr()),
-                      "rfrt_mesh_set_materials")
+        with torch.cuda.device(self.device):
+            check(self._lib.rfrt_mesh_set_materials(self._env, _ptr(self._materials), _stream_ptr()),
+                  "rfrt_mesh_set_materials")
 
     def trace_physical(self, tx_pos, tx_power, rx_positions, rx_radius, carrier_hz=2.4e9, want_ir=False):
         """Physical mode (rfrt_trace_physical; NOT reference behaviour, see include/rfrt.h): no t ~ 0 re-hits,
@@ -406,6 +433,20 @@ class Tracer:
                 if rxset:
                     self._lib.rfrt_rxset_destroy(rxset)
         return traced, received, mask
+
+    def receiver_mesh(self, rx_positions, rx_radius):
+        """tracer.py:26-30 for R receivers: (vertices (R, 42, 3) float32, faces (80, 3) int) as NumPy arrays — the
+        receiver meshes the trace uses (rfrt_rxset_export)."""
+        with torch.cuda.device(self.device):
+            centers = torch.as_tensor(np.ascontiguousarray(np.asarray(rx_positions, dtype=np.float64).reshape(-1, 3))).to(self.device)
+            rxset = self._make_rxset(centers, rx_radius)
+            try:
+                verts = torch.empty((centers.shape[0], self._unit_v.shape[0], 3), dtype=torch.float32, device=self.device)
+                check(self._lib.rfrt_rxset_export(rxset, _ptr(verts), _stream_ptr()), "rfrt_rxset_export")
+                out = verts.cpu().numpy()
+            finally:
+                self._lib.rfrt_rxset_destroy(rxset)
+        return out, np.asarray(self._unit_f, dtype=np.int64)
 
     def query_closest(self, origins, dirs, max_t=1.0e6):
         """Test probe: closest hit of arbitrary rays against the environment BVH -> (t, face) tensors."""
@@ -488,6 +529,55 @@ class TraceJob:
                                       self.counters_t.data_ptr() + 8 * _lib.CTR_RECORDS, self.n_rx, ir.shape[1], 0,
                                       _ptr(ir), _stream_ptr()), "rfrt_bin_ir")
                 self.kernel_launches += 1
+
+    def collect(self, seg_capacity, ir=None):
+        """Record exchange of the last enqueue, all on the current stream and without host synchronisation:
+        pack (this rank's records -> one segment) -> all-gather of the ranks' segments (ONE collective) -> library sort
+        by (receiver, ray id) [-> ordered impulse responses into ``ir``].  Returns (records dict of device tensors with
+        world * seg_capacity slots, summary u64[16] device tensor: _lib.SUM_*)."""
+        t, lib = self.t, self.t._lib
+        dev, world = t.device, t._world
+        B = t.max_bounces
+        row = (B + 1) * 3 if self.rec["paths"] is not None else 0
+        seg_capacity = int(seg_capacity)
+        with torch.cuda.device(dev):
+            if getattr(self, "_seg_capacity", None) != seg_capacity:
+                nbytes = c_i64(0)
+                check(lib.rfrt_record_segment_bytes(seg_capacity, row, nbytes), "rfrt_record_segment_bytes")
+                self._seg_bytes = nbytes.value
+                self._segs = torch.empty(world * nbytes.value, dtype=torch.uint8, device=dev)
+                self._seg_local = torch.empty(nbytes.value, dtype=torch.uint8, device=dev) if world > 1 else self._segs
+                n = world * seg_capacity
+                self._sorted = dict(ray=torch.empty(n, dtype=torch.int32, device=dev),
+                                    rx=torch.empty(n, dtype=torch.int32, device=dev),
+                                    nverts=torch.empty(n, dtype=torch.int32, device=dev),
+                                    bin=torch.empty(n, dtype=torch.int64, device=dev),
+                                    amp=torch.empty(n, dtype=torch.float64, device=dev),
+                                    dist=torch.empty(n, dtype=torch.float64, device=dev),
+                                    paths=torch.empty((n, B + 1, 3), dtype=torch.float32, device=dev) if row else None)
+                self._summary = torch.zeros(_lib.SUM_COUNT, dtype=torch.int64, device=dev)
+                self._seg_capacity = seg_capacity
+            r, o = self.rec, self._sorted
+            n = world * seg_capacity
+            check(lib.rfrt_records_pack(_ptr(self.counters_t), _ptr(r["ray"]), _ptr(r["rx"]), _ptr(r["nverts"]), _ptr(r["bin"]),
+                                        _ptr(r["amp"]), _ptr(r["dist"]), _ptr(r["paths"]), self.rec_capacity, row,
+                                        _ptr(self._seg_local), seg_capacity, _stream_ptr()), "rfrt_records_pack")
+            if world > 1:
+                sharding.exchange_segments(self._segs, self._seg_local)  # the one collective of the data path
+            ws = t._workspace(n)
+            check(lib.rfrt_records_sort(_ptr(self._segs), world, seg_capacity, row, self.n_rx, _ptr(o["ray"]), _ptr(o["rx"]),
+                                        _ptr(o["nverts"]), _ptr(o["bin"]), _ptr(o["amp"]), _ptr(o["dist"]), _ptr(o["paths"]),
+                                        _ptr(self._summary), _ptr(ws), ws.numel(), _stream_ptr()), "rfrt_records_sort")
+            self.kernel_launches += 3 + 4 * ((32 + max(self.n_rx, 1).bit_length() + 7) // 8)
+            if ir is not None:
+                ir.zero_()
+                L = ir.shape[1]
+                if L:
+                    check(lib.rfrt_arrivals_build(_ptr(o["rx"]), _ptr(o["bin"]), _ptr(o["amp"]), n, _ptr(self._summary), self.n_rx, L,
+                                                  None, None, None, _ptr(ir), _ptr(ws), ws.numel(), _stream_ptr()),
+                          "rfrt_arrivals_build")
+                    self.kernel_launches += 5 + 4 * max(1, ((self.n_rx * L - 1).bit_length() + 7) // 8)
+        return o, self._summary
 
     def bin_into(self, ir):
         """tracer.py:116-117 for the records of the last enqueue, ACCUMULATED into ir (R, L) with fp64 atomics
