@@ -74,7 +74,9 @@ enum rfrt_status {
 #define RFRT_CTR_CHECKSUM 6    /* with RFRT_FLAG_CHECKSUM: sum over segments of hash(ray id, bounce, hit triangle, bits of t)
                                   (mod 2^64; order-independent, so it compares whole runs of different kernels / GPU counts) */
 #define RFRT_CTR_QUEUE_OVERFLOW 7 /* receiver-enumeration queue overflows (must stay 0: results would be incomplete) */
-#define RFRT_CTR_COUNT 8
+#define RFRT_CTR_NODE_VISITS 8 /* with RFRT_FLAG_CHECKSUM, BVH scenes: internal nodes fetched by the environment walks */
+#define RFRT_CTR_TRI_TESTS 9   /* with RFRT_FLAG_CHECKSUM, BVH scenes: exact triangle tests run by the environment walks */
+#define RFRT_CTR_COUNT 10
 
 RFRT_API int rfrt_version(void);
 RFRT_API const char *rfrt_last_error(void);
@@ -202,7 +204,7 @@ RFRT_API int rfrt_bin_ir(const int32_t *d_rec_rx, const int64_t *d_rec_bin, cons
  * SEGMENT = fixed-capacity, self-describing block of received records, the unit of the multi-GPU exchange: every
  * rank packs its records into one segment of the same capacity and the ranks all-gather them (one collective; the
  * counts ride in the headers, so no host round trip is needed).  Layout (sections 16-byte aligned, cap = capacity):
- *   u64 header[16] : [0] records produced (> [1] means overflow), [1] records that fit, [2..9] the job's counter block
+ *   u64 header[16] : [0] records produced (> [1] means overflow), [1] records that fit, [2..11] the job's counter block
  *   u32 ray[cap] | i32 rx[cap] | i32 nverts[cap] | i64 bin[cap] | f64 amp[cap] | f64 dist[cap] | f32 paths[cap*path_floats]
  * rfrt_record_segment_bytes / rfrt_records_workspace_bytes are host-only size queries.
  * ------------------------------------------------------------------------------------------- */
@@ -217,8 +219,8 @@ RFRT_API int rfrt_records_pack(const uint64_t *d_counters, const uint32_t *d_rec
 /* Merges n_segments consecutive segments (stride = rfrt_record_segment_bytes) into records sorted by
  * (receiver, ray id) — per receiver the reference's own order (tracer.py:87,102).
  *   outputs: arrays of n_segments*seg_capacity entries (d_paths may be NULL); the first d_summary[0] are valid
- *   d_summary [16] u64: [0] records stored, [1] segments that overflowed, [2..9] counter block summed over segments,
- *                       [10] max records produced by one segment, [11] max candidates of one segment
+ *   d_summary [16] u64: [0] records stored, [1] segments that overflowed, [2..11] counter block summed over segments,
+ *                       [12] max records produced by one segment, [13] max candidates of one segment
  *   d_workspace: rfrt_records_workspace_bytes(n_segments*seg_capacity) bytes */
 RFRT_API int rfrt_records_sort(const void *d_segments, int64_t n_segments, int64_t seg_capacity, int32_t path_floats,
                       int64_t n_receivers, uint32_t *d_ray, int32_t *d_rx, int32_t *d_nverts, int64_t *d_bin,

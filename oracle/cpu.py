@@ -200,6 +200,24 @@ def max_threads():
     return int(lib().oracle_max_threads())
 
 
+class triangle_test:
+    """Context manager: which functor the restated mesh_query_ray runs — "woop" (the reference's watertight test,
+    default) or "mt" (Moeller-Trumbore, rfrt_oracle.c mt_tri)."""
+    KINDS = {"woop": 0, "mt": 1}
+
+    def __init__(self, kind):
+        self.kind = self.KINDS[kind]
+
+    def __enter__(self):
+        self.prev = int(lib().oracle_get_triangle_test())
+        lib().oracle_set_triangle_test(self.kind)
+        return self
+
+    def __exit__(self, *exc):
+        lib().oracle_set_triangle_test(self.prev)
+        return False
+
+
 def sphere_hits(tid_begin, n, tx, center, radius, cap=1 << 20, nthreads=0):
     """Ray ids whose generated direction hits the analytic sphere (KAT-1 helper)."""
     tx = np.ascontiguousarray(np.asarray(tx, dtype=np.float64)); center = np.ascontiguousarray(np.asarray(center, dtype=np.float64))

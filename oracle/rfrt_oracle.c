@@ -174,6 +174,7 @@ typedef struct {
     int kx, ky, kz;
     float Sx, Sy, Sz;
     float p[3];
+    float d[3]; /* the direction itself (Moeller-Trumbore functor) */
 } WoopRay;
 
 static inline void woop_setup(const float p[3], const float dir[3], WoopRay *r)
@@ -191,9 +192,10 @@ static inline void woop_setup(const float p[3], const float dir[3], WoopRay *r)
     r->Sy = dir[ky] / dir[kz];
     r->Sz = 1.0f / dir[kz];
     r->p[0] = p[0]; r->p[1] = p[1]; r->p[2] = p[2];
+    r->d[0] = dir[0]; r->d[1] = dir[1]; r->d[2] = dir[2];
 }
 
-static inline int woop_tri(const WoopRay *r, const float a[3], const float b[3], const float c[3], float *t_out)
+static inline int woop_tri_exact(const WoopRay *r, const float a[3], const float b[3], const float c[3], float *t_out)
 {
     const int kx = r->kx, ky = r->ky, kz = r->kz;
     const float Sx = r->Sx, Sy = r->Sy, Sz = r->Sz;
@@ -249,6 +251,42 @@ static inline int woop_tri(const WoopRay *r, const float a[3], const float b[3],
     float rcp_det = 1.0f / det;
     *t_out = T * rcp_det;
     return 1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Moeller-Trumbore functor (BASELINE.json north_star (2); SURVEY.md 7.3 "ship both functors").
+ * NOT the reference's arithmetic (Warp's mesh_query_ray runs the watertight test above): the
+ * classic two-sided test, no epsilon (det == 0 rejects), every operation a separate fp32
+ * rounding, dot products summed left to right.  Callers apply 0 <= t < best as for the
+ * watertight test.  The CUDA side (rfrt_math.cuh mt_hit) runs the same sequence.
+ * ---------------------------------------------------------------------------------------- */
+static inline int mt_tri(const WoopRay *r, const float a[3], const float b[3], const float c[3], float *t_out)
+{
+    const float *p = r->p, *d = r->d;
+    float e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+    float e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+    float pv[3] = {d[1] * e2[2] - d[2] * e2[1], d[2] * e2[0] - d[0] * e2[2], d[0] * e2[1] - d[1] * e2[0]};
+    float det = e1[0] * pv[0] + e1[1] * pv[1] + e1[2] * pv[2];
+    if (det == 0.0f || det != det) return 0;
+    float inv_det = 1.0f / det;
+    float tv[3] = {p[0] - a[0], p[1] - a[1], p[2] - a[2]};
+    float u = (tv[0] * pv[0] + tv[1] * pv[1] + tv[2] * pv[2]) * inv_det;
+    if (!(u >= 0.0f && u <= 1.0f)) return 0;
+    float qv[3] = {tv[1] * e1[2] - tv[2] * e1[1], tv[2] * e1[0] - tv[0] * e1[2], tv[0] * e1[1] - tv[1] * e1[0]};
+    float v = (d[0] * qv[0] + d[1] * qv[1] + d[2] * qv[2]) * inv_det;
+    if (!(v >= 0.0f && u + v <= 1.0f)) return 0;
+    *t_out = (e2[0] * qv[0] + e2[1] * qv[1] + e2[2] * qv[2]) * inv_det;
+    return 1;
+}
+
+/* which functor mesh_query_ray runs: 0 = watertight (reference-faithful, default), 1 = Moeller-Trumbore */
+static int g_tri_test = 0;
+ORACLE_API void oracle_set_triangle_test(int kind) { g_tri_test = kind; }
+ORACLE_API int oracle_get_triangle_test(void) { return g_tri_test; }
+
+static inline int woop_tri(const WoopRay *r, const float a[3], const float b[3], const float c[3], float *t_out)
+{
+    return g_tri_test ? mt_tri(r, a, b, c, t_out) : woop_tri_exact(r, a, b, c, t_out);
 }
 
 static inline int woop(const float p[3], const float dir[3], const float a[3], const float b[3], const float c[3],

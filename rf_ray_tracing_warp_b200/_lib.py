@@ -18,12 +18,12 @@ c_u64 = ctypes.c_uint64
 c_f = ctypes.c_float
 c_d = ctypes.c_double
 
-CTR_SEGMENTS, CTR_CANDIDATES, CTR_RECORDS, CTR_ENV_HITS, CTR_NEXT_RAY, CTR_NEXT_CAND, CTR_CHECKSUM, CTR_QUEUE_OVERFLOW, CTR_COUNT = \
-    0, 1, 2, 3, 4, 5, 6, 7, 8
+CTR_SEGMENTS, CTR_CANDIDATES, CTR_RECORDS, CTR_ENV_HITS, CTR_NEXT_RAY, CTR_NEXT_CAND, CTR_CHECKSUM, CTR_QUEUE_OVERFLOW, \
+    CTR_NODE_VISITS, CTR_TRI_TESTS, CTR_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 FLAG_NONE, FLAG_DIRS_READY, FLAG_FORCE_BVH, FLAG_CHECKSUM, FLAG_NO_RAY_SORT = 0, 1, 2, 8, 16
 SMALL_MAX_TRIS = 64
 # d_summary of rfrt_records_sort (u64[16])
-SUM_RECORDS, SUM_OVERFLOWED, SUM_COUNTERS, SUM_MAX_RECORDS, SUM_MAX_CANDIDATES, SUM_COUNT = 0, 1, 2, 10, 11, 16
+SUM_RECORDS, SUM_OVERFLOWED, SUM_COUNTERS, SUM_MAX_RECORDS, SUM_MAX_CANDIDATES, SUM_COUNT = 0, 1, 2, 12, 13, 16
 
 # name -> (restype, argtypes); mirrors include/rfrt.h one to one
 SIGNATURES = {

@@ -1,9 +1,12 @@
 // rfrt_bvh.cu — GPU LBVH builder (replaces wp.Mesh's BVH build, /root/reference tracer.py:24,30).
 //
-//   primitive boxes -> scene bounds -> 30-bit Morton code of the box centre, made unique by
-//   appending the primitive index (64-bit key) -> stable 8-bit LSD radix sort (4 passes over the
-//   Morton half; hand-written: per-tile histogram, exclusive scan, stable ranked scatter)
-//   -> Karras 2012 hierarchy emission -> bottom-up refit with per-node arrival counters.
+//   primitive boxes -> scene bounds -> 63-bit Morton code of the box centre (21 bits per axis, all three axes
+//   quantised with the SAME step = largest extent / 2^21, so the code's cells are cubes: a flat scene such as a
+//   heightfield is then split in x / y only until the cells are as small as its relief, instead of being cut into
+//   height bands at every third level) with the primitive index as the sort's value -> stable 8-bit LSD radix sort
+//   (8 passes; hand-written: per-tile histogram, exclusive scan, stable ranked scatter) -> Karras 2012 hierarchy
+//   emission (equal codes are split by their position in the sorted order) -> bottom-up refit with per-node
+//   arrival counters.
 //
 // The hierarchy only accelerates the query: the hit rule (closest t, ties to the lowest triangle
 // index) is order independent, so any valid BVH returns the oracle's answer.
@@ -65,32 +68,35 @@ __global__ void k_bounds_decode(const int *bounds_enc, float *bounds)
     if (threadIdx.x < 6) bounds[threadIdx.x] = ordered_to_float(bounds_enc[threadIdx.x]);
 }
 
-__device__ __forceinline__ uint32_t expand_bits10(uint32_t v)
+__device__ __forceinline__ uint64_t expand_bits21(uint32_t v)
 {
-    v = (v * 0x00010001u) & 0xFF0000FFu;
-    v = (v * 0x00000101u) & 0x0F00F00Fu;
-    v = (v * 0x00000011u) & 0xC30C30C3u;
-    v = (v * 0x00000005u) & 0x49249249u;
-    return v;
+    uint64_t x = v & 0x1fffffu;
+    x = (x | (x << 32)) & 0x001f00000000ffffull;
+    x = (x | (x << 16)) & 0x001f0000ff0000ffull;
+    x = (x | (x << 8)) & 0x100f00f00f00f00full;
+    x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
 }
 
 __global__ void k_morton(const float4 *__restrict__ lo, const float4 *__restrict__ hi, int64_t n,
-                         const float *__restrict__ bounds, uint64_t *__restrict__ keys)
+                         const float *__restrict__ bounds, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 a = lo[i], b = hi[i];
     float c[3] = {0.5f * (a.x + b.x), 0.5f * (a.y + b.y), 0.5f * (a.z + b.z)};
+    const float ext = fmaxf(fmaxf(bounds[3] - bounds[0], bounds[4] - bounds[1]), bounds[5] - bounds[2]);
+    const float scale = ext > 0.0f ? 2097152.0f / ext : 0.0f;
     uint32_t q[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        float ext = bounds[3 + k] - bounds[k];
-        float u = ext > 0.0f ? (c[k] - bounds[k]) / ext : 0.0f;
-        u = fminf(fmaxf(u * 1024.0f, 0.0f), 1023.0f);
+        float u = (c[k] - bounds[k]) * scale;
+        u = fminf(fmaxf(u, 0.0f), 2097151.0f); // (NaN -> 0)
         q[k] = (uint32_t)u;
     }
-    uint32_t m = (expand_bits10(q[0]) << 2) | (expand_bits10(q[1]) << 1) | expand_bits10(q[2]);
-    keys[i] = ((uint64_t)m << 32) | (uint64_t)(uint32_t)i;
+    keys[i] = (expand_bits21(q[0]) << 2) | (expand_bits21(q[1]) << 1) | expand_bits21(q[2]);
+    vals[i] = (uint32_t)i;
 }
 
 // ---- radix sort ------------------------------------------------------------------------------
@@ -155,9 +161,12 @@ __global__ void __launch_bounds__(256) k_scan_totals(uint32_t *row_tot)
     row_tot[threadIdx.x] = s[threadIdx.x];
 }
 
+// VALS: a 32-bit value travels with every key
+template <bool VALS>
 __global__ void __launch_bounds__(SORT_THREADS)
 k_sort_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int64_t n, int shift,
-               const uint32_t *__restrict__ gscan, const uint32_t *__restrict__ row_base, int nblocks)
+               const uint32_t *__restrict__ gscan, const uint32_t *__restrict__ row_base, int nblocks,
+               const uint32_t *__restrict__ vin, uint32_t *__restrict__ vout)
 {
     __shared__ uint32_t base[256];
     __shared__ uint32_t cnt[SORT_THREADS / 32][256];
@@ -180,6 +189,7 @@ k_sort_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int6
             uint32_t off = base[d];
             for (int w = 0; w < warp; ++w) off += cnt[w][d];
             out[off + rank] = key;
+            if (VALS) vout[off + rank] = vin[i];
         }
         __syncthreads();
         uint32_t s = 0;
@@ -193,7 +203,8 @@ k_sort_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int6
 __device__ __forceinline__ int delta(const uint64_t *__restrict__ keys, int n, int i, int j)
 {
     if (j < 0 || j >= n) return -1;
-    return __clzll((long long)(keys[i] ^ keys[j]));
+    const uint64_t x = keys[i] ^ keys[j];
+    return x ? __clzll((long long)x) : 64 + __clz(i ^ j); // equal codes: split by position in the sorted order
 }
 
 // children[i] = (c0, c1) for internal node i; parent arrays for the refit
@@ -244,14 +255,14 @@ __device__ __forceinline__ void load_child_box(const BvhNode *node, int slot, fl
     lo[0] = f[o + 0]; lo[1] = f[o + 1]; lo[2] = f[o + 2]; hi[0] = f[o + 3]; hi[1] = f[o + 4]; hi[2] = f[o + 5];
 }
 
-__global__ void k_refit(const uint64_t *__restrict__ keys, int n, const float4 *__restrict__ prim_lo,
+__global__ void k_refit(const uint32_t *__restrict__ order, int n, const float4 *__restrict__ prim_lo,
                         const float4 *__restrict__ prim_hi, float pad, const int2 *__restrict__ children,
                         const int *__restrict__ node_parent, const int *__restrict__ leaf_parent,
                         int *__restrict__ arrive, BvhNode *nodes, int *max_depth)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t prim = (uint32_t)(keys[i] & 0xffffffffull);
+    uint32_t prim = order[i];
     float4 a = prim_lo[prim], b = prim_hi[prim];
     float lo[3] = {a.x - pad, a.y - pad, a.z - pad};
     float hi[3] = {b.x + pad, b.y + pad, b.z + pad};
@@ -312,12 +323,6 @@ __global__ void k_single_prim_node(const float4 *prim_lo, const float4 *prim_hi,
     nodes[0] = nd;
 }
 
-__global__ void k_prim_order(const uint64_t *__restrict__ keys, int64_t n, int32_t *__restrict__ order)
-{
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) order[i] = (int32_t)(keys[i] & 0xffffffffull);
-}
-
 } // namespace
 
 // (stream-ordered frees on the stream the hierarchy was built on — no device-wide synchronisation as with cudaFree, and
@@ -358,6 +363,7 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
     }
     const int nblocks = (int)((n + SORT_TILE - 1) / SORT_TILE);
     uint64_t *keys_a = nullptr, *keys_b = nullptr;
+    uint32_t *vals_b = nullptr;
     uint32_t *ghist = nullptr;
     int *bounds_enc = nullptr, *node_parent = nullptr, *leaf_parent = nullptr, *arrive = nullptr, *d_depth = nullptr;
     float *d_bounds = nullptr;
@@ -367,6 +373,7 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
     Temporaries tmp; // (out->nodes / out->prim_order belong to the caller's Bvh: free_bvh)
     RFRT_CUDA(tmp.alloc_async(&keys_a, sizeof(uint64_t) * n, stream));
     RFRT_CUDA(tmp.alloc_async(&keys_b, sizeof(uint64_t) * n, stream));
+    RFRT_CUDA(tmp.alloc_async(&vals_b, sizeof(uint32_t) * n, stream));
     RFRT_CUDA(tmp.alloc_async(&ghist, sizeof(uint32_t) * 256 * ((size_t)nblocks + 1), stream));
     RFRT_CUDA(tmp.alloc_async(&bounds_enc, sizeof(int) * 8, stream));
     RFRT_CUDA(tmp.alloc_async(&d_bounds, sizeof(float) * 8, stream));
@@ -389,18 +396,21 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
     for (int k = 0; k < 6; ++k) m = fmaxf(m, fabsf(out->bounds[k]));
     out->pad = fmaxf(1.0e-3f, 1.0e-5f * m);
 
-    k_morton<<<nb, T, 0, stream>>>(d_lo, d_hi, n, d_bounds, keys_a);
+    // values: the primitive index; ping-pongs between out->prim_order and vals_b and ends in out->prim_order
+    uint32_t *order = reinterpret_cast<uint32_t *>(out->prim_order);
+    k_morton<<<nb, T, 0, stream>>>(d_lo, d_hi, n, d_bounds, keys_a, order);
     uint64_t *src = keys_a, *dst = keys_b;
-    for (int pass = 0; pass < 4; ++pass) {
-        int shift = 32 + 8 * pass;
+    uint32_t *vsrc = order, *vdst = vals_b;
+    for (int pass = 0; pass < 8; ++pass) {
+        int shift = 8 * pass;
         k_sort_hist<<<nblocks, SORT_THREADS, 0, stream>>>(src, n, shift, ghist, nblocks);
         k_scan_rows<<<256, 256, 0, stream>>>(ghist, nblocks, ghist + 256ll * nblocks);
         k_scan_totals<<<1, 256, 0, stream>>>(ghist + 256ll * nblocks);
-        k_sort_scatter<<<nblocks, SORT_THREADS, 0, stream>>>(src, dst, n, shift, ghist, ghist + 256ll * nblocks, nblocks);
-        uint64_t *tmp = src; src = dst; dst = tmp;
+        k_sort_scatter<true><<<nblocks, SORT_THREADS, 0, stream>>>(src, dst, n, shift, ghist, ghist + 256ll * nblocks, nblocks, vsrc, vdst);
+        uint64_t *tmpk = src; src = dst; dst = tmpk;
+        uint32_t *tmpv = vsrc; vsrc = vdst; vdst = tmpv;
     }
-    // after 4 passes the sorted keys are back in keys_a (src)
-    k_prim_order<<<nb, T, 0, stream>>>(src, n, out->prim_order);
+    // after 8 passes the sorted codes are back in keys_a (src) and the sorted primitive indices in out->prim_order
     RFRT_CUDA(cudaMemsetAsync(d_depth, 0, sizeof(int), stream));
     if (n == 1) {
         k_single_prim_node<<<1, 1, 0, stream>>>(d_lo, d_hi, out->pad, out->nodes);
@@ -408,7 +418,7 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
     } else {
         RFRT_CUDA(cudaMemsetAsync(arrive, 0, sizeof(int) * n_nodes, stream));
         k_karras<<<(int)((n - 1 + T - 1) / T), T, 0, stream>>>(src, (int)n, children, node_parent, leaf_parent);
-        k_refit<<<nb, T, 0, stream>>>(src, (int)n, d_lo, d_hi, out->pad, children, node_parent, leaf_parent, arrive,
+        k_refit<<<nb, T, 0, stream>>>(order, (int)n, d_lo, d_hi, out->pad, children, node_parent, leaf_parent, arrive,
                                       out->nodes, d_depth);
         k_depth<<<nb, T, 0, stream>>>((int)n, node_parent, leaf_parent, d_depth);
         RFRT_CUDA(cudaMemcpyAsync(&out->max_depth, d_depth, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -433,7 +443,7 @@ uint64_t *radix_sort_u64(uint64_t *a, uint64_t *b, uint32_t *hist, int64_t n, in
         k_sort_hist<<<nblocks, SORT_THREADS, 0, stream>>>(src, n, sh, hist, nblocks);
         k_scan_rows<<<256, 256, 0, stream>>>(hist, nblocks, hist + 256ll * nblocks);
         k_scan_totals<<<1, 256, 0, stream>>>(hist + 256ll * nblocks);
-        k_sort_scatter<<<nblocks, SORT_THREADS, 0, stream>>>(src, dst, n, sh, hist, hist + 256ll * nblocks, nblocks);
+        k_sort_scatter<false><<<nblocks, SORT_THREADS, 0, stream>>>(src, dst, n, sh, hist, hist + 256ll * nblocks, nblocks, nullptr, nullptr);
         uint64_t *tmp = src; src = dst; dst = tmp;
     }
     return src;

@@ -226,6 +226,55 @@ __device__ __forceinline__ bool woop_hit_mem(const WoopRay &r, const float *a, c
                              __fsub_rn(__ldg(c + r.kx), r.pkx), __fsub_rn(__ldg(c + r.ky), r.pky), __fsub_rn(__ldg(c + r.kz), r.pkz), t_out);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Moeller-Trumbore functor (BASELINE.json north_star (2); SURVEY.md 7.3 "ship both functors"; selected per mesh with
+// rfrt_mesh_set_triangle_test).  NOT the reference's arithmetic — Warp's mesh_query_ray runs the watertight test
+// above — but the classic two-sided test without an epsilon (det == 0 rejects), every operation a separate fp32
+// rounding, dot products summed left to right: the same sequence as oracle/rfrt_oracle.c mt_tri.
+// ---------------------------------------------------------------------------------------------
+struct MtRay {
+    float px, py, pz, dx, dy, dz;
+};
+
+__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+}
+
+__device__ __forceinline__ bool mt_hit(const MtRay &r, float3 a, float3 b, float3 c, float &t_out)
+{
+    const float e1x = __fsub_rn(b.x, a.x), e1y = __fsub_rn(b.y, a.y), e1z = __fsub_rn(b.z, a.z);
+    const float e2x = __fsub_rn(c.x, a.x), e2y = __fsub_rn(c.y, a.y), e2z = __fsub_rn(c.z, a.z);
+    const float pvx = __fsub_rn(__fmul_rn(r.dy, e2z), __fmul_rn(r.dz, e2y));
+    const float pvy = __fsub_rn(__fmul_rn(r.dz, e2x), __fmul_rn(r.dx, e2z));
+    const float pvz = __fsub_rn(__fmul_rn(r.dx, e2y), __fmul_rn(r.dy, e2x));
+    const float det = dot3_rn(e1x, e1y, e1z, pvx, pvy, pvz);
+    if (det == 0.0f || det != det) return false;
+    const float inv_det = __fdiv_rn(1.0f, det);
+    const float tvx = __fsub_rn(r.px, a.x), tvy = __fsub_rn(r.py, a.y), tvz = __fsub_rn(r.pz, a.z);
+    const float u = __fmul_rn(dot3_rn(tvx, tvy, tvz, pvx, pvy, pvz), inv_det);
+    if (!(u >= 0.0f && u <= 1.0f)) return false;
+    const float qvx = __fsub_rn(__fmul_rn(tvy, e1z), __fmul_rn(tvz, e1y));
+    const float qvy = __fsub_rn(__fmul_rn(tvz, e1x), __fmul_rn(tvx, e1z));
+    const float qvz = __fsub_rn(__fmul_rn(tvx, e1y), __fmul_rn(tvy, e1x));
+    const float v = __fmul_rn(dot3_rn(r.dx, r.dy, r.dz, qvx, qvy, qvz), inv_det);
+    if (!(v >= 0.0f && __fadd_rn(u, v) <= 1.0f)) return false;
+    t_out = __fmul_rn(dot3_rn(e2x, e2y, e2z, qvx, qvy, qvz), inv_det);
+    return true;
+}
+
+// The functor is chosen by the type of the per-ray constants: WoopRay (watertight, reference-faithful) or MtRay.
+template <class RAY> __device__ __forceinline__ RAY tri_ray_setup(float3 p, float3 d);
+template <> __device__ __forceinline__ WoopRay tri_ray_setup<WoopRay>(float3 p, float3 d) { return woop_setup(p, d); }
+template <> __device__ __forceinline__ MtRay tri_ray_setup<MtRay>(float3 p, float3 d)
+{
+    MtRay r;
+    r.px = p.x; r.py = p.y; r.pz = p.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
+    return r;
+}
+__device__ __forceinline__ bool tri_hit(const WoopRay &r, float3 a, float3 b, float3 c, float &t) { return woop_hit(r, a, b, c, t); }
+__device__ __forceinline__ bool tri_hit(const MtRay &r, float3 a, float3 b, float3 c, float &t) { return mt_hit(r, a, b, c, t); }
+
 // normalize(cross(b-a, c-a)); zero vector when degenerate  (normal returned by mesh_query_ray)
 __device__ __forceinline__ float3 tri_normal(float3 a, float3 b, float3 c)
 {

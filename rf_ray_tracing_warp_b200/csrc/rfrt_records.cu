@@ -109,15 +109,15 @@ k_rec_keys(const unsigned char *__restrict__ segs, int64_t n_seg, int64_t seg_by
     }
     if (blockIdx.x == 0 && threadIdx.x < SEG_HEADER_U64) {
         // [0] records stored, [1] segments that overflowed, [2 .. 2+CTR_COUNT) counters summed over segments,
-        // [10] / [11] largest record / candidate count of one segment (the capacities every rank needs)
+        // [12] / [13] largest record / candidate count of one segment (the capacities every rank needs)
         unsigned long long v = 0ull;
         for (int64_t s = 0; s < n_seg; ++s) {
             const unsigned long long *h = reinterpret_cast<const unsigned long long *>(segs + s * seg_bytes);
             if (threadIdx.x == 0) v += h[0] < h[1] ? h[0] : h[1];
             else if (threadIdx.x == 1) v += h[0] > h[1] ? 1ull : 0ull;
             else if (threadIdx.x < 2 + RFRT_CTR_COUNT) v += h[threadIdx.x];
-            else if (threadIdx.x == 10) v = h[0] > v ? h[0] : v;
-            else if (threadIdx.x == 11) v = h[2 + RFRT_CTR_CANDIDATES] > v ? h[2 + RFRT_CTR_CANDIDATES] : v;
+            else if (threadIdx.x == 2 + RFRT_CTR_COUNT) v = h[0] > v ? h[0] : v;
+            else if (threadIdx.x == 3 + RFRT_CTR_COUNT) v = h[2 + RFRT_CTR_CANDIDATES] > v ? h[2 + RFRT_CTR_CANDIDATES] : v;
         }
         summary[threadIdx.x] = v;
     }

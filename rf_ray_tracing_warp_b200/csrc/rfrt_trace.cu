@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
     int bounce = 0;
     bool entered = false; // the current segment is known to enter the scene's bounding box
     int64_t ray = 0;
-    unsigned int n_seg = 0, n_hit = 0;
+    unsigned int n_seg = 0, n_hit = 0, n_nodes = 0, n_tests = 0;
     unsigned long long csum = 0ull;
 
     // rays are handed out in blocks per warp: one atomic per block instead of one per trip
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
                 resolved = !entered; // outside the box: a miss (h stays empty)
             } else {
                 const WoopRay wr = woop_setup(pos, dir);
-                closest_hit(P.nodes, P.tris, P.n_tris, wr, sr_env, stack, stack_t, STRIDE, h);
+                closest_hit<DUMP>(P.nodes, P.tris, P.n_tris, wr, sr_env, stack, stack_t, STRIDE, h, -1, &n_nodes, &n_tests);
             }
             seg_done = resolved;
         }
@@ -377,8 +377,17 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
         atomicAdd(&P.counters[RFRT_CTR_ENV_HITS], (unsigned long long)n_hit);
     }
     if (DUMP) {
-        for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(FULL, csum, o);
-        if (lane == 0) atomicAdd(&P.counters[RFRT_CTR_CHECKSUM], csum);
+        unsigned long long nn = n_nodes, nt = n_tests;
+        for (int o = 16; o > 0; o >>= 1) {
+            csum += __shfl_xor_sync(FULL, csum, o);
+            nn += __shfl_xor_sync(FULL, nn, o);
+            nt += __shfl_xor_sync(FULL, nt, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&P.counters[RFRT_CTR_CHECKSUM], csum);
+            atomicAdd(&P.counters[RFRT_CTR_NODE_VISITS], nn);
+            atomicAdd(&P.counters[RFRT_CTR_TRI_TESTS], nt);
+        }
     }
 }
 

@@ -119,13 +119,15 @@ __device__ __forceinline__ int node_step(const BvhNode *__restrict__ nodes, int 
 
 // test the triangle of one leaf (closest t, 0 <= t < best; equal t -> lowest triangle index), then pop
 // (skip: a triangle index the query ignores — physical mode's "the triangle just left"; -1 = none)
-__device__ __forceinline__ int leaf_step(const BvhTri *__restrict__ tris, int node, const WoopRay &wr, Hit &h,
+// (RAY: WoopRay = the reference's watertight functor, MtRay = Moeller-Trumbore; rfrt_math.cuh)
+template <class RAY>
+__device__ __forceinline__ int leaf_step(const BvhTri *__restrict__ tris, int node, const RAY &wr, Hit &h,
                                          int *stack, float *stack_t, int stride, int &sp, int skip = -1)
 {
     const int slot = ~node;
     float3 a, b, c; int idx; float t;
     tri_vertices(tris, slot, a, b, c, idx);
-    if (idx != skip && woop_hit(wr, a, b, c, t) && t >= 0.0f && (t < h.t || (t == h.t && h.face >= 0 && idx < h.face))) {
+    if (idx != skip && tri_hit(wr, a, b, c, t) && t >= 0.0f && (t < h.t || (t == h.t && h.face >= 0 && idx < h.face))) {
         h.t = t; h.face = idx; h.slot = slot;
     }
     return stack_pop(stack, stack_t, stride, sp, h.t);
@@ -137,15 +139,24 @@ __device__ __forceinline__ int leaf_step(const BvhTri *__restrict__ tris, int no
 // lanes holding one test their triangles together.  Each loop has ONE back-edge so the warp re-converges on
 // every trip (several `continue` back-edges let sub-groups of lanes run the loop separately: measured 6/32
 // lanes active; testing leaves inside the node loop: 3/32 active in the triangle test).
+// COUNT: also count the internal nodes fetched and the triangles tested (RFRT_CTR_NODE_VISITS / RFRT_CTR_TRI_TESTS)
+template <bool COUNT = false, class RAY = WoopRay>
 __device__ __forceinline__ void closest_hit(const BvhNode *__restrict__ nodes, const BvhTri *__restrict__ tris,
-                                            int64_t n_prims, const WoopRay &wr, const SlabRay &sr, int *stack,
-                                            float *stack_t, int stride, Hit &h, int skip = -1)
+                                            int64_t n_prims, const RAY &wr, const SlabRay &sr, int *stack,
+                                            float *stack_t, int stride, Hit &h, int skip = -1,
+                                            unsigned *n_nodes = nullptr, unsigned *n_tests = nullptr)
 {
     int sp = 0;
     int node = n_prims > 0 ? 0 : TRAV_DONE;
     while (node != TRAV_DONE) {
-        while (node >= 0) node = node_step(nodes, node, sr, h.t, stack, stack_t, stride, sp);
-        if (node != TRAV_DONE) node = leaf_step(tris, node, wr, h, stack, stack_t, stride, sp, skip);
+        while (node >= 0) {
+            node = node_step(nodes, node, sr, h.t, stack, stack_t, stride, sp);
+            if (COUNT) ++*n_nodes;
+        }
+        if (node != TRAV_DONE) {
+            node = leaf_step(tris, node, wr, h, stack, stack_t, stride, sp, skip);
+            if (COUNT) ++*n_tests;
+        }
     }
 }
 
@@ -501,7 +512,8 @@ struct RxView {
 // [0, max_t) over ALL faces.  The faces actually tested are pruned with the unit-space BVH (boxes inflated by
 // 4e-3 of the radius; t is the same parameter in both spaces); every triangle test itself is the exact
 // world-space Woop test, so the result equals the brute-force minimum.
-__device__ __forceinline__ bool rx_query(const RxView &rx, const uint8_t *faces, int n_faces, const WoopRay &wr,
+template <class RAY>
+__device__ __forceinline__ bool rx_query(const RxView &rx, const uint8_t *faces, int n_faces, const RAY &wr,
                                          float3 pos, float3 dir, float max_t, int *stack, float *stack_t, int stride,
                                          float &t_out)
 {
@@ -522,7 +534,7 @@ __device__ __forceinline__ bool rx_query(const RxView &rx, const uint8_t *faces,
             float3 b = make_float3(__ldg(v + 3 * i1), __ldg(v + 3 * i1 + 1), __ldg(v + 3 * i1 + 2));
             float3 c = make_float3(__ldg(v + 3 * i2), __ldg(v + 3 * i2 + 1), __ldg(v + 3 * i2 + 2));
             float t;
-            if (woop_hit(wr, a, b, c, t) && t < best && t >= 0.0f) best = t;
+            if (tri_hit(wr, a, b, c, t) && t < best && t >= 0.0f) best = t;
         }
     }
     while (node != TRAV_DONE) {
@@ -535,7 +547,7 @@ __device__ __forceinline__ bool rx_query(const RxView &rx, const uint8_t *faces,
             float3 b = make_float3(__ldg(v + 3 * i1), __ldg(v + 3 * i1 + 1), __ldg(v + 3 * i1 + 2));
             float3 c = make_float3(__ldg(v + 3 * i2), __ldg(v + 3 * i2 + 1), __ldg(v + 3 * i2 + 2));
             float t;
-            if (woop_hit(wr, a, b, c, t) && t < best && t >= 0.0f) best = t;
+            if (tri_hit(wr, a, b, c, t) && t < best && t >= 0.0f) best = t;
             node = stack_pop(stack, stack_t, stride, sp, best);
         }
     }

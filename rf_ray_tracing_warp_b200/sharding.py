@@ -6,6 +6,7 @@ import numpy as np
 import torch
 
 SEG_HEADER_U64 = 16
+CTR_COUNT = 10  # include/rfrt.h RFRT_CTR_COUNT
 
 
 def ray_range(n_rays, rank, world):
@@ -56,7 +57,7 @@ def read_segments(buffer, n_segments, capacity, path_floats):
         seg = raw[s]
         header = seg[: 8 * SEG_HEADER_U64].view(np.uint64)
         n = int(min(header[0], header[1]))
-        d = dict(produced=int(header[0]), fit=int(header[1]), counters=header[2:10].copy())
+        d = dict(produced=int(header[0]), fit=int(header[1]), counters=header[2:2 + CTR_COUNT].copy())
         for name, dt in _SECTION_DTYPES.items():
             d[name] = seg[lay[name]: lay[name] + n * np.dtype(dt).itemsize].view(dt).copy()
         if path_floats:
@@ -73,7 +74,7 @@ def write_segment(records, counters, capacity, path_floats):
     n = min(produced, capacity)
     header = seg[: 8 * SEG_HEADER_U64].view(np.uint64)
     header[0], header[1] = produced, capacity
-    header[2:10] = np.asarray(counters, dtype=np.uint64)
+    header[2:2 + CTR_COUNT] = np.asarray(counters, dtype=np.uint64)
     for name, dt in _SECTION_DTYPES.items():
         seg[lay[name]: lay[name] + n * np.dtype(dt).itemsize] = np.ascontiguousarray(records[name][:n], dtype=dt).view(np.uint8)
     if path_floats:

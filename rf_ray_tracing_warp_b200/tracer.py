@@ -156,6 +156,7 @@ class Tracer:
         out = dict(segments=int(c[_lib.CTR_SEGMENTS]), env_hits=int(c[_lib.CTR_ENV_HITS]))
         if checksum or dump:
             out["checksum"] = int(c[_lib.CTR_CHECKSUM]) & 0xFFFFFFFFFFFFFFFF
+            out["node_visits"], out["tri_tests"] = int(c[_lib.CTR_NODE_VISITS]), int(c[_lib.CTR_TRI_TESTS])  # BVH scenes
         if dump:
             out.update(hit_tri=hit_tri, hit_t=hit_t)
         return out

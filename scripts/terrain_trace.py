@@ -28,3 +28,6 @@ for it in range(3):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     print(f"trace: {out['segments']} segments, {out['env_hits']} hits in {ms:.1f} ms -> {out['segments'] / ms * 1e3:.3e} segments/s")
+out = tr.trace_segments(tx, checksum=True)
+print(f"checksum {out['checksum']:016x}; per segment: {out['node_visits'] / out['segments']:.2f} internal nodes fetched, "
+      f"{out['tri_tests'] / out['segments']:.2f} triangles tested")

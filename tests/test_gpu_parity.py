@@ -97,7 +97,7 @@ def test_terrain_trajectory_bit_exact(torch_cuda):
     soup = mesh.triangles.astype(np.float32)
     n, B, tx = 1 << 17, 6, [10, 0, 4.5]
     tr = _tracer(mesh, B, n)
-    assert tr.mesh_info()["max_depth"] > 16
+    assert tr.mesh_info()["max_depth"] + 2 > 16  # rfrt_trace: stack depth = tree depth + 2 > 16 -> local-memory stack
     out = tr.trace_segments(tx, dump=True)
     seg, tri, t = cpu.trace_env(soup, tx, B, 0, n, bvh=cpu.Bvh(soup))
     assert out["segments"] == seg and (tri[:, 1] >= 0).sum() > 100

@@ -43,7 +43,7 @@ def _worker(rank, world, port, n_rays, out_dir):
     torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
     from rf_ray_tracing_warp_b200 import sharding
     begin, end = sharding.ray_range(n_rays, rank, world)
-    counters = [end - begin, 11 * (rank + 1), 0, 5, 0, 0, 0, 0]
+    counters = [end - begin, 11 * (rank + 1), 0, 5, 0, 0, 0, 0, 0, 0]
     local = torch.from_numpy(sharding.write_segment(_fake_records(begin, end), counters, CAP, ROW))
     gathered = torch.empty(world * local.numel(), dtype=torch.uint8)
     sharding.exchange_segments(gathered, local)
@@ -61,7 +61,7 @@ def test_two_rank_segment_exchange(tmp_path):
     outs = [torch.load(os.path.join(tmp_path, f"r{r}.pt")) for r in range(world)]
     assert outs[0]["range"][0] == 0 and outs[0]["range"][1] == outs[1]["range"][0] and outs[1]["range"][1] == n_rays
     assert torch.equal(outs[0]["gathered"], outs[1]["gathered"])
-    single = _merge(sharding.read_segments(sharding.write_segment(_fake_records(0, n_rays), [0] * 8, 2 * CAP, ROW), 1, 2 * CAP, ROW))
+    single = _merge(sharding.read_segments(sharding.write_segment(_fake_records(0, n_rays), [0] * sharding.CTR_COUNT, 2 * CAP, ROW), 1, 2 * CAP, ROW))
     for o in outs:
         assert o["stats"]["segments"] == n_rays and o["stats"]["rank_sum"] == 1
         segs = sharding.read_segments(o["gathered"], world, CAP, ROW)
@@ -78,7 +78,7 @@ def test_two_rank_segment_exchange(tmp_path):
 def test_segment_overflow_is_visible():
     from rf_ray_tracing_warp_b200 import sharding
     rec = _fake_records(0, 5000)
-    seg = sharding.read_segments(sharding.write_segment(rec, [0] * 8, 100, 0), 1, 100, 0)[0]
+    seg = sharding.read_segments(sharding.write_segment(rec, [0] * sharding.CTR_COUNT, 100, 0), 1, 100, 0)[0]
     assert seg["produced"] == len(rec["ray"]) > seg["fit"] == 100 and len(seg["ray"]) == 100
 
 
