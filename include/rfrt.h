@@ -101,6 +101,18 @@ RFRT_API int rfrt_mesh_reserve_rays(rfrt_handle mesh, int64_t max_chunk_rays);
  * _bounce_amplitude; with a table the triangle of each path vertex supplies n_1 (receiver vertices keep 5.0).
  *   d_refractive_index : [n_triangles] float32 (device; copied), or NULL to restore the reference's constant. */
 RFRT_API int rfrt_mesh_set_materials(rfrt_handle mesh, const float *d_refractive_index, void *stream);
+/* The ray/triangle functor behind every closest-hit query on this mesh and on the receivers traced against it
+ * (the `mesh_query_ray` of kernel.py:71,82):
+ *   RFRT_TRI_TEST_WOOP (default) the watertight Woop/Benthin/Wald test in the operation order of Warp's
+ *                      intersect_ray_tri_woop — the reference's arithmetic, bit-exact against the oracle;
+ *   RFRT_TRI_TEST_MT   Moeller-Trumbore (two-sided, no epsilon, one fp32 rounding per operation), bit-exact against
+ *                      the oracle's mt_tri.  NOT reference behaviour: the two functors round differently, so rays
+ *                      that graze an edge or re-hit their own triangle at t ~ 0 diverge (DESIGN.md reports the rate).
+ *                      Scenes of <= 64 triangles walk the BVH in this mode (the lockstep sweep's filter is derived
+ *                      for the watertight test); rfrt_trace_physical rejects such a mesh. */
+#define RFRT_TRI_TEST_WOOP 0
+#define RFRT_TRI_TEST_MT 1
+RFRT_API int rfrt_mesh_set_triangle_test(rfrt_handle mesh, int32_t kind);
 /* bounds6 = {lo.xyz, hi.xyz} (unpadded); any output pointer may be NULL. */
 RFRT_API int rfrt_mesh_info(rfrt_handle mesh, int64_t *n_triangles, int64_t *n_nodes, float *h_bounds6,
                    int32_t *max_depth, float *build_ms);

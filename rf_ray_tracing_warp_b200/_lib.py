@@ -22,6 +22,7 @@ CTR_SEGMENTS, CTR_CANDIDATES, CTR_RECORDS, CTR_ENV_HITS, CTR_NEXT_RAY, CTR_NEXT_
     CTR_NODE_VISITS, CTR_TRI_TESTS, CTR_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 FLAG_NONE, FLAG_DIRS_READY, FLAG_FORCE_BVH, FLAG_CHECKSUM, FLAG_NO_RAY_SORT = 0, 1, 2, 8, 16
 SMALL_MAX_TRIS = 64
+TRI_TEST_WOOP, TRI_TEST_MT = 0, 1
 # d_summary of rfrt_records_sort (u64[16])
 SUM_RECORDS, SUM_OVERFLOWED, SUM_COUNTERS, SUM_MAX_RECORDS, SUM_MAX_CANDIDATES, SUM_COUNT = 0, 1, 2, 12, 13, 16
 
@@ -33,6 +34,7 @@ SIGNATURES = {
     "rfrt_mesh_create": (ctypes.c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, ctypes.POINTER(c_u64)]),
     "rfrt_mesh_destroy": (ctypes.c_int, [c_u64]),
     "rfrt_mesh_set_materials": (ctypes.c_int, [c_u64, c_void_p, c_void_p]),
+    "rfrt_mesh_set_triangle_test": (ctypes.c_int, [c_u64, c_i32]),
     "rfrt_mesh_info": (ctypes.c_int, [c_u64, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_f),
                                       ctypes.POINTER(c_i32), ctypes.POINTER(c_f)]),
     "rfrt_mesh_export": (ctypes.c_int, [c_u64, c_void_p, c_void_p, c_void_p]),

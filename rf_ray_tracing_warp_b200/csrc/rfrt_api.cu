@@ -273,6 +273,18 @@ extern "C" int rfrt_mesh_set_materials(rfrt_handle mesh, const float *d_refracti
     return RFRT_OK;
 }
 
+extern "C" int rfrt_mesh_set_triangle_test(rfrt_handle mesh, int32_t kind)
+{
+    Mesh *m = get_mesh(mesh);
+    if (!m) { set_error("rfrt_mesh_set_triangle_test: unknown handle"); return RFRT_ERR_HANDLE; }
+    if (kind != RFRT_TRI_TEST_WOOP && kind != RFRT_TRI_TEST_MT) {
+        set_error("rfrt_mesh_set_triangle_test: kind must be RFRT_TRI_TEST_WOOP or RFRT_TRI_TEST_MT");
+        return RFRT_ERR_INVALID;
+    }
+    m->tri_test = kind;
+    return RFRT_OK;
+}
+
 extern "C" int rfrt_mesh_info(rfrt_handle mesh, int64_t *n_triangles, int64_t *n_nodes, float *h_bounds6,
                               int32_t *max_depth, float *build_ms)
 {

@@ -12,6 +12,7 @@
 // index) is order independent, so any valid BVH returns the oracle's answer.
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "rfrt_internal.h"
@@ -80,7 +81,7 @@ __device__ __forceinline__ uint64_t expand_bits21(uint32_t v)
 }
 
 __global__ void k_morton(const float4 *__restrict__ lo, const float4 *__restrict__ hi, int64_t n,
-                         const float *__restrict__ bounds, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+                         const float *__restrict__ bounds, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int legacy)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -94,6 +95,16 @@ __global__ void k_morton(const float4 *__restrict__ lo, const float4 *__restrict
         float u = (c[k] - bounds[k]) * scale;
         u = fminf(fmaxf(u, 0.0f), 2097151.0f); // (NaN -> 0)
         q[k] = (uint32_t)u;
+    }
+    if (legacy) {
+        // round 1's code, kept for A/B measurements (RFRT_BVH_LEGACY_MORTON=1): 10 bits per axis, every axis
+        // normalised by its OWN extent (a heightfield is then cut into height bands at every third level)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float e = bounds[3 + k] - bounds[k];
+            const float u = e > 0.0f ? (c[k] - bounds[k]) / e : 0.0f;
+            q[k] = (uint32_t)fminf(fmaxf(u * 1024.0f, 0.0f), 1023.0f) << 11;
+        }
     }
     keys[i] = (expand_bits21(q[0]) << 2) | (expand_bits21(q[1]) << 1) | expand_bits21(q[2]);
     vals[i] = (uint32_t)i;
@@ -398,7 +409,8 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
 
     // values: the primitive index; ping-pongs between out->prim_order and vals_b and ends in out->prim_order
     uint32_t *order = reinterpret_cast<uint32_t *>(out->prim_order);
-    k_morton<<<nb, T, 0, stream>>>(d_lo, d_hi, n, d_bounds, keys_a, order);
+    static const int legacy_morton = getenv("RFRT_BVH_LEGACY_MORTON") ? atoi(getenv("RFRT_BVH_LEGACY_MORTON")) : 0;
+    k_morton<<<nb, T, 0, stream>>>(d_lo, d_hi, n, d_bounds, keys_a, order, legacy_morton);
     uint64_t *src = keys_a, *dst = keys_b;
     uint32_t *vsrc = order, *vdst = vals_b;
     for (int pass = 0; pass < 8; ++pass) {

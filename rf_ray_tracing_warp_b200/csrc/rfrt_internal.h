@@ -53,6 +53,7 @@ struct Mesh {
     int32_t small_class[5] = {0, 0, 0, 0, 0}; // pair ranges of the plane classes (general, x-, y-, z-aligned)
     float small_extent = 0.0f;
     float build_ms = 0.0f;
+    int32_t tri_test = 0;        // RFRT_TRI_TEST_WOOP (reference-faithful) / RFRT_TRI_TEST_MT (rfrt_mesh_set_triangle_test)
     float *materials = nullptr;  // [n] refractive index per triangle (rfrt_mesh_set_materials) or NULL = 5.0 everywhere
     // BVH scenes: workspace of the direction-coherent ray order (grown on demand by rfrt_trace, freed with the mesh)
     uint64_t *ray_keys[2] = {nullptr, nullptr};

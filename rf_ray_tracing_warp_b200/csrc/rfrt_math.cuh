@@ -230,7 +230,7 @@ __device__ __forceinline__ bool woop_hit_mem(const WoopRay &r, const float *a, c
 // Moeller-Trumbore functor (BASELINE.json north_star (2); SURVEY.md 7.3 "ship both functors"; selected per mesh with
 // rfrt_mesh_set_triangle_test).  NOT the reference's arithmetic — Warp's mesh_query_ray runs the watertight test
 // above — but the classic two-sided test without an epsilon (det == 0 rejects), every operation a separate fp32
-// rounding, dot products summed left to right: the same sequence as oracle/rfrt_oracle.c mt_tri.
+// rounding, dot products summed left to right (the CPU restatement under tests/ runs the same sequence).
 // ---------------------------------------------------------------------------------------------
 struct MtRay {
     float px, py, pz, dx, dy, dz;

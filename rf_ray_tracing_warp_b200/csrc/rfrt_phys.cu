@@ -254,6 +254,7 @@ extern "C" int rfrt_trace_physical(rfrt_handle env_mesh, rfrt_handle rxset, cons
     cudaStream_t stream = (cudaStream_t)stream_;
     Mesh *m = get_mesh(env_mesh);
     if (!m) { set_error("rfrt_trace_physical: unknown environment mesh handle"); return RFRT_ERR_HANDLE; }
+    if (m->tri_test != RFRT_TRI_TEST_WOOP) { set_error("rfrt_trace_physical: only the watertight triangle test is supported"); return RFRT_ERR_INVALID; }
     RxSet *r = nullptr;
     if (rxset) {
         r = get_rxset(rxset);

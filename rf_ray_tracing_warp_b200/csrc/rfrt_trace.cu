@@ -13,6 +13,8 @@
 //   k_trace_compat  kernel.py:38-98  the reference kernel's dense contract (tracer.py:75-79)
 //   k_query         test probe for closest_hit
 #include <cmath>
+#include <cstdlib>
+#include <type_traits>
 
 #include "rfrt_trace.cuh"
 
@@ -63,6 +65,8 @@ struct TraceParams {
     int64_t dump_begin;
     int32_t stack_depth;
     int32_t fetch_block; // rays a warp claims per atomic (32..256, sized so that every warp sees >= 64 blocks)
+    int32_t walk_refill;   // k_trace_walk: lanes waiting for phase A that end phase B
+    int32_t walk_node_min; // k_trace_walk: fewest lanes worth another node step while other lanes hold a triangle
     int32_t rx_coop;   // dense receiver sets: the warp enumerates its lanes' segments together (rx_enumerate_coop)
 };
 
@@ -255,9 +259,11 @@ __device__ __forceinline__ unsigned long long segment_hash(uint32_t gid, int bou
 // BVH scenes.  LSTACK: see above.
 // COOP: dense receiver sets — the warp enumerates its lanes' segments together (rx_enumerate_coop) at a converged point
 //       after the closest hit; otherwise every lane handles its own receivers right where its segment is finished
-template <bool DUMP, bool LSTACK, bool COOP>
+// MT: the Moeller-Trumbore functor instead of the reference's watertight test (rfrt_mesh_set_triangle_test)
+template <bool DUMP, bool LSTACK, bool COOP, bool MT>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P)
 {
+    using Ray = typename std::conditional<MT, MtRay, WoopRay>::type;
     extern __shared__ __align__(16) int s_stack_raw[];
     int l_stack[LSTACK ? 64 : 1];
     float l_stack_t[LSTACK ? 64 : 1];
@@ -329,7 +335,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
                 entered = slab_hit(sr_env, P.env_lo[0], P.env_lo[1], P.env_lo[2], P.env_hi[0], P.env_hi[1], P.env_hi[2], 1.0e6f, tn);
                 resolved = !entered; // outside the box: a miss (h stays empty)
             } else {
-                const WoopRay wr = woop_setup(pos, dir);
+                const Ray wr = tri_ray_setup<Ray>(pos, dir);
                 closest_hit<DUMP>(P.nodes, P.tris, P.n_tris, wr, sr_env, stack, stack_t, STRIDE, h, -1, &n_nodes, &n_tests);
             }
             seg_done = resolved;
@@ -368,6 +374,166 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P
     }
 
     // warp-reduced counters
+    for (int o = 16; o > 0; o >>= 1) {
+        n_seg += __shfl_xor_sync(FULL, n_seg, o);
+        n_hit += __shfl_xor_sync(FULL, n_hit, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&P.counters[RFRT_CTR_SEGMENTS], (unsigned long long)n_seg);
+        atomicAdd(&P.counters[RFRT_CTR_ENV_HITS], (unsigned long long)n_hit);
+    }
+    if (DUMP) {
+        unsigned long long nn = n_nodes, nt = n_tests;
+        for (int o = 16; o > 0; o >>= 1) {
+            csum += __shfl_xor_sync(FULL, csum, o);
+            nn += __shfl_xor_sync(FULL, nn, o);
+            nt += __shfl_xor_sync(FULL, nt, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&P.counters[RFRT_CTR_CHECKSUM], csum);
+            atomicAdd(&P.counters[RFRT_CTR_NODE_VISITS], nn);
+            atomicAdd(&P.counters[RFRT_CTR_TRI_TESTS], nt);
+        }
+    }
+}
+
+// BVH scenes, second schedule: the walk is decoupled from the trip.  In k_trace_env a trip is one segment per lane and
+// ends when the LONGEST of the warp's 32 walks ends (measured on the 20 M-triangle terrain: 10 of 32 lanes active — the
+// walk lengths of secondary rays vary from 3 to 200 nodes).  Here every lane keeps its traversal state (node, stack
+// pointer, best hit, per-ray constants) across the phases of one loop:
+//   phase A  lanes whose walk has ended finish their segment (counters, receivers, advance + reflect, kernel.py:85-96),
+//            take a fresh ray if theirs is dead, and start the next segment (scene-box test, per-ray constants);
+//   phase B  the warp walks — a node loop for the lanes that hold an internal node, a leaf step for the lanes that hold
+//            a triangle — until `refill` lanes are waiting for phase A again.
+// The node loop stops early for a leaf step only when fewer than `node_min` lanes would still take part in it.
+// Same per-segment functions as k_trace_env (closest hit, ties, reflect): the segments are identical, only their
+// schedule differs (checked by the segment checksum against the other kernels and the CPU restatement).
+template <bool DUMP, bool LSTACK, bool COOP, bool MT>
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_walk(const TraceParams P)
+{
+    using Ray = typename std::conditional<MT, MtRay, WoopRay>::type;
+    extern __shared__ __align__(16) int s_stack_raw[];
+    int l_stack[LSTACK ? 64 : 1];
+    float l_stack_t[LSTACK ? 64 : 1];
+    int *stack = LSTACK ? l_stack : s_stack_raw + threadIdx.x;
+    float *stack_t = LSTACK ? l_stack_t : reinterpret_cast<float *>(s_stack_raw + P.stack_depth * TRACE_THREADS) + threadIdx.x;
+    constexpr int STRIDE = LSTACK ? 1 : TRACE_THREADS;
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    int *rx_queue = s_stack_raw + 2 * P.stack_depth * TRACE_THREADS + (COOP ? RX_COOP_INTS * (threadIdx.x >> 5) : 0);
+    const int REFILL = P.walk_refill, NODE_MIN = P.walk_node_min;
+
+    bool has_ray = false;   // this lane owns a ray
+    bool walking = false;   // ... and a segment of it is under way (node == TRAV_DONE: finished, waits for phase A)
+    bool exhausted = false; // warp-uniform: no rays left to fetch
+    int node = TRAV_DONE, sp = 0;
+    float3 pos = make_float3(0.f, 0.f, 0.f), dir = make_float3(0.f, 0.f, 1.f);
+    int bounce = 0;
+    int64_t ray = 0;
+    Hit h;
+    h.t = 1.0e6f; h.face = -1; h.slot = -1;
+    Ray wr = tri_ray_setup<Ray>(pos, dir);
+    SlabRay sr = slab_setup(pos, dir);
+    unsigned int n_seg = 0, n_hit = 0, n_nodes = 0, n_tests = 0;
+    unsigned long long csum = 0ull;
+    const int FETCH_BLOCK = P.fetch_block;
+    int64_t blk_next = 0, blk_end = 0; // warp-uniform
+
+    for (;;) {
+        // ================= phase A: lanes that are not in the middle of a walk =================
+        const bool seg_done = has_ray && walking && node == TRAV_DONE;
+        // ---- receivers hit strictly before the environment, or at all if it is missed (kernel.py:71,85) ----
+        if (COOP)
+            receivers_coop(P, seg_done, pos, dir, h.face >= 0 ? h.t : 1.0e6f, (uint32_t)(P.chunk_begin + ray), bounce, rx_queue, lane);
+        if (seg_done) {
+            const bool hit_env = h.face >= 0;
+            ++n_seg;
+            if (!COOP && P.n_rx > 0)
+                receivers_lane(P, pos, dir, hit_env ? h.t : 1.0e6f, (uint32_t)(P.chunk_begin + ray), bounce, stack, STRIDE);
+            if (DUMP) {
+                int64_t row = (P.chunk_begin + ray - P.dump_begin) * P.max_bounces + bounce;
+                if (P.hit_tri) P.hit_tri[row] = hit_env ? h.face : -1;
+                if (P.hit_t) P.hit_t[row] = hit_env ? h.t : 0.0f;
+                csum += segment_hash((uint32_t)(P.chunk_begin + ray), bounce, hit_env ? h.face : -1, hit_env ? h.t : 0.0f);
+            }
+            walking = false;
+            if (hit_env) {
+                ++n_hit;
+                pos = advance(pos, dir, h.t);                 // kernel.py:94
+                const float4 n4 = __ldg(P.normals + h.slot);  // normalize(cross(b-a, c-a)), precomputed at build time
+                dir = reflect(dir, make_float3(n4.x, n4.y, n4.z)); // kernel.py:96
+                ++bounce;
+                if (bounce >= P.max_bounces) has_ray = false;
+            } else {
+                has_ray = false; // a miss repeats forever in the reference (kernel.py:97-98): nothing more to do
+            }
+        }
+        // ---- refill (rays are handed out in blocks per warp: one atomic per block; second pass: the block ran out) ----
+        {
+            unsigned idle = __ballot_sync(FULL, !has_ray);
+#pragma unroll 1
+            for (int pass = 0; pass < 2 && idle != 0u && !exhausted; ++pass) {
+                if (blk_next == blk_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(&P.counters[RFRT_CTR_NEXT_RAY], (unsigned long long)FETCH_BLOCK);
+                    base = __shfl_sync(FULL, base, 0);
+                    blk_next = (int64_t)base;
+                    blk_end = blk_next + FETCH_BLOCK < P.chunk_n ? blk_next + FETCH_BLOCK : P.chunk_n;
+                    if (blk_next >= P.chunk_n) { exhausted = true; blk_end = blk_next; }
+                }
+                if (!has_ray) {
+                    int64_t r = blk_next + __popc(idle & ((1u << lane) - 1u));
+                    if (r < blk_end) {
+                        if (P.order) r = (int64_t)(uint32_t)__ldg(P.order + r); // direction-coherent order
+                        float4 d4 = __ldg(P.dirs + r);
+                        dir = make_float3(d4.x, d4.y, d4.z);
+                        pos = P.tx;
+                        bounce = 0;
+                        ray = r;
+                        has_ray = true;
+                    }
+                }
+                blk_next = blk_next + __popc(idle) < blk_end ? blk_next + __popc(idle) : blk_end;
+                idle = __ballot_sync(FULL, !has_ray);
+            }
+        }
+        if (!__any_sync(FULL, has_ray)) break;
+        // ---- start the next segment: scene-box test first (a miss is a finished segment with no hit) ----
+        if (has_ray && !walking) {
+            sr = slab_setup(pos, dir);
+            float tn;
+            const bool entered = P.n_tris > 0 &&
+                                 slab_hit(sr, P.env_lo[0], P.env_lo[1], P.env_lo[2], P.env_hi[0], P.env_hi[1], P.env_hi[2], 1.0e6f, tn);
+            h.t = 1.0e6f; h.face = -1; h.slot = -1;
+            walking = true;
+            sp = 0;
+            node = entered ? 0 : TRAV_DONE;
+            if (entered) wr = tri_ray_setup<Ray>(pos, dir);
+        }
+        // ================= phase B: walk until enough lanes wait for phase A =================
+        for (;;) {
+            unsigned internal, waiting;
+            for (;;) {
+                internal = __ballot_sync(FULL, node >= 0);
+                // (a lane waits for phase A when its walk has ended and phase A has something for it)
+                waiting = __ballot_sync(FULL, node == TRAV_DONE && (has_ray || !exhausted));
+                const unsigned idle_all = __ballot_sync(FULL, node == TRAV_DONE);
+                const unsigned leaves = ~(internal | idle_all);
+                if (internal == 0u || __popc(waiting) >= REFILL || (leaves != 0u && __popc(internal) < NODE_MIN)) break;
+                if (node >= 0) {
+                    node = node_step(P.nodes, node, sr, h.t, stack, stack_t, STRIDE, sp);
+                    if (DUMP) ++n_nodes;
+                }
+            }
+            if (node < 0 && node != TRAV_DONE) {
+                node = leaf_step(P.tris, node, wr, h, stack, stack_t, STRIDE, sp);
+                if (DUMP) ++n_tests;
+            }
+            waiting = __ballot_sync(FULL, node == TRAV_DONE && (has_ray || !exhausted));
+            if (__popc(waiting) >= REFILL || __all_sync(FULL, node == TRAV_DONE)) break;
+        }
+    }
+
     for (int o = 16; o > 0; o >>= 1) {
         n_seg += __shfl_xor_sync(FULL, n_seg, o);
         n_hit += __shfl_xor_sync(FULL, n_hit, o);
@@ -562,7 +728,7 @@ struct LiteralEnv {
 
 // kernel.py:38-98 for one ray and one receiver.  Sink receives the vertex writes and RX-hit events.
 // s_recs: unit-space face records in shared memory (lockstep receiver query) or NULL (unit-BVH walk)
-template <class Sink>
+template <bool MT, class Sink>
 __device__ __forceinline__ void literal_trace(const LiteralEnv &E, const RxView *rx, int n_faces, float3 tx,
                                               int max_bounces, uint32_t tid, int *stack, float *stack_t, int stride,
                                               Sink &sink, const float4 *s_recs = nullptr)
@@ -582,12 +748,20 @@ __device__ __forceinline__ void literal_trace(const LiteralEnv &E, const RxView 
             sink.received(bounce);            // :89-91
             continue;
         }
-        WoopRay wr = woop_setup(pos, dir);
+        using Ray = typename std::conditional<MT, MtRay, WoopRay>::type;
+        const Ray wr = tri_ray_setup<Ray>(pos, dir);
         SlabRay sr = slab_setup(pos, dir);
         float t_rx = 0.0f;
         bool maybe_hit_rx = false; // :71
-        if (rx) maybe_hit_rx = s_recs ? rx_query_sweep(*rx, s_recs, c_rx_faces, n_faces, wr, pos, dir, 1.0e6f, t_rx)
+        if (rx) {
+            // (the lockstep receiver query's candidate filter is derived for the watertight test only)
+            if constexpr (!MT) {
+                maybe_hit_rx = s_recs ? rx_query_sweep(*rx, s_recs, c_rx_faces, n_faces, wr, pos, dir, 1.0e6f, t_rx)
                                       : rx_query(*rx, c_rx_faces, n_faces, wr, pos, dir, 1.0e6f, stack, stack_t, stride, t_rx);
+            } else {
+                maybe_hit_rx = rx_query(*rx, c_rx_faces, n_faces, wr, pos, dir, 1.0e6f, stack, stack_t, stride, t_rx);
+            }
+        }
         Hit h;
         h.t = 1.0e6f; h.face = -1; h.slot = -1;
         closest_hit(E.nodes, E.tris, E.n_tris, wr, sr, stack, stack_t, stride, h);                          // :82
@@ -627,6 +801,7 @@ struct CompatSink {
     }
 };
 
+template <bool MT>
 __global__ void __launch_bounds__(TRACE_THREADS)
 k_trace_compat(LiteralEnv E, RxView rx, const double *rx_center, int n_faces, float3 tx, int max_bounces, int64_t ray_begin,
                int64_t n_rays, float *traced, float *received, uint32_t *mask, int stack_depth)
@@ -639,8 +814,8 @@ k_trace_compat(LiteralEnv E, RxView rx, const double *rx_center, int n_faces, fl
     const int64_t row = 3 * (int64_t)(max_bounces + 1);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_rays; i += (int64_t)gridDim.x * blockDim.x) {
         CompatSink sink{traced + i * row, received + i * row, mask + i};
-        literal_trace(E, has_rx ? &rx : nullptr, n_faces, tx, max_bounces, (uint32_t)(ray_begin + i), stack, stack_t,
-                      TRACE_THREADS, sink);
+        literal_trace<MT>(E, has_rx ? &rx : nullptr, n_faces, tx, max_bounces, (uint32_t)(ray_begin + i), stack, stack_t,
+                          TRACE_THREADS, sink);
     }
 }
 
@@ -714,7 +889,7 @@ struct ReceiveParams {
     int32_t stack_depth;
 };
 
-template <bool LSTACK>
+template <bool LSTACK, bool MT>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_receive(const ReceiveParams P)
 {
     extern __shared__ __align__(16) int s_stack_raw[];
@@ -743,7 +918,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_receive(const ReceivePa
         rx.unit_nodes = P.unit_nodes; rx.unit_order = P.unit_order;
         rx.cx = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y); rx.cy = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y + 1);
         rx.cz = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y + 2); rx.inv_r = P.inv_r;
-        literal_trace(P.env, &rx, P.n_faces, P.tx, P.max_bounces, cand.x, stack, stack_t, STRIDE, sink, s_recs);
+        literal_trace<MT>(P.env, &rx, P.n_faces, P.tx, P.max_bounces, cand.x, stack, stack_t, STRIDE, sink, MT ? nullptr : s_recs);
         // a candidate raised at a later bounce than the replay's first receiver hit is a duplicate
         if (sink.last_rx_bounce < 0 || sink.first_rx_bounce != (int)cand.z) continue;
         int nverts = sink.last_rx_bounce + 2;
@@ -794,6 +969,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_receive(const ReceivePa
     }
 }
 
+template <bool MT>
 __global__ void __launch_bounds__(TRACE_THREADS)
 k_query(LiteralEnv E, const float *__restrict__ origins, const float *__restrict__ dirs, int64_t n, float max_t,
         float *t_out, int32_t *face_out, int stack_depth)
@@ -804,7 +980,8 @@ k_query(LiteralEnv E, const float *__restrict__ origins, const float *__restrict
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float3 p = make_float3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
         float3 d = make_float3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
-        WoopRay wr = woop_setup(p, d);
+        using Ray = typename std::conditional<MT, MtRay, WoopRay>::type;
+        const Ray wr = tri_ray_setup<Ray>(p, d);
         SlabRay sr = slab_setup(p, d);
         Hit h;
         h.t = max_t; h.face = -1; h.slot = -1;
@@ -950,7 +1127,9 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     // DUMP instantiations also accumulate the checksum
     const bool dump = d_hit_tri || d_hit_t || (flags & RFRT_FLAG_CHECKSUM);
     // small scenes: lockstep sweep over the scene staged in shared memory (see closest_hit_small)
-    const bool small = m->small && P.n_tris > 0 && !(flags & RFRT_FLAG_FORCE_BVH);
+    // (the small-scene sweep's candidate filter is derived for the watertight test: Moeller-Trumbore meshes walk the BVH)
+    const bool mt = m->tri_test == RFRT_TRI_TEST_MT;
+    const bool small = m->small && P.n_tris > 0 && !(flags & RFRT_FLAG_FORCE_BVH) && !mt;
     if (small) P.stack_depth = (r && !P.rx_coop) ? stack_depth_for(nullptr, r) : 1;
     const bool lstack = !small && P.stack_depth > 16; // deep tree: local-memory stack (<= 64 entries by construction)
     if (lstack && P.stack_depth > 64) { set_error("rfrt_trace: BVH deeper than 64 levels"); return RFRT_ERR_INVALID; }
@@ -968,13 +1147,31 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
         };
         kern = small_kerns[P.rx_coop ? 1 : 0][m->small_pairs > 16 ? 1 : 0][dump ? 1 : 0];
     } else {
-        static const kern_t kerns[2][2][2] = {
-            {{k_trace_env<false, false, false>, k_trace_env<true, false, false>},
-             {k_trace_env<false, true, false>, k_trace_env<true, true, false>}},
-            {{k_trace_env<false, false, true>, k_trace_env<true, false, true>},
-             {k_trace_env<false, true, true>, k_trace_env<true, true, true>}},
+        static const kern_t kerns[2][2][2][2] = {
+            {{{k_trace_env<false, false, false, false>, k_trace_env<true, false, false, false>},
+              {k_trace_env<false, true, false, false>, k_trace_env<true, true, false, false>}},
+             {{k_trace_env<false, false, true, false>, k_trace_env<true, false, true, false>},
+              {k_trace_env<false, true, true, false>, k_trace_env<true, true, true, false>}}},
+            {{{k_trace_env<false, false, false, true>, k_trace_env<true, false, false, true>},
+              {k_trace_env<false, true, false, true>, k_trace_env<true, true, false, true>}},
+             {{k_trace_env<false, false, true, true>, k_trace_env<true, false, true, true>},
+              {k_trace_env<false, true, true, true>, k_trace_env<true, true, true, true>}}},
         };
-        kern = kerns[P.rx_coop ? 1 : 0][lstack ? 1 : 0][dump ? 1 : 0];
+        static const kern_t walk_kerns[2][2][2][2] = {
+            {{{k_trace_walk<false, false, false, false>, k_trace_walk<true, false, false, false>},
+              {k_trace_walk<false, true, false, false>, k_trace_walk<true, true, false, false>}},
+             {{k_trace_walk<false, false, true, false>, k_trace_walk<true, false, true, false>},
+              {k_trace_walk<false, true, true, false>, k_trace_walk<true, true, true, false>}}},
+            {{{k_trace_walk<false, false, false, true>, k_trace_walk<true, false, false, true>},
+              {k_trace_walk<false, true, false, true>, k_trace_walk<true, true, false, true>}},
+             {{k_trace_walk<false, false, true, true>, k_trace_walk<true, false, true, true>},
+              {k_trace_walk<false, true, true, true>, k_trace_walk<true, true, true, true>}}},
+        };
+        const int walk_mode = getenv("RFRT_WALK") ? atoi(getenv("RFRT_WALK")) : 1;
+        const int walk_refill = getenv("RFRT_WALK_REFILL") ? atoi(getenv("RFRT_WALK_REFILL")) : 12;
+        const int walk_node_min = getenv("RFRT_WALK_NODE_MIN") ? atoi(getenv("RFRT_WALK_NODE_MIN")) : 8;
+        P.walk_refill = walk_refill; P.walk_node_min = walk_node_min;
+        kern = (walk_mode ? walk_kerns : kerns)[mt ? 1 : 0][P.rx_coop ? 1 : 0][lstack ? 1 : 0][dump ? 1 : 0];
     }
     int grid = 0;
     int rc = grid_for((const void *)kern, smem, &grid, small);
@@ -1045,18 +1242,22 @@ extern "C" int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const
     P.amp0 = amp0; P.light_speed = light_speed_mps; P.sample_rate = sample_rate_hz;
     P.rec_ray = d_rec_ray; P.rec_rx = d_rec_rx; P.rec_nverts = d_rec_nverts; P.rec_bin = d_rec_bin;
     P.rec_amp = d_rec_amp; P.rec_dist = d_rec_dist; P.rec_paths = d_rec_paths; P.rec_capacity = rec_capacity;
-    P.stack_depth = stack_depth_for(m, nullptr); // only the environment BVH is walked here (receiver query: lockstep sweep)
+    // only the environment BVH is walked here (receiver query: lockstep sweep), except with the Moeller-Trumbore functor
+    P.stack_depth = stack_depth_for(m, m->tri_test == RFRT_TRI_TEST_MT ? r : nullptr);
     const bool lstack = P.stack_depth > 16;
     if (lstack && P.stack_depth > 64) { set_error("rfrt_trace_receive: BVH deeper than 64 levels"); return RFRT_ERR_INVALID; }
     if (lstack) P.stack_depth = 0;
     const size_t smem = stack_bytes(P.stack_depth) + sizeof(float4) * 4 * (size_t)r->n_faces;
     int grid = 0;
-    int rc = grid_for(lstack ? (const void *)k_trace_receive<true> : (const void *)k_trace_receive<false>, smem, &grid);
+    typedef void (*recv_kern_t)(const ReceiveParams);
+    static const recv_kern_t recv_kerns[2][2] = {{k_trace_receive<false, false>, k_trace_receive<true, false>},
+                                                 {k_trace_receive<false, true>, k_trace_receive<true, true>}};
+    const recv_kern_t recv_kern = recv_kerns[m->tri_test == RFRT_TRI_TEST_MT ? 1 : 0][lstack ? 1 : 0];
+    int rc = grid_for((const void *)recv_kern, smem, &grid);
     if (rc) return rc;
     rc = upload_faces(r, stream);
     if (rc) return rc;
-    if (lstack) k_trace_receive<true><<<grid, TRACE_THREADS, smem, stream>>>(P);
-    else k_trace_receive<false><<<grid, TRACE_THREADS, smem, stream>>>(P);
+    recv_kern<<<grid, TRACE_THREADS, smem, stream>>>(P);
     RFRT_CUDA(cudaGetLastError());
     return RFRT_OK;
 }
@@ -1085,7 +1286,8 @@ extern "C" int rfrt_trace_paths_compat(rfrt_handle env_mesh, const float *h_tx_p
     int depth = stack_depth_for(m, r);
     const size_t smem = stack_bytes(depth);
     int grid = 0;
-    int rc = grid_for((const void *)k_trace_compat, smem, &grid);
+    const bool mt = m->tri_test == RFRT_TRI_TEST_MT;
+    int rc = grid_for(mt ? (const void *)k_trace_compat<true> : (const void *)k_trace_compat<false>, smem, &grid);
     RxView rxv{};
     if (r) {
         rxv.verts = r->verts + rx_index * r->n_unit * 3;
@@ -1096,7 +1298,7 @@ extern "C" int rfrt_trace_paths_compat(rfrt_handle env_mesh, const float *h_tx_p
     int64_t need = (n_rays + TRACE_THREADS - 1) / TRACE_THREADS;
     if (need < grid) grid = (int)need;
     if (r) { rc = upload_faces(r, stream); if (rc) return rc; }
-    k_trace_compat<<<grid, TRACE_THREADS, smem, stream>>>(
+    (mt ? k_trace_compat<true> : k_trace_compat<false>)<<<grid, TRACE_THREADS, smem, stream>>>(
         E, rxv, r ? r->centers + 3 * rx_index : nullptr, r ? r->n_faces : 0, make_float3(h_tx_pos[0], h_tx_pos[1], h_tx_pos[2]), max_bounces, ray_begin, n_rays,
         d_traced_paths, d_received_paths, d_row_mask, depth);
     RFRT_CUDA(cudaGetLastError());
@@ -1115,11 +1317,12 @@ extern "C" int rfrt_query_closest(rfrt_handle mesh, const float *d_origins, cons
     int depth = stack_depth_for(m, nullptr);
     const size_t smem = stack_bytes(depth);
     int grid = 0;
-    int rc = grid_for((const void *)k_query, smem, &grid);
+    const bool mt = m->tri_test == RFRT_TRI_TEST_MT;
+    int rc = grid_for(mt ? (const void *)k_query<true> : (const void *)k_query<false>, smem, &grid);
     if (rc) return rc;
     int64_t need = (n + TRACE_THREADS - 1) / TRACE_THREADS;
     if (need < grid) grid = (int)need;
-    k_query<<<grid, TRACE_THREADS, smem, stream>>>(E, d_origins, d_dirs, n, max_t, d_t, d_face, depth);
+    (mt ? k_query<true> : k_query<false>)<<<grid, TRACE_THREADS, smem, stream>>>(E, d_origins, d_dirs, n, max_t, d_t, d_face, depth);
     RFRT_CUDA(cudaGetLastError());
     return RFRT_OK;
 }

@@ -49,12 +49,14 @@ class Tracer:
       exchange_records   initial capacity of the record segment every rank contributes to the exchange (grown on overflow)
       verbose       print the reference's progress line (tracer.py:119)
       force_bvh     walk the BVH even for scenes of <= 64 triangles (default: lockstep sweep for those)
+      triangle_test "woop" (default: the reference's watertight test, i.e. Warp's intersect_ray_tri_woop) or "mt"
+                    (Moeller-Trumbore; not reference behaviour — see rfrt_mesh_set_triangle_test in include/rfrt.h)
     """
 
     def __init__(self, environment_trimesh, light_speed_mps, sample_rate_hz, sample_window_s, max_bounces,
                  tx_num_rays, *, device=None, ray_range=None, shard=False, chunk_rays=1 << 26,
                  max_candidates=1 << 20, max_records=1 << 20, exchange_records=1 << 16, verbose=False,
-                 force_bvh=False):
+                 force_bvh=False, triangle_test="woop"):
         if not torch.cuda.is_available():
             raise RfrtError("rf_ray_tracing_warp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self._lib = _lib.load()
@@ -88,6 +90,11 @@ class Tracer:
             check(self._lib.rfrt_mesh_create(_ptr(self._d_vertices), vertices.shape[0], _ptr(self._d_faces),
                                              faces.shape[0] // 3, _stream_ptr(), handle), "rfrt_mesh_create")
         self._env = handle.value
+        if triangle_test not in ("woop", "mt"):
+            raise ValueError('triangle_test must be "woop" or "mt"')
+        self.triangle_test = triangle_test
+        if triangle_test == "mt":
+            check(self._lib.rfrt_mesh_set_triangle_test(self._env, _lib.TRI_TEST_MT), "rfrt_mesh_set_triangle_test")
         # BVH scenes trace each wave in direction-coherent order: size that workspace now, not on the hot path
         check(self._lib.rfrt_mesh_reserve_rays(self._env, min(self.chunk_rays, max(self.ray_range[1] - self.ray_range[0], 1))),
               "rfrt_mesh_reserve_rays")
