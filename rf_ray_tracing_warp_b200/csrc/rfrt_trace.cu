@@ -4,10 +4,10 @@
 //   k_trace_small   kernel.py:57-98  scenes of <= 64 filter slots, staged in shared memory: persistent kernel, every
 //                                    lane owns several rays and runs one bounce iteration of one of them per loop
 //                                    trip (lockstep sweep or self-re-hit test, whichever more lanes can join)
-//   k_trace_env     kernel.py:57-98  BVH scenes: persistent kernel, every lane owns one ray, runs one bounce
-//                                    iteration per loop trip and is refilled with a fresh ray (warp-aggregated
-//                                    fetch: ballot + popc + one atomic per block of rays) as soon as its ray
-//                                    misses the environment or exhausts its bounces
+//   k_trace_walk    kernel.py:57-98  BVH scenes: persistent kernel, every lane owns one ray and keeps its traversal state
+//                                    across the phases of the loop: lanes whose walk has ended finish their segment,
+//                                    start the next one or take a fresh ray (warp-aggregated fetch: ballot + popc + one
+//                                    atomic per block of rays) while the other lanes stay in the middle of theirs
 //   k_trace_receive kernel.py:38-98  literal replay for the rare (ray, receiver) candidates + the per-path
 //                                    post-processing of tracer.py:102-115
 //   k_trace_compat  kernel.py:38-98  the reference kernel's dense contract (tracer.py:75-79)
@@ -28,6 +28,9 @@ constexpr int TRACE_THREADS = 128;
 constexpr int RX_CAND_BUF = 256; // receivers staged per warp between two appends (cooperative enumeration)
 constexpr int RX_COOP_INTS = RX_QUEUE_CAP + RX_CAND_BUF + 4; // per-warp shared memory of the cooperative enumeration
 constexpr int MAX_RECV_BOUNCES = 32;
+#ifndef WALK_MIN_CTAS
+#define WALK_MIN_CTAS 9
+#endif
 
 struct TraceParams {
     const BvhNode *nodes;
@@ -244,8 +247,6 @@ __device__ __forceinline__ void receivers_coop(const TraceParams &P, bool seg_do
     if (!ok && lane == 0) atomicAdd(&P.counters[RFRT_CTR_QUEUE_OVERFLOW], 1ull);
 }
 
-// LSTACK: deep trees (big meshes) keep the traversal stack in per-thread local memory (L1-cached) instead of
-// shared memory, whose depth x 1 KiB per CTA would otherwise cap the occupancy of this latency-bound case.
 __device__ __forceinline__ unsigned long long segment_hash(uint32_t gid, int bounce, int face, float t)
 {
     // splitmix64 finaliser of (ray id, bounce | triangle, bits of t): RFRT_CTR_CHECKSUM sums it over all segments
@@ -256,160 +257,29 @@ __device__ __forceinline__ unsigned long long segment_hash(uint32_t gid, int bou
     return z ^ (z >> 31);
 }
 
-// BVH scenes.  LSTACK: see above.
-// COOP: dense receiver sets — the warp enumerates its lanes' segments together (rx_enumerate_coop) at a converged point
-//       after the closest hit; otherwise every lane handles its own receivers right where its segment is finished
-// MT: the Moeller-Trumbore functor instead of the reference's watertight test (rfrt_mesh_set_triangle_test)
-template <bool DUMP, bool LSTACK, bool COOP, bool MT>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_env(const TraceParams P)
-{
-    using Ray = typename std::conditional<MT, MtRay, WoopRay>::type;
-    extern __shared__ __align__(16) int s_stack_raw[];
-    int l_stack[LSTACK ? 64 : 1];
-    float l_stack_t[LSTACK ? 64 : 1];
-    int *stack = LSTACK ? l_stack : s_stack_raw + threadIdx.x;
-    float *stack_t = LSTACK ? l_stack_t : reinterpret_cast<float *>(s_stack_raw + P.stack_depth * TRACE_THREADS) + threadIdx.x;
-    constexpr int STRIDE = LSTACK ? 1 : TRACE_THREADS;
-    const int lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    // behind the stacks: this warp's receiver-enumeration queue (+ candidate buffer)
-    int *rx_queue = s_stack_raw + 2 * P.stack_depth * TRACE_THREADS + (COOP ? RX_COOP_INTS * (threadIdx.x >> 5) : 0);
-
-    bool has_ray = false;
-    bool exhausted = false; // warp-uniform
-    float3 pos = make_float3(0.f, 0.f, 0.f), dir = make_float3(0.f, 0.f, 1.f);
-    int bounce = 0;
-    bool entered = false; // the current segment is known to enter the scene's bounding box
-    int64_t ray = 0;
-    unsigned int n_seg = 0, n_hit = 0, n_nodes = 0, n_tests = 0;
-    unsigned long long csum = 0ull;
-
-    // rays are handed out in blocks per warp: one atomic per block instead of one per trip
-    const int FETCH_BLOCK = P.fetch_block;
-    int64_t blk_next = 0, blk_end = 0; // warp-uniform
-
-    for (;;) {
-        unsigned idle = __ballot_sync(FULL, !has_ray);
-        // (second pass: the block ran out in the middle of the refill -> continue from a fresh block in the same trip)
-#pragma unroll 1
-        for (int pass = 0; pass < 2 && idle != 0u && !exhausted; ++pass) {
-            if (blk_next == blk_end) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(&P.counters[RFRT_CTR_NEXT_RAY], (unsigned long long)FETCH_BLOCK);
-                base = __shfl_sync(FULL, base, 0);
-                blk_next = (int64_t)base;
-                blk_end = blk_next + FETCH_BLOCK < P.chunk_n ? blk_next + FETCH_BLOCK : P.chunk_n;
-                if (blk_next >= P.chunk_n) { exhausted = true; blk_end = blk_next; }
-            }
-            if (!has_ray) {
-                int64_t r = blk_next + __popc(idle & ((1u << lane) - 1u));
-                if (r < blk_end) {
-                    if (P.order) r = (int64_t)(uint32_t)__ldg(P.order + r); // direction-coherent order
-                    float4 d4 = __ldg(P.dirs + r);
-                    dir = make_float3(d4.x, d4.y, d4.z);
-                    pos = P.tx;
-                    bounce = 0;
-                    entered = false;
-                    ray = r;
-                    has_ray = true;
-                }
-            }
-            blk_next = blk_next + __popc(idle) < blk_end ? blk_next + __popc(idle) : blk_end;
-            idle = __ballot_sync(FULL, !has_ray);
-        }
-        if (!__any_sync(FULL, has_ray)) break;
-        // A trip is either a box trip (the lanes whose segment has not been tested against the scene's bounding box do
-        // just that: a miss finishes the segment at once and frees the lane for the next refill) or a walk.  Without it
-        // the many rays that leave the scene immediately (half of them above an open terrain) would sit idle in warps
-        // whose other lanes walk 50 nodes (measured: 5.6 of 32 lanes active).
-        const bool boxtrip = __any_sync(FULL, has_ray && !entered);
-        // ---- one bounce iteration (kernel.py:57-98, environment branch) -----------------------
-        Hit h;
-        h.t = 1.0e6f; h.face = -1; h.slot = -1;
-        bool seg_done = false; // this lane finished a segment in this trip (h = its closest hit)
-        if (has_ray && (!boxtrip || !entered)) {
-            bool resolved = true;
-            const SlabRay sr_env = slab_setup(pos, dir);
-            if (boxtrip) {
-                float tn;
-                entered = slab_hit(sr_env, P.env_lo[0], P.env_lo[1], P.env_lo[2], P.env_hi[0], P.env_hi[1], P.env_hi[2], 1.0e6f, tn);
-                resolved = !entered; // outside the box: a miss (h stays empty)
-            } else {
-                const Ray wr = tri_ray_setup<Ray>(pos, dir);
-                closest_hit<DUMP>(P.nodes, P.tris, P.n_tris, wr, sr_env, stack, stack_t, STRIDE, h, -1, &n_nodes, &n_tests);
-            }
-            seg_done = resolved;
-        }
-
-        // ---- receivers hit strictly before the environment, or at all if it is missed (kernel.py:71,85) ----
-        if (COOP)
-            receivers_coop(P, seg_done, pos, dir, h.face >= 0 ? h.t : 1.0e6f, (uint32_t)(P.chunk_begin + ray), bounce, rx_queue, lane);
-
-        if (seg_done) {
-            const bool hit_env = h.face >= 0;
-            ++n_seg;
-
-            if (!COOP && P.n_rx > 0)
-                receivers_lane(P, pos, dir, hit_env ? h.t : 1.0e6f, (uint32_t)(P.chunk_begin + ray), bounce, stack, STRIDE);
-
-            if (DUMP) {
-                int64_t row = (P.chunk_begin + ray - P.dump_begin) * P.max_bounces + bounce;
-                if (P.hit_tri) P.hit_tri[row] = hit_env ? h.face : -1;
-                if (P.hit_t) P.hit_t[row] = hit_env ? h.t : 0.0f;
-                csum += segment_hash((uint32_t)(P.chunk_begin + ray), bounce, hit_env ? h.face : -1, hit_env ? h.t : 0.0f);
-            }
-
-            if (hit_env) {
-                ++n_hit;
-                pos = advance(pos, dir, h.t);                 // kernel.py:94
-                const float4 n4 = __ldg(P.normals + h.slot);  // normalize(cross(b-a, c-a)), precomputed at build time
-                dir = reflect(dir, make_float3(n4.x, n4.y, n4.z)); // kernel.py:96
-                entered = false;
-                ++bounce;
-                if (bounce >= P.max_bounces) has_ray = false;
-            } else {
-                has_ray = false; // a miss repeats forever in the reference (kernel.py:97-98): nothing more to do
-            }
-        }
-    }
-
-    // warp-reduced counters
-    for (int o = 16; o > 0; o >>= 1) {
-        n_seg += __shfl_xor_sync(FULL, n_seg, o);
-        n_hit += __shfl_xor_sync(FULL, n_hit, o);
-    }
-    if (lane == 0) {
-        atomicAdd(&P.counters[RFRT_CTR_SEGMENTS], (unsigned long long)n_seg);
-        atomicAdd(&P.counters[RFRT_CTR_ENV_HITS], (unsigned long long)n_hit);
-    }
-    if (DUMP) {
-        unsigned long long nn = n_nodes, nt = n_tests;
-        for (int o = 16; o > 0; o >>= 1) {
-            csum += __shfl_xor_sync(FULL, csum, o);
-            nn += __shfl_xor_sync(FULL, nn, o);
-            nt += __shfl_xor_sync(FULL, nt, o);
-        }
-        if (lane == 0) {
-            atomicAdd(&P.counters[RFRT_CTR_CHECKSUM], csum);
-            atomicAdd(&P.counters[RFRT_CTR_NODE_VISITS], nn);
-            atomicAdd(&P.counters[RFRT_CTR_TRI_TESTS], nt);
-        }
-    }
-}
-
-// BVH scenes, second schedule: the walk is decoupled from the trip.  In k_trace_env a trip is one segment per lane and
-// ends when the LONGEST of the warp's 32 walks ends (measured on the 20 M-triangle terrain: 10 of 32 lanes active — the
-// walk lengths of secondary rays vary from 3 to 200 nodes).  Here every lane keeps its traversal state (node, stack
-// pointer, best hit, per-ray constants) across the phases of one loop:
+// BVH scenes: the walk is decoupled from the trip.  With one segment per lane and trip (round 1's k_trace_env) a trip
+// ends when the LONGEST of the warp's 32 walks ends (measured on the 20 M-triangle terrain: 10-12 of 32 lanes active —
+// the walk lengths of secondary rays vary from 3 to 200 nodes; 3.1e9 segments/s against 3.9e9 with this schedule on
+// the same tree).  Here every lane keeps its traversal state (node, stack pointer, best hit, slab constants) across
+// the phases of one loop:
 //   phase A  lanes whose walk has ended finish their segment (counters, receivers, advance + reflect, kernel.py:85-96),
 //            take a fresh ray if theirs is dead, and start the next segment (scene-box test, per-ray constants);
 //   phase B  the warp walks — a node loop for the lanes that hold an internal node, a leaf step for the lanes that hold
 //            a triangle — until `refill` lanes are waiting for phase A again.
 // The node loop stops early for a leaf step only when fewer than `node_min` lanes would still take part in it.
-// Same per-segment functions as k_trace_env (closest hit, ties, reflect): the segments are identical, only their
-// schedule differs (checked by the segment checksum against the other kernels and the CPU restatement).
+// The per-segment functions (closest hit, ties, reflect) do not depend on the schedule: the segments are checked by the
+// segment checksum against the small-scene kernel and the CPU restatement.
+#ifndef WALK_UNROLL_N
+#define WALK_UNROLL_N 2
+#endif
+constexpr int WALK_UNROLL = WALK_UNROLL_N;
+// LSTACK: deep trees (big meshes) keep the traversal stack in per-thread local memory (L1-cached) instead of
+//         shared memory, whose depth x 1 KiB per CTA would otherwise cap the occupancy of this latency-bound case
+// COOP:   dense receiver sets — the warp enumerates its lanes' segments together (rx_enumerate_coop) at the converged
+//         point of phase A; otherwise every lane handles its own receivers right where its segment is finished
+// MT:     the Moeller-Trumbore functor instead of the reference's watertight test (rfrt_mesh_set_triangle_test) // node steps per vote of the node loop
 template <bool DUMP, bool LSTACK, bool COOP, bool MT>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_walk(const TraceParams P)
+__global__ void __launch_bounds__(TRACE_THREADS, WALK_MIN_CTAS) k_trace_walk(const TraceParams P)
 {
     using Ray = typename std::conditional<MT, MtRay, WoopRay>::type;
     extern __shared__ __align__(16) int s_stack_raw[];
@@ -432,7 +302,6 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_walk(const TraceParams 
     int64_t ray = 0;
     Hit h;
     h.t = 1.0e6f; h.face = -1; h.slot = -1;
-    Ray wr = tri_ray_setup<Ray>(pos, dir);
     SlabRay sr = slab_setup(pos, dir);
     unsigned int n_seg = 0, n_hit = 0, n_nodes = 0, n_tests = 0;
     unsigned long long csum = 0ull;
@@ -508,29 +377,32 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_walk(const TraceParams 
             walking = true;
             sp = 0;
             node = entered ? 0 : TRAV_DONE;
-            if (entered) wr = tri_ray_setup<Ray>(pos, dir);
         }
         // ================= phase B: walk until enough lanes wait for phase A =================
+        // (a lane waits for phase A when its walk has ended and phase A has something for it: amask)
+        const unsigned amask = __ballot_sync(FULL, has_ray || !exhausted);
         for (;;) {
-            unsigned internal, waiting;
             for (;;) {
-                internal = __ballot_sync(FULL, node >= 0);
-                // (a lane waits for phase A when its walk has ended and phase A has something for it)
-                waiting = __ballot_sync(FULL, node == TRAV_DONE && (has_ray || !exhausted));
-                const unsigned idle_all = __ballot_sync(FULL, node == TRAV_DONE);
-                const unsigned leaves = ~(internal | idle_all);
-                if (internal == 0u || __popc(waiting) >= REFILL || (leaves != 0u && __popc(internal) < NODE_MIN)) break;
-                if (node >= 0) {
-                    node = node_step(P.nodes, node, sr, h.t, stack, stack_t, STRIDE, sp);
-                    if (DUMP) ++n_nodes;
+                const unsigned internal = __ballot_sync(FULL, node >= 0), ended = __ballot_sync(FULL, node == TRAV_DONE);
+                if (internal == 0u || __popc(ended & amask) >= REFILL ||
+                    ((internal | ended) != FULL && __popc(internal) < NODE_MIN)) break;
+#pragma unroll
+                for (int u = 0; u < WALK_UNROLL; ++u) {
+                    if (node >= 0) {
+                        node = node_step(P.nodes, node, sr, h.t, stack, stack_t, STRIDE, sp);
+                        if (DUMP) ++n_nodes;
+                    }
                 }
             }
             if (node < 0 && node != TRAV_DONE) {
+                // (the per-ray constants of the triangle test are rebuilt here, 2 leaves per segment, instead of
+                // living in 9 registers through the node loop)
+                const Ray wr = tri_ray_setup<Ray>(pos, dir);
                 node = leaf_step(P.tris, node, wr, h, stack, stack_t, STRIDE, sp);
                 if (DUMP) ++n_tests;
             }
-            waiting = __ballot_sync(FULL, node == TRAV_DONE && (has_ray || !exhausted));
-            if (__popc(waiting) >= REFILL || __all_sync(FULL, node == TRAV_DONE)) break;
+            const unsigned ended = __ballot_sync(FULL, node == TRAV_DONE);
+            if (__popc(ended & amask) >= REFILL || ended == FULL) break;
         }
     }
 
@@ -1147,16 +1019,6 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
         };
         kern = small_kerns[P.rx_coop ? 1 : 0][m->small_pairs > 16 ? 1 : 0][dump ? 1 : 0];
     } else {
-        static const kern_t kerns[2][2][2][2] = {
-            {{{k_trace_env<false, false, false, false>, k_trace_env<true, false, false, false>},
-              {k_trace_env<false, true, false, false>, k_trace_env<true, true, false, false>}},
-             {{k_trace_env<false, false, true, false>, k_trace_env<true, false, true, false>},
-              {k_trace_env<false, true, true, false>, k_trace_env<true, true, true, false>}}},
-            {{{k_trace_env<false, false, false, true>, k_trace_env<true, false, false, true>},
-              {k_trace_env<false, true, false, true>, k_trace_env<true, true, false, true>}},
-             {{k_trace_env<false, false, true, true>, k_trace_env<true, false, true, true>},
-              {k_trace_env<false, true, true, true>, k_trace_env<true, true, true, true>}}},
-        };
         static const kern_t walk_kerns[2][2][2][2] = {
             {{{k_trace_walk<false, false, false, false>, k_trace_walk<true, false, false, false>},
               {k_trace_walk<false, true, false, false>, k_trace_walk<true, true, false, false>}},
@@ -1167,11 +1029,12 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
              {{k_trace_walk<false, false, true, true>, k_trace_walk<true, false, true, true>},
               {k_trace_walk<false, true, true, true>, k_trace_walk<true, true, true, true>}}},
         };
-        const int walk_mode = getenv("RFRT_WALK") ? atoi(getenv("RFRT_WALK")) : 1;
-        const int walk_refill = getenv("RFRT_WALK_REFILL") ? atoi(getenv("RFRT_WALK_REFILL")) : 12;
-        const int walk_node_min = getenv("RFRT_WALK_NODE_MIN") ? atoi(getenv("RFRT_WALK_NODE_MIN")) : 8;
-        P.walk_refill = walk_refill; P.walk_node_min = walk_node_min;
-        kern = (walk_mode ? walk_kerns : kerns)[mt ? 1 : 0][P.rx_coop ? 1 : 0][lstack ? 1 : 0][dump ? 1 : 0];
+        // thresholds of the walk schedule (20 M-triangle terrain, segments/s: refill 8 / 12 / 16 / 24 lanes = 3.53 / 3.69 /
+        // 3.89 / 3.91e9 at node_min 8; node_min 4 / 8 / 12 / 16 = 3.64 / 3.75 / 3.80 / 3.68e9 at refill 16); the
+        // environment variables are tuning aids of scripts/walk_sweep.py
+        P.walk_refill = getenv("RFRT_WALK_REFILL") ? atoi(getenv("RFRT_WALK_REFILL")) : 24;
+        P.walk_node_min = getenv("RFRT_WALK_NODE_MIN") ? atoi(getenv("RFRT_WALK_NODE_MIN")) : 8;
+        kern = walk_kerns[mt ? 1 : 0][P.rx_coop ? 1 : 0][lstack ? 1 : 0][dump ? 1 : 0];
     }
     int grid = 0;
     int rc = grid_for((const void *)kern, smem, &grid, small);

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Tuning sweep of the BVH-scene trace kernels on the synthetic terrain: k_trace_env (RFRT_WALK=0) against k_trace_walk
-with different refill / node-loop thresholds.  Usage: walk_sweep.py [n_grid] [n_rays]"""
+"""Tuning sweep of the BVH-scene trace kernel (k_trace_walk) on the synthetic terrain: refill / node-loop thresholds
+(RFRT_WALK_REFILL, RFRT_WALK_NODE_MIN).  Usage: walk_sweep.py [n_grid] [n_rays]"""
 import os
 import sys
 
@@ -32,10 +32,8 @@ def run(tag):
           f"nodes/seg {c['node_visits'] / c['segments']:.2f} tris/seg {c['tri_tests'] / c['segments']:.2f}", flush=True)
 
 
-os.environ["RFRT_WALK"] = "0"
-run("k_trace_env")
-os.environ["RFRT_WALK"] = "1"
-for refill in (4, 8, 12, 16, 24):
-    for node_min in (1, 8, 16, 24):
+run("defaults")
+for refill in (8, 16, 24):
+    for node_min in (4, 8, 12):
         os.environ["RFRT_WALK_REFILL"], os.environ["RFRT_WALK_NODE_MIN"] = str(refill), str(node_min)
         run(f"walk refill={refill} node_min={node_min}")
