@@ -167,9 +167,8 @@ RFRT_API int rfrt_ray_directions(int64_t ray_begin, int64_t ray_end, float *d_di
  *   d_counters      : [RFRT_CTR_COUNT] uint64, zeroed by the CALLER before the first call of a job;
  *                     accumulates across calls
  *   d_candidates    : [cand_capacity*4] uint32 quads (ray id, receiver, bounce, 0) or NULL when rxset == 0
- *   d_hit_tri/d_hit_t : optional dense [n*max_bounces] hit history (int32 triangle index, -1 = miss /
- *                     dead; float32 hit distance, 0 = miss / dead); NULL to skip.  Parity dumps, and the record
- *                     rfrt_trace_receive can rebuild a candidate's first iterations from
+ *   d_hit_tri/d_hit_t : optional dense [n*max_bounces] parity dumps (int32 triangle index, -1 = miss /
+ *                     dead; float32 hit distance, 0 = miss / dead); NULL to skip
  * ------------------------------------------------------------------------------------------- */
 RFRT_API int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *h_tx_pos, int32_t max_bounces,
                int64_t ray_begin, int64_t ray_end, uint32_t flags, float *d_dir_scratch,
@@ -189,18 +188,12 @@ RFRT_API int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *h_
  *   d_rec_ray [cap] uint32, d_rec_rx [cap] int32, d_rec_nverts [cap] int32, d_rec_bin [cap] int64,
  *   d_rec_amp [cap] float64, d_rec_dist [cap] float64,
  *   d_rec_paths [cap*(max_bounces+1)*3] float32 (NaN padded like tracer.py:67-71) or NULL
- * Optional hit history (both arrays or neither): d_hist_tri / d_hist_t = the d_hit_tri / d_hit_t that rfrt_trace
- * wrote for rays [hist_ray_begin, hist_ray_begin + hist_rays).  Until its first receiver hit the ray of a pair IS the
- * environment trajectory, so the replay of a candidate (ray, k, bounce) whose ray lies in that range rebuilds the
- * iterations before `bounce` from (triangle, t) with the trace's own arithmetic instead of walking the BVH again
- * (identical records; dense receiver lattices replay each ray once per overlapping receiver).
  * ------------------------------------------------------------------------------------------- */
 RFRT_API int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const float *h_tx_pos, int32_t max_bounces,
                        const uint32_t *d_candidates, int64_t cand_capacity, uint64_t *d_counters,
                        double amp0, double light_speed_mps, double sample_rate_hz, uint32_t *d_rec_ray,
                        int32_t *d_rec_rx, int32_t *d_rec_nverts, int64_t *d_rec_bin, double *d_rec_amp,
-                       double *d_rec_dist, float *d_rec_paths, int64_t rec_capacity, const int32_t *d_hist_tri,
-                       const float *d_hist_t, int64_t hist_ray_begin, int64_t hist_rays, void *stream);
+                       double *d_rec_dist, float *d_rec_paths, int64_t rec_capacity, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Impulse-response binning (tracer.py:101,116-117):  ir[rx][bin] += amp  if bin < n_bins.

@@ -600,18 +600,22 @@ struct LiteralEnv {
 
 // kernel.py:38-98 for one ray and one receiver.  Sink receives the vertex writes and RX-hit events.
 // s_recs: unit-space face records in shared memory (lockstep receiver query) or NULL (unit-BVH walk)
-// literal_loop runs the iterations first_bounce .. max_bounces-1 from the state (pos, dir) the ray has there.
 template <bool MT, class Sink>
-__device__ __forceinline__ void literal_loop(const LiteralEnv &E, const RxView *rx, int n_faces, float3 pos, float3 dir,
-                                             int first_bounce, int max_bounces, int *stack, float *stack_t, int stride,
-                                             Sink &sink, const float4 *s_recs = nullptr)
+__device__ __forceinline__ void literal_trace(const LiteralEnv &E, const RxView *rx, int n_faces, float3 tx,
+                                              int max_bounces, uint32_t tid, int *stack, float *stack_t, int stride,
+                                              Sink &sink, const float4 *s_recs = nullptr)
 {
+    float3 dir = ray_direction(tid); // kernel.py:51-52
+    float3 pos = tx;                 // :53
+    sink.vertex(0, pos);             // :55
     // A receiver hit at t == 0 leaves the ray where it is with the direction it had (kernel.py:87: pos += dir * 0, no
     // reflection), so every later iteration evaluates the same two queries on the same values and takes the same branch
     // — the "stuck" paths of the reference's golden scene.  They are replayed without queries.
     bool stuck = false;
     float t_stuck = 0.0f;
-    for (int bounce = first_bounce; bounce < max_bounces; ++bounce) {
+    RxFaceCache rx_cache; // candidate faces of the current line (valid from a receiver query until the direction changes)
+    rx_cache.valid = false;
+    for (int bounce = 0; bounce < max_bounces; ++bounce) {
         if (stuck) {
             pos = advance(pos, dir, t_stuck); // :87
             sink.vertex(bounce + 1, pos);     // :88
@@ -626,7 +630,7 @@ __device__ __forceinline__ void literal_loop(const LiteralEnv &E, const RxView *
         if (rx) {
             // (the lockstep receiver query's candidate filter is derived for the watertight test only)
             if constexpr (!MT) {
-                maybe_hit_rx = s_recs ? rx_query_sweep(*rx, s_recs, c_rx_faces, n_faces, wr, pos, dir, 1.0e6f, t_rx)
+                maybe_hit_rx = s_recs ? rx_query_sweep(*rx, s_recs, c_rx_faces, n_faces, wr, pos, dir, 1.0e6f, t_rx, &rx_cache)
                                       : rx_query(*rx, c_rx_faces, n_faces, wr, pos, dir, 1.0e6f, stack, stack_t, stride, t_rx);
             } else {
                 maybe_hit_rx = rx_query(*rx, c_rx_faces, n_faces, wr, pos, dir, 1.0e6f, stack, stack_t, stride, t_rx);
@@ -649,21 +653,11 @@ __device__ __forceinline__ void literal_loop(const LiteralEnv &E, const RxView *
             float3 a, b, c; int idx;
             tri_vertices(E.tris, h.slot, a, b, c, idx);
             dir = reflect(dir, tri_normal(a, b, c)); // :96
+            rx_cache.valid = false;
         } else {
             break; // :97-98: nothing changes, so every later iteration repeats the same two misses
         }
     }
-}
-
-template <bool MT, class Sink>
-__device__ __forceinline__ void literal_trace(const LiteralEnv &E, const RxView *rx, int n_faces, float3 tx,
-                                              int max_bounces, uint32_t tid, int *stack, float *stack_t, int stride,
-                                              Sink &sink, const float4 *s_recs = nullptr)
-{
-    const float3 dir = ray_direction(tid); // kernel.py:51-52
-    const float3 pos = tx;                 // :53
-    sink.vertex(0, pos);                   // :55
-    literal_loop<MT>(E, rx, n_faces, pos, dir, 0, max_bounces, stack, stack_t, stride, sink, s_recs);
 }
 
 struct CompatSink {
@@ -750,14 +744,6 @@ struct ReceiveParams {
     const BvhNode *unit_nodes;
     const int32_t *unit_order;
     const float *unit_recs; // [n_faces*16] face records of the lockstep receiver query
-    // hit history of the environment trace (rfrt_trace's dense dumps), or NULL: the iterations before the candidate's
-    // bounce are then rebuilt from it instead of being walked again
-    const int32_t *hist_tri;
-    const float *hist_t;
-    int64_t hist_begin;         // ray id of history row 0
-    int64_t hist_rays;          // rows
-    const float *face_normals;  // [n_tris*3] original order (the normals the trace reflects with)
-    float rx_radius;
     float inv_r;
     int32_t n_unit;
     int32_t n_faces;
@@ -807,44 +793,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_receive(const ReceivePa
         rx.unit_nodes = P.unit_nodes; rx.unit_order = P.unit_order;
         rx.cx = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y); rx.cy = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y + 1);
         rx.cz = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y + 2); rx.inv_r = P.inv_r;
-        const float4 *recs = MT ? nullptr : s_recs;
-        const int64_t hrow = (int64_t)cand.x - P.hist_begin;
-        if (P.hist_tri && hrow >= 0 && hrow < P.hist_rays && (int)cand.z <= P.max_bounces) {
-            // Iterations 0 .. cand.z-1 of kernel.py:57-98 from the environment trace's own record: until its first
-            // receiver hit the ray of this pair IS the environment trajectory (same positions, directions and
-            // closest hits, bit for bit), so (triangle, t) per bounce give every state with the trace's arithmetic
-            // — advance + reflect with the build-time normal — and no BVH walk.  The receiver test of those
-            // iterations is still made wherever the trace's own sphere filter admits a hit (it raised a candidate
-            // there too): a hit there makes this candidate a duplicate of that earlier one.
-            using Ray = typename std::conditional<MT, MtRay, WoopRay>::type;
-            const int32_t *ht = P.hist_tri + hrow * P.max_bounces;
-            const float *hd = P.hist_t + hrow * P.max_bounces;
-            float3 dir = ray_direction(cand.x), pos = P.tx;
-            sink.vertex(0, pos);
-            bool duplicate = false;
-            for (int j = 0; j < (int)cand.z; ++j) {
-                const int f = __ldg(ht + j);
-                const float t_env = __ldg(hd + j);
-                if (f < 0) { duplicate = true; break; } // (cannot happen: the ray was alive at bounce cand.z)
-                if (rx_sphere_filter(pos, dir, rx.cx, rx.cy, rx.cz, P.rx_radius, t_env)) {
-                    const Ray wr = tri_ray_setup<Ray>(pos, dir);
-                    float t_rx = 0.0f;
-                    bool hit_rx;
-                    if constexpr (!MT) hit_rx = rx_query_sweep(rx, recs, c_rx_faces, P.n_faces, wr, pos, dir, 1.0e6f, t_rx);
-                    else hit_rx = rx_query(rx, c_rx_faces, P.n_faces, wr, pos, dir, 1.0e6f, stack, stack_t, STRIDE, t_rx);
-                    if (hit_rx && t_env > t_rx) { duplicate = true; break; } // kernel.py:85
-                }
-                pos = advance(pos, dir, t_env);   // kernel.py:94
-                sink.vertex(j + 1, pos);          // :95
-                sink.env_face(j + 1, f);
-                const float *nv = P.face_normals + 3 * (int64_t)f;
-                dir = reflect(dir, make_float3(__ldg(nv), __ldg(nv + 1), __ldg(nv + 2))); // :96
-            }
-            if (duplicate) continue;
-            literal_loop<MT>(P.env, &rx, P.n_faces, pos, dir, (int)cand.z, P.max_bounces, stack, stack_t, STRIDE, sink, recs);
-        } else {
-            literal_trace<MT>(P.env, &rx, P.n_faces, P.tx, P.max_bounces, cand.x, stack, stack_t, STRIDE, sink, recs);
-        }
+        literal_trace<MT>(P.env, &rx, P.n_faces, P.tx, P.max_bounces, cand.x, stack, stack_t, STRIDE, sink, MT ? nullptr : s_recs);
         // a candidate raised at a later bounce than the replay's first receiver hit is a duplicate
         if (sink.last_rx_bounce < 0 || sink.first_rx_bounce != (int)cand.z) continue;
         int nverts = sink.last_rx_bounce + 2;
@@ -1130,17 +1079,12 @@ extern "C" int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const
                                   uint64_t *d_counters, double amp0, double light_speed_mps, double sample_rate_hz,
                                   uint32_t *d_rec_ray, int32_t *d_rec_rx, int32_t *d_rec_nverts, int64_t *d_rec_bin,
                                   double *d_rec_amp, double *d_rec_dist, float *d_rec_paths, int64_t rec_capacity,
-                                  const int32_t *d_hist_tri, const float *d_hist_t, int64_t hist_ray_begin,
-                                  int64_t hist_rays, void *stream_)
+                                  void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     Mesh *m = get_mesh(env_mesh);
     RxSet *r = get_rxset(rxset);
     if (!m || !r) { set_error("rfrt_trace_receive: unknown handle"); return RFRT_ERR_HANDLE; }
-    if ((d_hist_tri == nullptr) != (d_hist_t == nullptr) || (d_hist_tri && (hist_ray_begin < 0 || hist_rays < 0))) {
-        set_error("rfrt_trace_receive: the hit history needs both arrays and a non-negative ray range");
-        return RFRT_ERR_INVALID;
-    }
     if (!h_tx_pos || !d_candidates || !d_counters || !d_rec_ray || !d_rec_rx || !d_rec_nverts || !d_rec_bin ||
         !d_rec_amp || !d_rec_dist || rec_capacity <= 0 || cand_capacity <= 0) {
         set_error("rfrt_trace_receive: null buffer or empty capacity");
@@ -1156,8 +1100,6 @@ extern "C" int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const
     P.rx_verts = r->verts; P.n_unit = r->n_unit; P.n_faces = r->n_faces;
     P.rx_centers = r->centers; P.unit_nodes = r->unit_bvh.nodes; P.unit_order = r->unit_bvh.prim_order;
     P.unit_recs = r->unit_recs;
-    P.hist_tri = d_hist_tri; P.hist_t = d_hist_t; P.hist_begin = hist_ray_begin; P.hist_rays = d_hist_tri ? hist_rays : 0;
-    P.face_normals = m->face_normals; P.rx_radius = (float)r->radius;
     P.inv_r = (float)(1.0 / r->radius);
     P.tx = make_float3(h_tx_pos[0], h_tx_pos[1], h_tx_pos[2]);
     P.max_bounces = max_bounces;

@@ -630,81 +630,120 @@ __device__ __forceinline__ bool rx_enumerate_coop(const BvhNode *__restrict__ rx
 // the edge distances of the handful of faces whose plane is crossed inside the receiver's sphere (stage B), where the
 // unit-BVH walk left 7.7 of 32 lanes active.  The ray is mapped into unit space in fp32, so the tolerance also carries the rounding of
 // that mapping (2^-21 * (|c|_1 + |p|_1) / r).
+//
+// RxFaceCache: the candidate faces are a property of the LINE.  A receiver hit moves the origin along the ray and keeps
+// the direction (kernel.py:87), so the queries that follow it — the exit through the far side, the t ~ 0 repeats — run
+// on the same line up to the rounding of `advance` (one ulp of the position, an eighth of the mapping tolerance above):
+// a face the filter dropped for the first origin (plane crossed outside the chord of the inflated sphere, behind the
+// origin, or outside the face by more than the tolerance) stays dropped for every later origin on that line, because
+// the later origins lie farther along the ray (what was behind stays behind) and no farther from the receiver than the
+// first origin or the receiver's own sphere (their tolerance is no larger than the one taken here).  The first query
+// of a line therefore stores its candidate masks — computed with TWICE that tolerance — and the later ones run only
+// the exact tests on them (4-5 queries per received pair on a dense lattice:
+// the filter stages were 2/3 of the replay kernel's instructions).  The caller invalidates the cache whenever the
+// direction changes.
+struct RxFaceCache {
+    unsigned m[4]; // candidate faces, 32 per word (n_faces <= 128)
+    bool valid;
+};
+
 __device__ __forceinline__ bool rx_query_sweep(const RxView &rx, const float4 *s_recs, const uint8_t *faces, int n_faces,
-                                               const WoopRay &wr, float3 pos, float3 dir, float max_t, float &t_out)
+                                               const WoopRay &wr, float3 pos, float3 dir, float max_t, float &t_out,
+                                               RxFaceCache *cache = nullptr)
 {
-    const float3 ou = make_float3((pos.x - rx.cx) * rx.inv_r, (pos.y - rx.cy) * rx.inv_r, (pos.z - rx.cz) * rx.inv_r);
-    const float3 du = make_float3(dir.x * rx.inv_r, dir.y * rx.inv_r, dir.z * rx.inv_r);
-    const float far = fmaxf(fmaxf(fabsf(ou.x), fabsf(ou.y)), fabsf(ou.z));
-    const bool all_faces = !(far <= 8192.0f); // origin farther than 8192 radii (or NaN): unit space too coarse
-    const float dl = (1.0f + fabsf(ou.x) + fabsf(ou.y) + fabsf(ou.z)) * (1.0f / 65536.0f) +
-                     (fabsf(rx.cx) + fabsf(rx.cy) + fabsf(rx.cz) + fabsf(pos.x) + fabsf(pos.y) + fabsf(pos.z)) * rx.inv_r * (1.0f / 2097152.0f);
-    const float dd = du.x * du.x + du.y * du.y + du.z * du.z;
-    const float dl_h = dl * (sqrt_approx(dd) * 1.001f);
-    // Stage A works on the chord of the unit sphere inflated by 1 % (+ tolerance): the shape lies inside the unit
-    // sphere, so a face can only be hit where its plane is crossed inside that sphere, and not behind the origin.
-    // (Chord through the closest-approach point: no cancellation for far origins.)
-    const float inv_dd = rcp_approx(dd);
-    const float tc = -(ou.x * du.x + ou.y * du.y + ou.z * du.z) * inv_dd;
-    const float mx = fmaf(tc, du.x, ou.x), my = fmaf(tc, du.y, ou.y), mz = fmaf(tc, du.z, ou.z);
-    const float rho2 = 1.0201f + 4.0f * dl + 1.0e-3f * far * (1.0f / 8192.0f);
-    const float half2 = (rho2 - (mx * mx + my * my + mz * mz)) * inv_dd;
-    float best = max_t;
-    const float half = sqrt_approx(half2);
-    // no hit is possible when the line misses the inflated sphere, or when the whole chord lies more than 0.05 radii
-    // behind the origin (hits need t >= 0); NaN falls through to the sweep
-    const bool can_hit = all_faces || !(half2 < 0.0f || (tc + half) * sqrt_approx(dd) < -0.05f);
-    if (can_hit) {
-        const float lo0 = all_faces ? -3.0e38f : fmaxf(tc - half, 0.0f), hi0 = all_faces ? 3.0e38f : tc + half;
+    unsigned masks[4] = {0u, 0u, 0u, 0u};
+    if (cache && cache->valid) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) masks[w] = cache->m[w];
+    } else {
+        const float slack = cache ? 2.0f : 1.0f;
+        const float3 ou = make_float3((pos.x - rx.cx) * rx.inv_r, (pos.y - rx.cy) * rx.inv_r, (pos.z - rx.cz) * rx.inv_r);
+        const float3 du = make_float3(dir.x * rx.inv_r, dir.y * rx.inv_r, dir.z * rx.inv_r);
+        const float far = fmaxf(fmaxf(fabsf(ou.x), fabsf(ou.y)), fabsf(ou.z));
+        const bool all_faces = !(far <= 8192.0f); // origin farther than 8192 radii (or NaN): unit space too coarse
+        // (with a cache: later origins of the line lie on or inside the inflated sphere, |ou|_1 <= 1.75, or between
+        // the first origin and the sphere)
+        const float ou1 = fabsf(ou.x) + fabsf(ou.y) + fabsf(ou.z);
+        const float dl = slack * ((1.0f + (cache ? fmaxf(ou1, 1.75f) : ou1)) * (1.0f / 65536.0f) +
+                                  (fabsf(rx.cx) + fabsf(rx.cy) + fabsf(rx.cz) + fabsf(pos.x) + fabsf(pos.y) + fabsf(pos.z)) * rx.inv_r * (1.0f / 2097152.0f));
+        const float dd = du.x * du.x + du.y * du.y + du.z * du.z;
+        const float dl_h = dl * (sqrt_approx(dd) * 1.001f);
+        // Stage A works on the chord of the unit sphere inflated by 1 % (+ tolerance): the shape lies inside the unit
+        // sphere, so a face can only be hit where its plane is crossed inside that sphere, and not behind the origin.
+        // (Chord through the closest-approach point: no cancellation for far origins.)
+        const float inv_dd = rcp_approx(dd);
+        const float tc = -(ou.x * du.x + ou.y * du.y + ou.z * du.z) * inv_dd;
+        const float mx = fmaf(tc, du.x, ou.x), my = fmaf(tc, du.y, ou.y), mz = fmaf(tc, du.z, ou.z);
+        const float rho2 = 1.0201f + 4.0f * dl + 1.0e-3f * far * (1.0f / 8192.0f);
+        const float half2 = (rho2 - (mx * mx + my * my + mz * mz)) * inv_dd;
+        const float half = sqrt_approx(half2);
+        // no hit is possible when the line misses the inflated sphere, or when the whole chord lies more than 0.05 radii
+        // behind the origin (hits need t >= 0); NaN falls through to the sweep
+        const bool can_hit = all_faces || !(half2 < 0.0f || (tc + half) * sqrt_approx(dd) < -0.05f);
+        if (can_hit) {
+            const float lo0 = all_faces ? -3.0e38f : fmaxf(tc - half, 0.0f), hi0 = all_faces ? 3.0e38f : tc + half;
 #pragma unroll 1
-        for (int f0 = 0; f0 < n_faces; f0 += 32) {
-            const int cnt = n_faces - f0 < 32 ? n_faces - f0 : 32;
-            // Stage A (lockstep, plane parameter only) for faces f0 .. f0 + cnt - 1
-            unsigned dropped = 0u;
-            const float4 *rec = s_recs + 4 * (f0 + cnt - 1);
+            for (int f0 = 0; f0 < n_faces; f0 += 32) {
+                const int cnt = n_faces - f0 < 32 ? n_faces - f0 : 32;
+                // Stage A (lockstep, plane parameter only) for faces f0 .. f0 + cnt - 1
+                unsigned dropped = 0u;
+                const float4 *rec = s_recs + 4 * (f0 + cnt - 1);
 #pragma unroll 4
-            for (int k = 0; k < cnt; ++k, rec -= 4) { // backwards: face f0 + j ends up at bit j
-                const float4 P = rec[0];
-                const float nd = fmaf(P.x, du.x, fmaf(P.y, du.y, P.z * du.z));
-                const float np = fmaf(P.x, ou.x, fmaf(P.y, ou.y, fmaf(P.z, ou.z, -P.w)));
-                const float r = rcp_approx(nd);
-                const float t = -np * r;
-                const float kt = dl * fabsf(r);
-                // sign set <=> t + kt < lo0 or t - kt > hi0 (NaN operands are ignored by min: kept)
-                dropped = __funnelshift_l(__float_as_uint(fminf((t + kt) - lo0, hi0 - (t - kt))), dropped, 1);
-            }
-            unsigned m = ~dropped & (cnt >= 32 ? 0xffffffffu : (1u << cnt) - 1u);
-            // Stage B (per lane, the few faces left): in-plane edge distances of the plane hit point
-            if (!all_faces) {
-                unsigned mb = m;
-                while (mb) {
-                    const int b = __ffs((int)mb) - 1;
-                    mb &= mb - 1u;
-                    const float4 *fr = s_recs + 4 * (f0 + b);
-                    const float4 P = fr[0], e0 = fr[1], e1 = fr[2], e2 = fr[3];
+                for (int k = 0; k < cnt; ++k, rec -= 4) { // backwards: face f0 + j ends up at bit j
+                    const float4 P = rec[0];
                     const float nd = fmaf(P.x, du.x, fmaf(P.y, du.y, P.z * du.z));
                     const float np = fmaf(P.x, ou.x, fmaf(P.y, ou.y, fmaf(P.z, ou.z, -P.w)));
                     const float r = rcp_approx(nd);
                     const float t = -np * r;
-                    const float thr = -(dl_h * fabsf(r));
-                    const float hx = fmaf(t, du.x, ou.x), hy = fmaf(t, du.y, ou.y), hz = fmaf(t, du.z, ou.z);
-                    const float d0 = fmaf(e0.x, hx, fmaf(e0.y, hy, fmaf(e0.z, hz, e0.w)));
-                    const float d1 = fmaf(e1.x, hx, fmaf(e1.y, hy, fmaf(e1.z, hz, e1.w)));
-                    const float d2 = fmaf(e2.x, hx, fmaf(e2.y, hy, fmaf(e2.z, hz, e2.w)));
-                    if (min3f(d0, d1, d2) < thr) m &= ~(1u << b); // definitely outside the face (false for NaN: kept)
+                    const float kt = dl * fabsf(r);
+                    // sign set <=> t + kt < lo0 or t - kt > hi0 (NaN operands are ignored by min: kept)
+                    dropped = __funnelshift_l(__float_as_uint(fminf((t + kt) - lo0, hi0 - (t - kt))), dropped, 1);
                 }
-            }
-            // exact test on the survivors (a separate loop: the lanes that still hold a face run it together)
-            while (m) {
-                const int b = __ffs((int)m) - 1;
-                m &= m - 1u;
-                const int f = f0 + b;
-                const float *v = rx.verts;
-                float t;
-                if (woop_hit_mem(wr, v + 3 * faces[3 * f], v + 3 * faces[3 * f + 1], v + 3 * faces[3 * f + 2], t) && t < best && t >= 0.0f)
-                    best = t;
+                unsigned m = ~dropped & (cnt >= 32 ? 0xffffffffu : (1u << cnt) - 1u);
+                // Stage B (per lane, the few faces left): in-plane edge distances of the plane hit point
+                if (!all_faces) {
+                    unsigned mb = m;
+                    while (mb) {
+                        const int b = __ffs((int)mb) - 1;
+                        mb &= mb - 1u;
+                        const float4 *fr = s_recs + 4 * (f0 + b);
+                        const float4 P = fr[0], e0 = fr[1], e1 = fr[2], e2 = fr[3];
+                        const float nd = fmaf(P.x, du.x, fmaf(P.y, du.y, P.z * du.z));
+                        const float np = fmaf(P.x, ou.x, fmaf(P.y, ou.y, fmaf(P.z, ou.z, -P.w)));
+                        const float r = rcp_approx(nd);
+                        const float t = -np * r;
+                        const float thr = -(dl_h * fabsf(r));
+                        const float hx = fmaf(t, du.x, ou.x), hy = fmaf(t, du.y, ou.y), hz = fmaf(t, du.z, ou.z);
+                        const float d0 = fmaf(e0.x, hx, fmaf(e0.y, hy, fmaf(e0.z, hz, e0.w)));
+                        const float d1 = fmaf(e1.x, hx, fmaf(e1.y, hy, fmaf(e1.z, hz, e1.w)));
+                        const float d2 = fmaf(e2.x, hx, fmaf(e2.y, hy, fmaf(e2.z, hz, e2.w)));
+                        if (min3f(d0, d1, d2) < thr) m &= ~(1u << b); // definitely outside the face (false for NaN: kept)
+                    }
+                }
+                masks[f0 >> 5] = m;
             }
         }
+        if (cache) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) cache->m[w] = masks[w];
+            cache->valid = true;
+        }
+    }
+    // exact test on the candidates (a separate loop: the lanes that still hold a face run it together; ONE copy of the
+    // test in the instruction stream — unrolled per mask word the kernel outgrew the instruction cache)
+    float best = max_t;
+    unsigned m0 = masks[0], m1 = masks[1], m2 = masks[2], m3 = masks[3];
+#pragma unroll 1
+    while (m0 | m1 | m2 | m3) {
+        int f;
+        if (m0) { f = __ffs((int)m0) - 1; m0 &= m0 - 1u; }
+        else if (m1) { f = 31 + __ffs((int)m1); m1 &= m1 - 1u; }
+        else if (m2) { f = 63 + __ffs((int)m2); m2 &= m2 - 1u; }
+        else { f = 95 + __ffs((int)m3); m3 &= m3 - 1u; }
+        const float *v = rx.verts;
+        float t;
+        if (woop_hit_mem(wr, v + 3 * faces[3 * f], v + 3 * faces[3 * f + 1], v + 3 * faces[3 * f + 2], t) && t < best && t >= 0.0f)
+            best = t;
     }
     t_out = best;
     return best < max_t;

@@ -303,15 +303,13 @@ class Tracer:
         return power
 
     def coverage(self, tx_pos, tx_power, rx_positions, rx_radius, carrier_hz=2.4e9, dense_budget_bytes=96 << 30,
-                 ray_chunk=None, history=None):
+                 ray_chunk=None):
         """coverage.py:38-57 without the per-receiver re-trace: one trace, every receiver tested per segment.
 
         Dense mode (default when the (R, L) float64 impulse responses fit `dense_budget_bytes`): rays are traced
         in chunks sized to the device work lists, every chunk's records are binned into the resident impulse
         responses (atomics), ranks combine them with ONE all-reduce, and the power kernel reads the rows once.
         Otherwise the sparse record path (sort + CSR) is used.
-        ``history``: keep the trace's hit history so the replay rebuilds a candidate's first iterations instead of
-        walking the BVH again (default: on for lattices of >= 1024 receivers, where every ray is replayed many times).
         Returns dict(power (R,) linear, dbm (R,), stats)."""
         centers = np.ascontiguousarray(np.asarray(rx_positions, dtype=np.float64).reshape(-1, 3))
         n_rx = centers.shape[0]
@@ -325,11 +323,7 @@ class Tracer:
         with torch.cuda.device(self.device):
             ir = torch.zeros((n_rx, L), dtype=torch.float64, device=self.device)
             chunk = int(ray_chunk or min(max(end - begin, 1), 1 << 22))
-            if history is None:
-                history = n_rx >= 1024
-            hist_rays = max(chunk, min(max(end - begin, 1), 1 << 22)) if history else 0
-            max_chunk = hist_rays if history else 1 << 26
-            job = TraceJob(self, centers, rx_radius, False, self.max_candidates, self.max_records, history_rays=hist_rays)
+            job = TraceJob(self, centers, rx_radius, False, self.max_candidates, self.max_records)
             stats = dict(segments=0, env_hits=0, candidates=0, records=0)
             try:
                 pos = begin
@@ -341,7 +335,7 @@ class Tracer:
                         if hi - pos <= 1024:
                             job.close()
                             job = TraceJob(self, centers, rx_radius, False, max(2 * job.cand_capacity, c["candidates"] + 1),
-                                           max(2 * job.rec_capacity, c["candidates"] + 1), history_rays=hist_rays)
+                                           max(2 * job.rec_capacity, c["candidates"] + 1))
                         else:
                             chunk = max(1024, (hi - pos) // 2)
                         continue
@@ -351,7 +345,7 @@ class Tracer:
                     pos = hi
                     # grow / shrink the chunk so the work lists run ~60 % full
                     fill = max(c["candidates"] / job.cand_capacity, c["records"] / job.rec_capacity, 1e-9)
-                    chunk = int(min(max(1024, chunk * 0.6 / fill), max_chunk))
+                    chunk = int(min(max(1024, chunk * 0.6 / fill), 1 << 26))
             finally:
                 job.close()
             if self._world > 1:
@@ -486,10 +480,7 @@ class TraceJob:
     synchronisation: [directions ->] environment trace -> literal replay of the candidates -> (optional)
     impulse-response binning."""
 
-    def __init__(self, tracer, rx_positions, rx_radius, want_paths, cand_capacity, rec_capacity, history_rays=0):
-        """history_rays > 0: keep the environment trace's hit history (triangle, t per bounce) of waves of up to that
-        many rays, so that the replay rebuilds a candidate's first iterations instead of walking the BVH again
-        (8 bytes per ray and bounce; pays when rays are replayed for many receivers each: dense lattices)."""
+    def __init__(self, tracer, rx_positions, rx_radius, want_paths, cand_capacity, rec_capacity):
         self.t = tracer
         dev = tracer.device
         B = tracer.max_bounces
@@ -512,9 +503,6 @@ class TraceJob:
                             amp=torch.empty(rc, dtype=torch.float64, device=dev),
                             dist=torch.empty(rc, dtype=torch.float64, device=dev),
                             paths=torch.empty((rc, B + 1, 3), dtype=torch.float32, device=dev) if want_paths else None)
-            self.history_rays = int(history_rays)
-            self.hist_tri = torch.empty((self.history_rays, B), dtype=torch.int32, device=dev) if history_rays else None
-            self.hist_t = torch.empty((self.history_rays, B), dtype=torch.float32, device=dev) if history_rays else None
         self.kernel_launches = 0
 
     def enqueue(self, tx_pos, tx_power, ray_range=None, dirs=None, ir=None):
@@ -524,19 +512,16 @@ class TraceJob:
         begin, end = ray_range if ray_range is not None else t.ray_range
         n, B = end - begin, t.max_bounces
         tx = float3(tx_pos)
-        # the hit history covers this call when all its rays fit the history rows
-        hist = 0 < n <= self.history_rays
-        h_tri, h_t = (self.hist_tri, self.hist_t) if hist else (None, None)
         with torch.cuda.device(t.device):
             self.counters_t.zero_()
             if dirs is None:
                 check(lib.rfrt_trace(t._env, self.rxset, tx, B, begin, end, t.trace_flags, _ptr(t._scratch(n)), t.chunk_rays,
-                                     _ptr(self.counters_t), _ptr(self.cands), self.cand_capacity, _ptr(h_tri), _ptr(h_t),
+                                     _ptr(self.counters_t), _ptr(self.cands), self.cand_capacity, None, None,
                                      _stream_ptr()), "rfrt_trace")
                 self.kernel_launches += 2 * max(1, -(-n // t.chunk_rays))
             else:
                 check(lib.rfrt_trace(t._env, self.rxset, tx, B, begin, end, _lib.FLAG_DIRS_READY | t.trace_flags, _ptr(dirs), n, _ptr(self.counters_t),
-                                     _ptr(self.cands), self.cand_capacity, _ptr(h_tri), _ptr(h_t), _stream_ptr()), "rfrt_trace")
+                                     _ptr(self.cands), self.cand_capacity, None, None, _stream_ptr()), "rfrt_trace")
                 self.kernel_launches += 1
             amp0 = tx_power / t.tx_num_rays if t.tx_num_rays else 0.0  # tracer.py:103
             r = self.rec
@@ -544,8 +529,7 @@ class TraceJob:
                                          _ptr(self.counters_t), float(amp0), float(t.light_speed_mps),
                                          float(t.sample_rate_hz), _ptr(r["ray"]), _ptr(r["rx"]), _ptr(r["nverts"]),
                                          _ptr(r["bin"]), _ptr(r["amp"]), _ptr(r["dist"]), _ptr(r["paths"]),
-                                         self.rec_capacity, _ptr(h_tri), _ptr(h_t), begin, n if hist else 0,
-                                         _stream_ptr()), "rfrt_trace_receive")
+                                         self.rec_capacity, _stream_ptr()), "rfrt_trace_receive")
             self.kernel_launches += 1
             if ir is not None:
                 ir.zero_()

@@ -358,37 +358,3 @@ def test_headless_coverage_driver(torch_cuda, room_stl, tmp_path):
         else:
             np.testing.assert_allclose(cov["power"][k], p, rtol=1e-4)
             np.testing.assert_allclose(flat[k], post.to_dbm(p), rtol=1e-4, atol=1e-3)
-
-
-@pytest.mark.parametrize("scene", ["terrain", "room"])
-def test_replay_from_hit_history_is_identical(torch_cuda, room_stl, scene):
-    """rfrt_trace_receive with the trace's hit history (iterations before the candidate's bounce rebuilt from
-    (triangle, t) instead of walked again) produces the same records, bit for bit, as the literal replay from the
-    transmitter — on a lattice dense enough that most rays are replayed for several receivers and after a bounce."""
-    from rf_ray_tracing_warp_b200 import load_mesh, synthetic_terrain
-    from rf_ray_tracing_warp_b200.coverage import plane_lattice
-    from rf_ray_tracing_warp_b200.tracer import TraceJob
-    if scene == "terrain":
-        mesh, tx, B, n = synthetic_terrain(96, 20.0, 17), [10, 0, 4.5], 6, 1 << 17
-        rx, radius = plane_lattice(48, 48, z=3.0), 0.5
-    else:
-        mesh, tx, B, n = load_mesh(room_stl), [10, 0, 5], 5, 1 << 17
-        rx, radius = plane_lattice(24, 24, z=5.0, extent=12.0), 0.6
-    from rf_ray_tracing_warp_b200 import Tracer
-    tr = Tracer(mesh, C, 100e9, 100e-9, B, n)
-    out = []
-    for hist in (0, n):
-        job = TraceJob(tr, rx, radius, True, 1 << 23, 1 << 23, history_rays=hist)
-        job.enqueue(tx, 1.0)
-        c = job.counters()
-        assert c["candidates"] <= job.cand_capacity and c["records"] <= job.rec_capacity
-        k = c["records"]
-        rec = {name: v[:k].cpu().numpy() for name, v in job.rec.items()}
-        order = np.lexsort((rec["ray"].view(np.uint32), rec["rx"]))
-        out.append(({name: v[order] for name, v in rec.items()}, c))
-        job.close()
-    (a, ca), (b, cb) = out
-    assert ca == cb and ca["records"] > 20000
-    assert (a["nverts"] > 2).mean() > 0.1  # a good share of the paths has at least one environment bounce
-    for name in a:
-        assert np.array_equal(a[name].view(np.uint8), b[name].view(np.uint8)), name
