@@ -431,7 +431,7 @@ def main():
                              "kernel": "k_trace_small", "kernel_ms": k_ms,
                              "how": "the 44-triangle scene and the ray states live in shared memory, so instruction issue bounds "
                                     "this kernel, not HBM: achieved = warp instructions per launch (smsp__inst_executed.sum of the "
-                                    "committed ncu capture of this command, profiles/ncu_summary.json, scaled by this run's segment "
+                                    "committed ncu capture of this kernel on this scene and receiver set, profiles/ncu_summary.json, scaled by this run's segment "
                                     "count) / the kernel's CUDA-event time in THIS run; peak = SMs x 4 schedulers x the SM clock "
                                     "sampled in this run",
                              "active_lanes_per_instruction": ncu.get("active_lanes"), "issue_active_pct_ncu": ncu.get("issue_active_pct"),
