@@ -157,7 +157,11 @@ __device__ __forceinline__ void rx_filter_and_emit(const TraceParams &P, int k, 
 
 // Receivers of one finished segment, per lane (sparse receiver sets): the segment's own box against the bounds of all
 // receivers (no division: most segments of a sparse set stop here), then this lane walks the receiver BVH with its
-// column of the shared-memory stack.
+// column of the shared-memory stack.  The receivers whose box the segment overlaps are only QUEUED during the walk (a
+// few entries of local memory) and filtered + appended afterwards, in a loop that the lanes with queued receivers run
+// together: handled right where the walk finds them, the sphere filter and the append ran at 2 of 32 lanes and were
+// half of the trace kernel's instructions on a 256 x 256 lattice (C2).
+constexpr int RX_LANE_QUEUE = 12;
 __device__ __forceinline__ void receivers_lane(const TraceParams &P, float3 pos, float3 dir, float t_limit, uint32_t gid,
                                                int bounce, int *stack, int stride)
 {
@@ -169,28 +173,39 @@ __device__ __forceinline__ void receivers_lane(const TraceParams &P, float3 pos,
     const bool near_rx = fminf(pos.x, ex) <= P.rx_hi[0] && fmaxf(pos.x, ex) >= P.rx_lo[0] &&
                          fminf(pos.y, ey) <= P.rx_hi[1] && fmaxf(pos.y, ey) >= P.rx_lo[1] &&
                          fminf(pos.z, ez) <= P.rx_hi[2] && fmaxf(pos.z, ez) >= P.rx_lo[2];
+    if (!near_rx) return;
     const SlabRay sr = slab_setup_fast(pos, dir);
-    int sp = 0;
-    int node = near_rx ? 0 : -1;
-    while (node >= 0) {
-        const float4 *np = reinterpret_cast<const float4 *>(P.rx_nodes + node);
-        float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-        int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
-        float tn0, tn1;
-        bool h0 = slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_limit, tn0);
-        bool h1 = slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_limit, tn1);
-        int c0 = q3.x, c1 = q3.y;
-        if (c1 == c0) h1 = false;
-        if (h0) {
-            if (c0 < 0) rx_filter_and_emit(P, __ldg(P.rx_order + (~c0)), pos, dir, t_limit, gid, bounce);
-            else { stack[sp * stride] = c0; ++sp; }
+    int queue[RX_LANE_QUEUE];
+    int qn = 0, sp = 0;
+    // next internal node from the stack; leaf entries (deferred while the queue was full) move to the queue on the way.
+    // TRAV_DONE when the stack is empty or the queue is full (the caller drains it and asks again)
+    auto pop = [&]() -> int {
+        while (sp > 0 && qn < RX_LANE_QUEUE) {
+            const int c = stack[(--sp) * stride];
+            if (c >= 0) return c;
+            queue[qn++] = ~c;
         }
-        if (h1) {
-            if (c1 < 0) rx_filter_and_emit(P, __ldg(P.rx_order + (~c1)), pos, dir, t_limit, gid, bounce);
-            else { stack[sp * stride] = c1; ++sp; }
+        return TRAV_DONE;
+    };
+    int node = 0;
+    for (;;) {
+        while (node >= 0) {
+            const float4 *np = reinterpret_cast<const float4 *>(P.rx_nodes + node);
+            float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+            int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
+            float tn0, tn1;
+            bool h0 = slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_limit, tn0);
+            bool h1 = slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_limit, tn1);
+            const int c0 = q3.x, c1 = q3.y;
+            if (c1 == c0) h1 = false;
+            if (h0) { if (c0 < 0 && qn < RX_LANE_QUEUE) queue[qn++] = ~c0; else { stack[sp * stride] = c0; ++sp; } }
+            if (h1) { if (c1 < 0 && qn < RX_LANE_QUEUE) queue[qn++] = ~c1; else { stack[sp * stride] = c1; ++sp; } }
+            node = pop();
         }
-        node = -1;
-        if (sp > 0) { --sp; node = stack[sp * stride]; }
+        // drain: sphere filter + warp-aggregated append for the queued receivers
+        while (qn > 0) rx_filter_and_emit(P, __ldg(P.rx_order + queue[--qn]), pos, dir, t_limit, gid, bounce);
+        if (sp == 0) break;
+        node = pop();
     }
 }
 
@@ -997,6 +1012,7 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
         if (ex * ez > face) face = ex * ez;
         const double d2 = 4.0 * r->radius * r->radius;
         P.rx_coop = (double)r->n_receivers * d2 >= 8.0 * (face > d2 ? face : d2) ? 1 : 0;
+        if (getenv("RFRT_RX_COOP")) P.rx_coop = atoi(getenv("RFRT_RX_COOP")) ? 1 : 0; // tuning aid
     }
     P.stack_depth = stack_depth_for(m, P.rx_coop ? nullptr : r);
     // DUMP instantiations also accumulate the checksum
