@@ -215,25 +215,47 @@ k_rx_power_dense(const double *__restrict__ ir, int64_t n_bins, double window, d
     const double K = __dmul_rn(__dmul_rn(2.0, 3.141592653589793), carrier);
     const int64_t half = (n_bins - 1) / 2;
 
-    // 1. ordered compaction of the non-zero bins
+    // 1. ordered compaction of the non-zero bins.  The row is taken in blocks of 8 x 2048 bins: every warp owns a
+    //    contiguous 2048-bin slice of the block, reads it with 64 independent loads per lane and remembers which of its
+    //    bins are non-zero in a 64-bit mask (pass a: no barrier, the loads of all warps are in flight together — one
+    //    barrier-separated 256-bin step at a time left this kernel latency-bound at 13 % of the HBM peak); the slices'
+    //    counts give every warp its offset (one barrier), and only the non-zero bins are read again, from cache, to
+    //    be staged in bin order (pass b).
     if (tid == 0) s_total = 0;
     __syncthreads();
-    for (int64_t base = 0; base < n_bins; base += RXP_THREADS) {
-        const int64_t b = base + tid;
-        const double a = b < n_bins ? row[b] : 0.0;
-        const bool nz = a != 0.0;
-        const unsigned m = __ballot_sync(0xffffffffu, nz);
-        if (lane == 0) s_warp_cnt[warp] = __popc(m);
+    constexpr int SLICE = 2048;
+    for (int64_t blk = 0; blk < n_bins; blk += (int64_t)SLICE * (RXP_THREADS / 32)) {
+        const int64_t slice = blk + (int64_t)warp * SLICE;
+        unsigned long long nzmask = 0ull;
+#pragma unroll 8
+        for (int it = 0; it < SLICE / 32; ++it) {
+            const int64_t b = slice + it * 32 + lane;
+            const double a = b < n_bins ? row[b] : 0.0;
+            if (a != 0.0) nzmask |= 1ull << it;
+        }
+        int cnt = __popcll(nzmask);
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) s_warp_cnt[warp] = cnt;
         __syncthreads();
         int off = s_total;
         for (int w = 0; w < warp; ++w) off += s_warp_cnt[w];
-        off += __popc(m & ((1u << lane) - 1u));
-        if (nz && off < RXP_CAP) {
-            double sn, cs;
-            sincos(stx_arg(b, n_bins, window, K), &sn, &cs);
-            s_bin[off] = (int)b;
-            s_re[off] = a * cs;   // a * e^{-i arg(b)}
-            s_im[off] = -a * sn;
+        if (cnt > 0) {
+            for (int it = 0; it < SLICE / 32; ++it) {
+                const bool nz = (nzmask >> it) & 1ull;
+                const unsigned m = __ballot_sync(0xffffffffu, nz);
+                if (m == 0u) continue;
+                const int pos = off + __popc(m & ((1u << lane) - 1u));
+                if (nz && pos < RXP_CAP) {
+                    const int64_t b = slice + it * 32 + lane;
+                    const double a = row[b];
+                    double sn, cs;
+                    sincos(stx_arg(b, n_bins, window, K), &sn, &cs);
+                    s_bin[pos] = (int)b;
+                    s_re[pos] = a * cs;   // a * e^{-i arg(b)}
+                    s_im[pos] = -a * sn;
+                }
+                off += __popc(m);
+            }
         }
         __syncthreads();
         if (tid == 0) {
