@@ -305,7 +305,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, WALK_MIN_CTAS) k_trace_walk(con
     constexpr int STRIDE = LSTACK ? 1 : TRACE_THREADS;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    int *rx_queue = s_stack_raw + 2 * P.stack_depth * TRACE_THREADS + (COOP ? RX_COOP_INTS * (threadIdx.x >> 5) : 0);
+    // per-ray constants of the watertight test, written once per segment in phase A (where the starting lanes compute
+    // them together) and read back at every leaf: (kx | ky << 2 | kz << 4, Sx, Sy, Sz); the permuted origin follows from pos
+    float4 *s_wr = reinterpret_cast<float4 *>(s_stack_raw + 2 * P.stack_depth * TRACE_THREADS) + threadIdx.x;
+    int *rx_queue = s_stack_raw + 2 * P.stack_depth * TRACE_THREADS + 4 * TRACE_THREADS + (COOP ? RX_COOP_INTS * (threadIdx.x >> 5) : 0);
     const int REFILL = P.walk_refill, NODE_MIN = P.walk_node_min;
 
     bool has_ray = false;   // this lane owns a ray
@@ -384,7 +387,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, WALK_MIN_CTAS) k_trace_walk(con
         if (!__any_sync(FULL, has_ray)) break;
         // ---- start the next segment: scene-box test first (a miss is a finished segment with no hit) ----
         if (has_ray && !walking) {
-            sr = slab_setup(pos, dir);
+            // (approximate reciprocals: the slab test only prunes, and a hit point inside a box padded by >= 1e-3 m leaves
+            // a chord of >= 2e-3 m through it, four orders of magnitude above the 2.4e-7 relative error per axis)
+            sr = slab_setup_fast(pos, dir);
             float tn;
             const bool entered = P.n_tris > 0 &&
                                  slab_hit(sr, P.env_lo[0], P.env_lo[1], P.env_lo[2], P.env_hi[0], P.env_hi[1], P.env_hi[2], 1.0e6f, tn);
@@ -392,6 +397,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, WALK_MIN_CTAS) k_trace_walk(con
             walking = true;
             sp = 0;
             node = entered ? 0 : TRAV_DONE;
+            if constexpr (!MT) {
+                if (entered) {
+                    const WoopRay w0 = woop_setup(pos, dir);
+                    *s_wr = make_float4(__int_as_float(w0.kx | (w0.ky << 2) | (w0.kz << 4)), w0.Sx, w0.Sy, w0.Sz);
+                }
+            }
         }
         // ================= phase B: walk until enough lanes wait for phase A =================
         // (a lane waits for phase A when its walk has ended and phase A has something for it: amask)
@@ -410,9 +421,20 @@ __global__ void __launch_bounds__(TRACE_THREADS, WALK_MIN_CTAS) k_trace_walk(con
                 }
             }
             if (node < 0 && node != TRAV_DONE) {
-                // (the per-ray constants of the triangle test are rebuilt here, 2 leaves per segment, instead of
-                // living in 9 registers through the node loop)
-                const Ray wr = tri_ray_setup<Ray>(pos, dir);
+                // (the per-ray constants of the triangle test come back from shared memory instead of living in 9
+                // registers through the node loop)
+                Ray wr;
+                if constexpr (MT) {
+                    wr = tri_ray_setup<Ray>(pos, dir);
+                } else {
+                    const float4 w4 = *s_wr;
+                    const int kk = __float_as_int(w4.x);
+                    wr.kx = kk & 3; wr.ky = (kk >> 2) & 3; wr.kz = (kk >> 4) & 3;
+                    wr.Sx = w4.y; wr.Sy = w4.z; wr.Sz = w4.w;
+                    wr.px = pos.x; wr.py = pos.y; wr.pz = pos.z;
+                    wr.pkx = sel3(pos.x, pos.y, pos.z, wr.kx); wr.pky = sel3(pos.x, pos.y, pos.z, wr.ky);
+                    wr.pkz = sel3(pos.x, pos.y, pos.z, wr.kz);
+                }
                 node = leaf_step(P.tris, node, wr, h, stack, stack_t, STRIDE, sp);
                 if (DUMP) ++n_tests;
             }
@@ -1025,7 +1047,7 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     const bool lstack = !small && P.stack_depth > 16; // deep tree: local-memory stack (<= 64 entries by construction)
     if (lstack && P.stack_depth > 64) { set_error("rfrt_trace: BVH deeper than 64 levels"); return RFRT_ERR_INVALID; }
     if (lstack) P.stack_depth = 0;
-    size_t smem = stack_bytes(P.stack_depth) + (P.rx_coop ? sizeof(int) * RX_COOP_INTS * (TRACE_THREADS / 32) : 0);
+    size_t smem = stack_bytes(P.stack_depth) + sizeof(float4) * TRACE_THREADS + (P.rx_coop ? sizeof(int) * RX_COOP_INTS * (TRACE_THREADS / 32) : 0);
     typedef void (*kern_t)(const TraceParams);
     kern_t kern;
     if (small) {
