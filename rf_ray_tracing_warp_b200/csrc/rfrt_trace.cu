@@ -645,9 +645,10 @@ __device__ __forceinline__ void literal_trace(const LiteralEnv &E, const RxView 
     float3 dir = ray_direction(tid); // kernel.py:51-52
     float3 pos = tx;                 // :53
     sink.vertex(0, pos);             // :55
-    // A receiver hit at t == 0 leaves the ray where it is with the direction it had (kernel.py:87: pos += dir * 0, no
-    // reflection), so every later iteration evaluates the same two queries on the same values and takes the same branch
-    // — the "stuck" paths of the reference's golden scene.  They are replayed without queries.
+    // A receiver hit that leaves the ray where it is — t == 0, or a t so small that pos + dir * t rounds back to pos —
+    // with the direction it had (kernel.py:87, no reflection) makes every later iteration evaluate the same two queries
+    // on the same values and take the same branch: the "stuck" paths of the reference's golden scene (SURVEY.md
+    // Appendix C).  They are replayed without queries.
     bool stuck = false;
     float t_stuck = 0.0f;
     RxFaceCache rx_cache; // candidate faces of the current line (valid from a receiver query until the direction changes)
@@ -679,10 +680,11 @@ __device__ __forceinline__ void literal_trace(const LiteralEnv &E, const RxView 
         bool maybe_hit_env = h.face >= 0;
         bool hit_recv = maybe_hit_rx && (!maybe_hit_env || h.t > t_rx);                                     // :85
         if (hit_recv) {
-            pos = advance(pos, dir, t_rx);  // :87
+            const float3 moved = advance(pos, dir, t_rx);  // :87
+            if (moved.x == pos.x && moved.y == pos.y && moved.z == pos.z) { stuck = true; t_stuck = t_rx; }
+            pos = moved;
             sink.vertex(bounce + 1, pos);   // :88
             sink.received(bounce);          // :89-91
-            if (t_rx == 0.0f) { stuck = true; t_stuck = t_rx; }
         } else if (maybe_hit_env) {
             pos = advance(pos, dir, h.t);   // :94
             sink.vertex(bounce + 1, pos);   // :95
