@@ -21,6 +21,7 @@ namespace rfrt {
 
 namespace {
 
+constexpr int BVH_MAX_DEPTH = 60; // deeper hierarchies are rebuilt over coarser Morton cells (the walk's stack: 64 entries)
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
@@ -81,7 +82,8 @@ __device__ __forceinline__ uint64_t expand_bits21(uint32_t v)
 }
 
 __global__ void k_morton(const float4 *__restrict__ lo, const float4 *__restrict__ hi, int64_t n,
-                         const float *__restrict__ bounds, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int legacy)
+                         const float *__restrict__ bounds, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int legacy,
+                         int drop_bits)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -94,7 +96,7 @@ __global__ void k_morton(const float4 *__restrict__ lo, const float4 *__restrict
     for (int k = 0; k < 3; ++k) {
         float u = (c[k] - bounds[k]) * scale;
         u = fminf(fmaxf(u, 0.0f), 2097151.0f); // (NaN -> 0)
-        q[k] = (uint32_t)u;
+        q[k] = ((uint32_t)u >> drop_bits) << drop_bits; // coarser cells: fewer levels (see build_lbvh)
     }
     if (legacy) {
         // round 1's code, kept for A/B measurements (RFRT_BVH_LEGACY_MORTON=1): 10 bits per axis, every axis
@@ -410,30 +412,39 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
     // values: the primitive index; ping-pongs between out->prim_order and vals_b and ends in out->prim_order
     uint32_t *order = reinterpret_cast<uint32_t *>(out->prim_order);
     static const int legacy_morton = getenv("RFRT_BVH_LEGACY_MORTON") ? atoi(getenv("RFRT_BVH_LEGACY_MORTON")) : 0;
-    k_morton<<<nb, T, 0, stream>>>(d_lo, d_hi, n, d_bounds, keys_a, order, legacy_morton);
-    uint64_t *src = keys_a, *dst = keys_b;
-    uint32_t *vsrc = order, *vdst = vals_b;
-    for (int pass = 0; pass < 8; ++pass) {
-        int shift = 8 * pass;
-        k_sort_hist<<<nblocks, SORT_THREADS, 0, stream>>>(src, n, shift, ghist, nblocks);
-        k_scan_rows<<<256, 256, 0, stream>>>(ghist, nblocks, ghist + 256ll * nblocks);
-        k_scan_totals<<<1, 256, 0, stream>>>(ghist + 256ll * nblocks);
-        k_sort_scatter<true><<<nblocks, SORT_THREADS, 0, stream>>>(src, dst, n, shift, ghist, ghist + 256ll * nblocks, nblocks, vsrc, vdst);
-        uint64_t *tmpk = src; src = dst; dst = tmpk;
-        uint32_t *tmpv = vsrc; vsrc = vdst; vdst = tmpv;
-    }
-    // after 8 passes the sorted codes are back in keys_a (src) and the sorted primitive indices in out->prim_order
-    RFRT_CUDA(cudaMemsetAsync(d_depth, 0, sizeof(int), stream));
-    if (n == 1) {
-        k_single_prim_node<<<1, 1, 0, stream>>>(d_lo, d_hi, out->pad, out->nodes);
-        out->max_depth = 1;
-    } else {
-        RFRT_CUDA(cudaMemsetAsync(arrive, 0, sizeof(int) * n_nodes, stream));
+    // The walk's stack holds 64 entries, and a hierarchy over 63-bit codes can be deeper than that when the primitives
+    // cluster at many scales (one level per code bit that splits something off).  Such a scene is rebuilt over coarser
+    // cells — 14, then 10 bits per axis: at most 30 levels of code plus log2(n) levels of equal codes split by position.
+    const int bit_choices[3] = {21, 14, 10};
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        k_morton<<<nb, T, 0, stream>>>(d_lo, d_hi, n, d_bounds, keys_a, order, legacy_morton, 21 - bit_choices[attempt]);
+        uint64_t *src = keys_a, *dst = keys_b;
+        uint32_t *vsrc = order, *vdst = vals_b;
+        for (int pass = 0; pass < 8; ++pass) {
+            int shift = 8 * pass;
+            k_sort_hist<<<nblocks, SORT_THREADS, 0, stream>>>(src, n, shift, ghist, nblocks);
+            k_scan_rows<<<256, 256, 0, stream>>>(ghist, nblocks, ghist + 256ll * nblocks);
+            k_scan_totals<<<1, 256, 0, stream>>>(ghist + 256ll * nblocks);
+            k_sort_scatter<true><<<nblocks, SORT_THREADS, 0, stream>>>(src, dst, n, shift, ghist, ghist + 256ll * nblocks, nblocks, vsrc, vdst);
+            uint64_t *tmpk = src; src = dst; dst = tmpk;
+            uint32_t *tmpv = vsrc; vsrc = vdst; vdst = tmpv;
+        }
+        // after 8 passes the sorted codes are back in keys_a (src) and the sorted primitive indices in out->prim_order
+        if (n == 1) {
+            k_single_prim_node<<<1, 1, 0, stream>>>(d_lo, d_hi, out->pad, out->nodes);
+            out->max_depth = 1;
+            break;
+        }
+        RFRT_CUDA(cudaMemsetAsync(d_depth, 0, sizeof(int), stream));
         k_karras<<<(int)((n - 1 + T - 1) / T), T, 0, stream>>>(src, (int)n, children, node_parent, leaf_parent);
-        k_refit<<<nb, T, 0, stream>>>(order, (int)n, d_lo, d_hi, out->pad, children, node_parent, leaf_parent, arrive,
-                                      out->nodes, d_depth);
         k_depth<<<nb, T, 0, stream>>>((int)n, node_parent, leaf_parent, d_depth);
         RFRT_CUDA(cudaMemcpyAsync(&out->max_depth, d_depth, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        RFRT_CUDA(cudaStreamSynchronize(stream));
+        if (out->max_depth > BVH_MAX_DEPTH && attempt < 2 && !legacy_morton) continue;
+        RFRT_CUDA(cudaMemsetAsync(arrive, 0, sizeof(int) * n_nodes, stream));
+        k_refit<<<nb, T, 0, stream>>>(order, (int)n, d_lo, d_hi, out->pad, children, node_parent, leaf_parent, arrive,
+                                      out->nodes, d_depth);
+        break;
     }
     out->n_nodes = n_nodes;
     RFRT_CUDA(cudaStreamSynchronize(stream));

@@ -177,3 +177,36 @@ def test_small_scene_sweep_equals_bvh_and_oracle(torch_cuda, case):
         assert np.array_equal(res[k]["hit_tri"].cpu().numpy(), tri), (case, k)
         assert np.array_equal(res[k]["hit_t"].cpu().numpy().view(np.uint32), t.view(np.uint32)), (case, k)
     assert res[False]["checksum"] == res[True]["checksum"]
+
+
+def test_multi_scale_mesh_keeps_the_hierarchy_within_the_walk_stack(torch_cuda):
+    """Triangles clustered at 22 scales (each cluster 2x closer to a corner than the last) make a hierarchy over 63-bit
+    Morton codes deeper than the walk's 64-entry stack; the builder then falls back to coarser cells.  The answers stay
+    those of the brute-force oracle (any valid BVH returns them)."""
+    from oracle import cpu
+    from rf_ray_tracing_warp_b200 import Tracer
+    rng = np.random.default_rng(3)
+    tris = []
+    for k in range(22):
+        c = 10.0 * 2.0 ** -k * np.ones(3)
+        for _ in range(6):
+            tris.append(c + 0.2 * 2.0 ** -k * rng.normal(size=(3, 3)))
+    soup = np.asarray(tris, dtype=np.float32).reshape(-1, 9)
+    tr = Tracer(_mesh(soup.reshape(-1, 3, 3)), C, 100e9, 200e-9, 1, 1)
+    info = tr.mesh_info()
+    # 21 distinguishable scales x 3 code bits each would need > 60 levels; the 14-bit fallback needs about 45
+    assert info["n_triangles"] == len(soup) and 30 <= info["max_depth"] <= 60, info
+    n = 4000
+    o = rng.uniform(-1, 11, size=(n, 3)).astype(np.float32)
+    target = soup[rng.integers(0, len(soup), n)].reshape(n, 3, 3).mean(axis=1)
+    d = (target - o + rng.normal(scale=0.01, size=(n, 3))).astype(np.float32)
+    t, f = tr.query_closest(o, d)
+    t, f = t.cpu().numpy(), f.cpu().numpy()
+    hits = 0
+    for i in range(n):
+        hit, t_o, f_o = cpu.query(soup, o[i], d[i])
+        assert (f[i] >= 0) == hit
+        if hit:
+            hits += 1
+            assert f[i] == f_o and np.float32(t[i]) == np.float32(t_o)
+    assert hits > n // 4
