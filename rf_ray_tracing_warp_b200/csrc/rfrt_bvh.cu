@@ -440,7 +440,8 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
         k_depth<<<nb, T, 0, stream>>>((int)n, node_parent, leaf_parent, d_depth);
         RFRT_CUDA(cudaMemcpyAsync(&out->max_depth, d_depth, sizeof(int), cudaMemcpyDeviceToHost, stream));
         RFRT_CUDA(cudaStreamSynchronize(stream));
-        if (out->max_depth > BVH_MAX_DEPTH && attempt < 2 && !legacy_morton) continue;
+        const int depth_limit = getenv("RFRT_BVH_MAX_DEPTH") ? atoi(getenv("RFRT_BVH_MAX_DEPTH")) : BVH_MAX_DEPTH; // (test aid)
+        if (out->max_depth > depth_limit && attempt < 2 && !legacy_morton) continue;
         RFRT_CUDA(cudaMemsetAsync(arrive, 0, sizeof(int) * n_nodes, stream));
         k_refit<<<nb, T, 0, stream>>>(order, (int)n, d_lo, d_hi, out->pad, children, node_parent, leaf_parent, arrive,
                                       out->nodes, d_depth);
