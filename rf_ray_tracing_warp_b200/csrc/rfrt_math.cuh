@@ -86,14 +86,19 @@ __device__ __forceinline__ double det_asin_small(double x)
     return __dmul_rn(x, p);
 }
 
+// One series evaluation for all three ranges: written as three branches the 28-step Horner chain was executed three
+// times by every warp (the lanes of a warp fall into all ranges).  Per lane the operations and their operands are the
+// ones of the branchy form — 1 + z for z < -0.5 and 1 - z for z > 0.5 are both 1 - |z|, the same IEEE subtraction.
 __device__ __forceinline__ double det_acos(double z)
 {
     const double PI = 3.141592653589793;
     const double PIO2 = 1.5707963267948966;
-    if (z > 0.5) return __dmul_rn(2.0, det_asin_small(__dsqrt_rn(__dmul_rn(__dsub_rn(1.0, z), 0.5))));
-    if (z < -0.5)
-        return __dsub_rn(PI, __dmul_rn(2.0, det_asin_small(__dsqrt_rn(__dmul_rn(__dadd_rn(1.0, z), 0.5)))));
-    return __dsub_rn(PIO2, det_asin_small(z));
+    const double az = fabs(z);
+    const double x = az > 0.5 ? __dsqrt_rn(__dmul_rn(__dsub_rn(1.0, az), 0.5)) : z;
+    const double p = det_asin_small(x);
+    if (z > 0.5) return __dmul_rn(2.0, p);
+    if (z < -0.5) return __dsub_rn(PI, __dmul_rn(2.0, p));
+    return __dsub_rn(PIO2, p);
 }
 
 // kernel.py:51-52
