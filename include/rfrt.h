@@ -87,7 +87,7 @@ RFRT_API int rfrt_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_
 /* ---------------------------------------------------------------------------------------------
  * Environment mesh + LBVH.   Replaces wp.Mesh(points, velocities=None, indices) at tracer.py:22-24.
  *   d_vertices_xyz : [n_vertices*3] float32      d_indices : [n_triangles*3] int32
- * Builds (on `stream`): per-triangle bounds -> 30-bit Morton codes -> 8-bit LSD radix sort ->
+ * Builds (on `stream`): per-triangle bounds -> 63-bit Morton codes on a cubic grid -> 8-bit LSD radix sort ->
  * Karras hierarchy -> bottom-up refit.  Triangle index == row of d_indices (== STL facet order).
  * Synchronises the stream once before returning (the handle is ready to use on any stream).
  * ------------------------------------------------------------------------------------------- */

@@ -48,7 +48,7 @@ struct TraceParams {
     const double *rx_centers;
     int64_t n_rx;
     float rx_lo[3], rx_hi[3];   // padded bounds of all receivers (cheap pre-test of a segment's box)
-    float env_lo[3], env_hi[3]; // padded bounds of the environment (BVH variants: box trips)
+    float env_lo[3], env_hi[3]; // padded bounds of the environment (BVH scenes: tested before every walk)
     int32_t n_unit;
     int32_t n_faces;
     float rx_radius;
