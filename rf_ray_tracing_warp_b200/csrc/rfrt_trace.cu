@@ -28,6 +28,9 @@ constexpr int TRACE_THREADS = 128;
 constexpr int RX_CAND_BUF = 256; // receivers staged per warp between two appends (cooperative enumeration)
 constexpr int RX_COOP_INTS = RX_QUEUE_CAP + RX_CAND_BUF + 4; // per-warp shared memory of the cooperative enumeration
 constexpr int MAX_RECV_BOUNCES = 32;
+#ifndef RECV_MIN_CTAS
+#define RECV_MIN_CTAS 8
+#endif
 #ifndef WALK_MIN_CTAS
 #define WALK_MIN_CTAS 9
 #endif
@@ -804,7 +807,7 @@ struct ReceiveParams {
 };
 
 template <bool LSTACK, bool MT>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_receive(const ReceiveParams P)
+__global__ void __launch_bounds__(TRACE_THREADS, RECV_MIN_CTAS) k_trace_receive(const ReceiveParams P)
 {
     extern __shared__ __align__(16) int s_stack_raw[];
     int l_stack[LSTACK ? 64 : 1];
