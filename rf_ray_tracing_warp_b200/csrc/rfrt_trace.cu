@@ -297,7 +297,7 @@ constexpr int WALK_UNROLL = WALK_UNROLL_N;
 //         point of phase A; otherwise every lane handles its own receivers right where its segment is finished
 // MT:     the Moeller-Trumbore functor instead of the reference's watertight test (rfrt_mesh_set_triangle_test) // node steps per vote of the node loop
 template <bool DUMP, bool LSTACK, bool COOP, bool MT>
-__global__ void __launch_bounds__(TRACE_THREADS, WALK_MIN_CTAS) k_trace_walk(const TraceParams P)
+__global__ void __launch_bounds__(TRACE_THREADS, COOP ? WALK_MIN_CTAS - 1 : WALK_MIN_CTAS) k_trace_walk(const TraceParams P)
 {
     using Ray = typename std::conditional<MT, MtRay, WoopRay>::type;
     extern __shared__ __align__(16) int s_stack_raw[];
