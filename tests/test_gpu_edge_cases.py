@@ -214,3 +214,33 @@ def test_multi_scale_mesh_keeps_the_hierarchy_within_the_walk_stack(torch_cuda, 
             hits += 1
             assert f[i] == f_o and np.float32(t[i]) == np.float32(t_o)
     assert hits > 300
+
+
+def test_receiver_enumeration_paths_agree(torch_cuda, room_stl, monkeypatch):
+    """64 heavily overlapping receivers on a line: a segment through them overlaps far more receiver boxes than the
+    per-lane enumeration queues at once (12), so its drain-and-resume path runs; the cooperative enumeration of the
+    same set must produce the same records, and both the oracle's for sampled receivers."""
+    from oracle import cpu, geometry, post
+    from rf_ray_tracing_warp_b200 import Tracer, load_mesh
+    n, B, tx, r = 1 << 16, 4, [10, 0, 5], 0.5
+    rxs = np.array([[2.0 + 0.05 * k, 6.0, 5.0] for k in range(64)])
+    results = []
+    for coop in ("0", "1"):
+        monkeypatch.setenv("RFRT_RX_COOP", coop)
+        tr = Tracer(load_mesh(room_stl), C, 100e9, 200e-9, B, n)
+        out = tr.compute_cir_multi(tx, 1, rxs, r, return_paths=True)
+        rec = {k: v.cpu().numpy() for k, v in out["records"].items()}
+        results.append(rec)
+    monkeypatch.delenv("RFRT_RX_COOP")
+    a, b = results
+    assert a["ray"].shape[0] > 2000
+    for name in a:
+        assert np.array_equal(a[name].view(np.uint8), b[name].view(np.uint8)), name
+    soup = geometry.load_stl_soup(room_stl)
+    for k in (0, 31, 63):
+        o = cpu.trace_paths(soup, geometry.rx_soup(rxs[k], r), tx, B, 0, n, instrument=False)
+        o_paths = post.clean_paths(o["received"], o["mask"])
+        sel = a["rx"] == k
+        assert np.array_equal(a["ray"][sel].astype(np.uint32), np.nonzero(o["mask"])[0].astype(np.uint32))
+        for row, nv, op in zip(a["paths"][sel], a["nverts"][sel], o_paths):
+            assert np.array_equal(row[:nv].view(np.uint32), op.view(np.uint32))
