@@ -280,29 +280,65 @@ k_rx_power_dense(const double *__restrict__ ir, int64_t n_bins, double window, d
             s_re[nnz] = ar; s_im[nnz] = ai;
         }
         __syncthreads();
-        // 3. samples
-        // the carrier phase of sample q is linear in q: each thread evaluates sincos once (its first sample, and the
-        // step of RXP_THREADS samples) and then rotates — one fp64 sincos per sample made this kernel fp64-bound
-        // (27 ms for 65 536 x 10 000 bins); re-anchored every 64 steps so the recurrence error stays < 1e-14
-        double sn = 0.0, cs = 1.0, dsn, dcs;
-        sincos(__dmul_rn(K, __dmul_rn((double)RXP_THREADS, __ddiv_rn(window, (double)(n_bins > 1 ? n_bins - 1 : 1)))), &dsn, &dcs);
-        int step = 0;
-        for (int64_t n = tid; n < n_bins && nnz > 0; n += RXP_THREADS, ++step) {
-            const int64_t q = n + half;
-            if ((step & 63) == 0) sincos(stx_arg(q, n_bins, window, K), &sn, &cs);
-            const double sn_q = sn, cs_q = cs;
-            sn = sn_q * dcs + cs_q * dsn;
-            cs = cs_q * dcs - sn_q * dsn;
-            const int64_t lo_bin = q - (n_bins - 1); // valid arrivals: lo_bin <= b_j <= q
-            int lo = 0, hi = nnz;
-            { int a = 0, b = nnz; while (a < b) { int m = (a + b) >> 1; if (s_bin[m] < lo_bin) a = m + 1; else b = m; } lo = a; }
-            { int a = lo, b = nnz; while (a < b) { int m = (a + b) >> 1; if (s_bin[m] <= q) a = m + 1; else b = m; } hi = a; }
-            const int c = hi - lo;
-            if (c == 0) continue;
-            if (c == 1 && s_bin[lo] == q) continue; // the only term is a * sin(0) == 0
-            const double pr = s_re[hi] - s_re[lo], pi = s_im[hi] - s_im[lo];
-            const double s = sn_q * pr + cs_q * pi;
-            if (s != 0.0) { sum += s * s; ++cnt; }
+        // 3. samples, in closed form per RUN.  Sample q = n + half sees the arrivals with q - (L-1) <= b_j <= q, a
+        //    contiguous range [lo, hi) of the sorted bins; as q goes up an arrival enters at q = b_j (> half) and leaves
+        //    at q = b_j + L, and every enter (q <= L-1) precedes every leave (q >= L): at most nnz + 1 runs of samples
+        //    with a constant phasor sum Z = P[hi] - P[lo].  Inside a run s_rx[q] = Im(e^{i d q} Z) with d = K * step, so
+        //        sum_q s_rx[q]^2 = ( m |Z|^2 - Re( Z^2 * sum_q e^{2 i d q} ) ) / 2,   a geometric series:
+        //    O(nnz) work per receiver instead of O(L) (one thread per run), which leaves this kernel with reading the
+        //    rows.  Samples that are exactly zero do not count (np.nonzero, main.py:48): empty windows, and the sample
+        //    q = b_j of a window that holds only arrival j (its one term is a_j sin(0)); agrees with the per-sample
+        //    evaluation to ~1e-12 relative.
+        const double d = __dmul_rn(K, __ddiv_rn(window, (double)(n_bins > 1 ? n_bins - 1 : 1)));
+        double s2d, c2d;
+        sincos(2.0 * d, &s2d, &c2d);
+        const double den_re = 1.0 - c2d, den_im = -s2d;           // 1 - e^{2 i d}
+        const double den2 = den_re * den_re + den_im * den_im;
+        int j_enter = 0;
+        { int a0 = 0, b0 = nnz; while (a0 < b0) { int m = (a0 + b0) >> 1; if (s_bin[m] <= half) a0 = m + 1; else b0 = m; } j_enter = a0; }
+        int n_leave = 0; // arrivals with b_j <= half - 1
+        { int a0 = 0, b0 = nnz; while (a0 < b0) { int m = (a0 + b0) >> 1; if (s_bin[m] < half) a0 = m + 1; else b0 = m; } n_leave = a0; }
+        const int n_enter = nnz - j_enter;
+        const int n_runs = nnz > 0 ? 1 + n_enter + n_leave : 0;
+        const int64_t q_end = half + n_bins;
+        for (int r = tid; r < n_runs; r += RXP_THREADS) {
+            int lo, hi;
+            int64_t qa, qb;
+            if (r <= n_enter) {
+                lo = 0; hi = j_enter + r;
+                qa = r == 0 ? half : (int64_t)s_bin[j_enter + r - 1];
+                qb = r < n_enter ? (int64_t)s_bin[j_enter + r] : (n_leave > 0 ? (int64_t)s_bin[0] + n_bins : q_end);
+            } else {
+                const int k = r - n_enter; // 1 .. n_leave
+                lo = k; hi = nnz;
+                qa = (int64_t)s_bin[k - 1] + n_bins;
+                qb = k < n_leave ? (int64_t)s_bin[k] + n_bins : q_end;
+            }
+            if (qb > q_end) qb = q_end;
+            const int64_t m = qb - qa;
+            if (m <= 0 || hi <= lo) continue;
+            const double zr = s_re[hi] - s_re[lo], zi = s_im[hi] - s_im[lo];
+            // geometric series G = e^{2 i d qa} (1 - e^{2 i d m}) / (1 - e^{2 i d})
+            double sa, ca, sm, cm;
+            sincos(2.0 * d * (double)qa, &sa, &ca);
+            sincos(2.0 * d * (double)m, &sm, &cm);
+            double g_re, g_im;
+            if (den2 > 1.0e-24) {
+                const double nr = 1.0 - cm, ni = -sm;                               // 1 - e^{2 i d m}
+                const double qr = (nr * den_re + ni * den_im) / den2, qi = (ni * den_re - nr * den_im) / den2;
+                g_re = ca * qr - sa * qi; g_im = ca * qi + sa * qr;
+            } else { // 2 d is a multiple of 2 pi: every term of the series equals e^{2 i d qa}
+                g_re = ca * (double)m; g_im = sa * (double)m;
+            }
+            // s = Im(e^{i phi} Z) = |Z| sin(phi + psi):  sum s^2 = (m |Z|^2 - Re(conj-free Z^2 G)) / 2 with Z^2 = (zi + i zr)^2
+            // rotated so that the sine's phase is right: sin(phi) zr + cos(phi) zi = Im(e^{i phi} (zr + i zi))
+            const double z2_re = zr * zr - zi * zi, z2_im = 2.0 * zr * zi;        // (zr + i zi)^2
+            const double mag2 = zr * zr + zi * zi;
+            // Im(w)^2 = (|w|^2 - Re(w^2)) / 2 with w = e^{i phi} (zr + i zi):  Re(w^2) summed = Re(Z^2 G)
+            const double run = 0.5 * ((double)m * mag2 - (z2_re * g_re - z2_im * g_im));
+            unsigned long long c = (unsigned long long)m;
+            if (hi - lo == 1 && (int64_t)s_bin[lo] == qa) --c; // q = b_j with only arrival j in the window: sin(0)
+            if (mag2 != 0.0) { sum += run; cnt += c; }
         }
     } else if (!SECOND) {
         if (tid == 0) power[blockIdx.x] = -1.0; // too dense for the small staging area: left to the second launch
