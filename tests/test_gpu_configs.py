@@ -358,3 +358,38 @@ def test_headless_coverage_driver(torch_cuda, room_stl, tmp_path):
         else:
             np.testing.assert_allclose(cov["power"][k], p, rtol=1e-4)
             np.testing.assert_allclose(flat[k], post.to_dbm(p), rtol=1e-4, atol=1e-3)
+
+
+def test_dense_power_kernel_matches_np_convolve(torch_cuda):
+    """rfrt_rx_power_dense (closed-form sums per run of samples with a constant arrival window) against the literal
+    main.py:39,46-55 evaluation (np.convolve "same", np.nonzero selection) of the same impulse-response rows: sparse
+    rows with arrivals at the window's ends, at the centre bin, single arrivals, an empty row, and even / odd lengths."""
+    import torch
+    from oracle import post
+    from rf_ray_tracing_warp_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(23)
+    for L, window in ((1000, 10e-9), (1001, 10e-9), (10_000, 100e-9)):
+        half = (L - 1) // 2
+        rows = np.zeros((48, L))
+        for k in range(48):
+            nnz = [0, 1, 1, 2, 3][k] if k < 5 else int(rng.integers(1, 60))
+            bins = rng.choice(L, size=nnz, replace=False)
+            if k == 1:
+                bins = np.array([half])            # the one arrival sits on the centre bin
+            if k == 2:
+                bins = np.array([0])
+            if k == 3:
+                bins = np.array([0, L - 1])
+            if k == 4:
+                bins = np.array([half - 1, half, half + 1])
+            rows[k, bins] = rng.uniform(0.1, 2.0, size=len(bins)) * 10.0 ** rng.integers(-9, -3)
+        d_ir = torch.from_numpy(rows).to(dev)
+        power = torch.empty(48, dtype=torch.float64, device=dev)
+        _lib.check(lib.rfrt_rx_power_dense(d_ir.data_ptr(), 48, L, window, 2.4e9, power.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream), "rfrt_rx_power_dense")
+        got = power.cpu().numpy()
+        want = np.array([post.rx_power(rows[k], window) for k in range(48)])
+        assert np.isnan(got[0]) and np.isnan(want[0])
+        np.testing.assert_allclose(got[1:], want[1:], rtol=1e-9, atol=0)
