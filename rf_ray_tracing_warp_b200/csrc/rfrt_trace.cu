@@ -176,7 +176,11 @@ __device__ __forceinline__ void rx_filter_and_emit(const TraceParams &P, int k, 
 // few entries of local memory) and filtered + appended afterwards, in a loop that the lanes with queued receivers run
 // together: handled right where the walk finds them, the sphere filter and the append ran at 2 of 32 lanes and were
 // half of the trace kernel's instructions on a 256 x 256 lattice (C2).
+// RUNS: append a segment's candidates as one contiguous block (sets of many receivers: the replay's neighbouring lanes
+//       then share their ray); otherwise one candidate per lane and step (a dozen instructions instead of a hundred:
+//       the small-scene kernel of sparse sets is sensitive to the size of its loop body — 43.6 vs 46.5 ms on C4)
 constexpr int RX_LANE_QUEUE = 12;
+template <bool RUNS>
 __device__ __forceinline__ void receivers_lane(const TraceParams &P, float3 pos, float3 dir, float t_limit, uint32_t gid,
                                                int bounce, int *stack, int stride)
 {
@@ -217,8 +221,40 @@ __device__ __forceinline__ void receivers_lane(const TraceParams &P, float3 pos,
             if (h1) { if (c1 < 0 && qn < RX_LANE_QUEUE) queue[qn++] = ~c1; else { stack[sp * stride] = c1; ++sp; } }
             node = pop();
         }
-        // drain: sphere filter + warp-aggregated append for the queued receivers
-        while (qn > 0) rx_filter_and_emit(P, __ldg(P.rx_order + queue[--qn]), pos, dir, t_limit, gid, bounce);
+        // drain: sphere filter of the queued receivers, then ONE block of candidate slots per lane (one atomic per group
+        // of lanes that drain together, a shuffle prefix over them): a segment's candidates stay next to each other, so
+        // the replay's neighbouring lanes share their ray (interleaved lane by lane, every lane of a replay warp had
+        // another ray)
+        if (!RUNS) {
+            while (qn > 0) rx_filter_and_emit(P, __ldg(P.rx_order + queue[--qn]), pos, dir, t_limit, gid, bounce);
+            if (sp == 0) break;
+            node = pop();
+            continue;
+        }
+        int m = 0;
+        for (int i = 0; i < qn; ++i) {
+            const int k = __ldg(P.rx_order + queue[i]);
+            const float cx = (float)__ldg(P.rx_centers + 3 * k), cy = (float)__ldg(P.rx_centers + 3 * k + 1),
+                        cz = (float)__ldg(P.rx_centers + 3 * k + 2);
+            if (rx_sphere_filter(pos, dir, cx, cy, cz, P.rx_radius, t_limit)) queue[m++] = k;
+        }
+        qn = 0;
+        if (m > 0) {
+            const unsigned am = __activemask();
+            const int lane = threadIdx.x & 31, leader = __ffs((int)am) - 1;
+            int before = 0, total = 0;
+            for (unsigned rest = am; rest; rest &= rest - 1u) {
+                const int src = __ffs((int)rest) - 1;
+                const int v = __shfl_sync(am, m, src);
+                if (src < lane) before += v;
+                total += v;
+            }
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(&P.counters[RFRT_CTR_CANDIDATES], (unsigned long long)total);
+            base = __shfl_sync(am, base, leader) + (unsigned long long)before;
+            for (int i = 0; i < m; ++i)
+                if ((int64_t)(base + i) < P.cand_capacity) P.candidates[base + i] = make_uint4(gid, (uint32_t)queue[i], (uint32_t)bounce, 0u);
+        }
         if (sp == 0) break;
         node = pop();
     }
@@ -351,7 +387,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, COOP ? WALK_MIN_CTAS - 1 : WALK
             const bool hit_env = h.face >= 0;
             ++n_seg;
             if (!COOP && P.n_rx > 0)
-                receivers_lane(P, pos, dir, hit_env ? h.t : 1.0e6f, (uint32_t)(P.chunk_begin + ray), bounce, stack, STRIDE);
+                receivers_lane<true>(P, pos, dir, hit_env ? h.t : 1.0e6f, (uint32_t)(P.chunk_begin + ray), bounce, stack, STRIDE);
             if (DUMP) {
                 int64_t row = (P.chunk_begin + ray - P.dump_begin) * P.max_bounces + bounce;
                 if (P.hit_tri) P.hit_tri[row] = hit_env ? h.face : -1;
@@ -495,7 +531,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, COOP ? WALK_MIN_CTAS - 1 : WALK
 constexpr int SMALL_SLOTS = 5;       // rays per lane     (measured on room.stl: 2: 28e9, 3: 33.6e9, 4: 34.5e9, 5: 35.1e9
 constexpr int SMALL_REFILL_MIN = 16; // lanes with an empty slot that make a refill pass worth its instructions (8 / 16 / 24: 34.6 / 35.1 / 35.2e9)
 
-template <bool DUMP, int SMALL, bool COOP>
+template <bool DUMP, int SMALL, bool COOP, bool RUNS>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_small(const TraceParams P)
 {
     extern __shared__ __align__(16) int s_raw[];
@@ -602,7 +638,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_small(const TraceParams
         if (seg_done) {
             const bool hit_env = h.face >= 0;
             ++n_seg;
-            if (!COOP && P.n_rx > 0) receivers_lane(P, pos, dir, t_limit, gid, bounce, stack, TRACE_THREADS);
+            if (!COOP && P.n_rx > 0) receivers_lane<RUNS>(P, pos, dir, t_limit, gid, bounce, stack, TRACE_THREADS);
             if (DUMP) {
                 int64_t row = (P.chunk_begin + ray - P.dump_begin) * P.max_bounces + bounce;
                 if (P.hit_tri) P.hit_tri[row] = hit_env ? h.face : -1;
@@ -1071,11 +1107,17 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
         // several rays per lane: ray slots | scene image | one int column per thread for the receiver walk | queues
         smem = sizeof(float4) * 2 * SMALL_SLOTS * TRACE_THREADS + sizeof(float) * small_image_floats(m->small_pairs, (int)P.n_tris) +
                sizeof(int) * P.stack_depth * TRACE_THREADS + (P.rx_coop ? sizeof(int) * RX_COOP_INTS * (TRACE_THREADS / 32) : 0);
-        static const kern_t small_kerns[2][2][2] = {
-            {{k_trace_small<false, 1, false>, k_trace_small<true, 1, false>}, {k_trace_small<false, 2, false>, k_trace_small<true, 2, false>}},
-            {{k_trace_small<false, 1, true>, k_trace_small<true, 1, true>}, {k_trace_small<false, 2, true>, k_trace_small<true, 2, true>}},
+        // [cooperative enumeration | per-lane with candidate runs | per-lane, one candidate per step][pairs > 16][dump]
+        static const kern_t small_kerns[3][2][2] = {
+            {{k_trace_small<false, 1, false, false>, k_trace_small<true, 1, false, false>},
+             {k_trace_small<false, 2, false, false>, k_trace_small<true, 2, false, false>}},
+            {{k_trace_small<false, 1, false, true>, k_trace_small<true, 1, false, true>},
+             {k_trace_small<false, 2, false, true>, k_trace_small<true, 2, false, true>}},
+            {{k_trace_small<false, 1, true, false>, k_trace_small<true, 1, true, false>},
+             {k_trace_small<false, 2, true, false>, k_trace_small<true, 2, true, false>}},
         };
-        kern = small_kerns[P.rx_coop ? 1 : 0][m->small_pairs > 16 ? 1 : 0][dump ? 1 : 0];
+        const int rx_mode = P.rx_coop ? 2 : (P.n_rx >= 64 ? 1 : 0);
+        kern = small_kerns[rx_mode][m->small_pairs > 16 ? 1 : 0][dump ? 1 : 0];
     } else {
         static const kern_t walk_kerns[2][2][2][2] = {
             {{{k_trace_walk<false, false, false, false>, k_trace_walk<true, false, false, false>},
