@@ -308,7 +308,9 @@ class Tracer:
 
         Dense mode (default when the (R, L) float64 impulse responses fit `dense_budget_bytes`): rays are traced
         in chunks sized to the device work lists, every chunk's records are binned into the resident impulse
-        responses (atomics), ranks combine them with ONE all-reduce, and the power kernel reads the rows once.
+        responses (atomics), and the power kernel reads the rows once.  Several ranks combine their impulse
+        responses with ONE reduce-scatter (every rank receives the summed rows of R / world receivers: half the
+        traffic of an all-reduce, and the power kernel runs on all GPUs) and all-gather the R powers.
         Otherwise the sparse record path (sort + CSR) is used.
         Returns dict(power (R,) linear, dbm (R,), stats)."""
         centers = np.ascontiguousarray(np.asarray(rx_positions, dtype=np.float64).reshape(-1, 3))
@@ -321,7 +323,9 @@ class Tracer:
             return dict(power=p, dbm=to_dbm(p), stats=dict(self.last_stats), records=rec)
         begin, end = self.ray_range
         with torch.cuda.device(self.device):
-            ir = torch.zeros((n_rx, L), dtype=torch.float64, device=self.device)
+            # (rows padded to a multiple of the world size: the reduce-scatter hands out equal row blocks)
+            rows_per_rank = -(-n_rx // self._world)
+            ir = torch.zeros((rows_per_rank * self._world, L), dtype=torch.float64, device=self.device)
             chunk = int(ray_chunk or min(max(end - begin, 1), 1 << 22))
             job = TraceJob(self, centers, rx_radius, False, self.max_candidates, self.max_records)
             stats = dict(segments=0, env_hits=0, candidates=0, records=0)
@@ -348,13 +352,26 @@ class Tracer:
                     chunk = int(min(max(1024, chunk * 0.6 / fill), 1 << 26))
             finally:
                 job.close()
+            rows = (0, n_rx)
             if self._world > 1:
-                torch.distributed.all_reduce(ir)  # the one exchange step: sum of per-GPU impulse responses (NCCL)
+                dist = torch.distributed
+                mine = torch.empty((rows_per_rank, L), dtype=torch.float64, device=self.device)
+                dist.reduce_scatter_tensor(mine, ir)  # the one exchange step of the data path (NCCL): summed row blocks
+                del ir
+                local = self.rx_power_dense(mine, carrier_hz)
+                power = torch.empty(rows_per_rank * self._world, dtype=torch.float64, device=self.device)
+                dist.all_gather_into_tensor(power, local)  # R scalars
+                power = power[:n_rx]
+                rows = (min(self._rank * rows_per_rank, n_rx), min((self._rank + 1) * rows_per_rank, n_rx))
+                ir = mine[: rows[1] - rows[0]]
                 stats = sharding.sum_stats(stats, self.device)
-            power = self.rx_power_dense(ir, carrier_hz)
+            else:
+                ir = ir[:n_rx]
+                power = self.rx_power_dense(ir, carrier_hz)
             p = power.cpu().numpy()
         self.last_stats = stats
-        return dict(power=p, dbm=to_dbm(p), stats=dict(stats), impulse_response=ir)
+        # impulse_response: the summed rows of receivers [rows[0], rows[1]) (all of them on one GPU)
+        return dict(power=p, dbm=to_dbm(p), stats=dict(stats), impulse_response=ir, impulse_response_rows=rows)
 
     # ------------------------------------------------------------------------------------------
     def set_materials(self, refractive_index):
