@@ -188,12 +188,17 @@ RFRT_API int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *h_
  *   d_rec_ray [cap] uint32, d_rec_rx [cap] int32, d_rec_nverts [cap] int32, d_rec_bin [cap] int64,
  *   d_rec_amp [cap] float64, d_rec_dist [cap] float64,
  *   d_rec_paths [cap*(max_bounces+1)*3] float32 (NaN padded like tracer.py:67-71) or NULL
+ * Direct mode (d_ir != NULL: [n_receivers*n_bins] float64, accumulated into): every received pair is binned right
+ * away — ir[k][bin] += amplitude if 0 <= bin < n_bins (tracer.py:116-117, fp64 atomics, order-free) — and no record is
+ * stored (the d_rec_* arrays may be NULL; RFRT_CTR_RECORDS still counts): the dense coverage maps' path, which needs
+ * neither the paths nor a second pass over a record list.
  * ------------------------------------------------------------------------------------------- */
 RFRT_API int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const float *h_tx_pos, int32_t max_bounces,
                        const uint32_t *d_candidates, int64_t cand_capacity, uint64_t *d_counters,
                        double amp0, double light_speed_mps, double sample_rate_hz, uint32_t *d_rec_ray,
                        int32_t *d_rec_rx, int32_t *d_rec_nverts, int64_t *d_rec_bin, double *d_rec_amp,
-                       double *d_rec_dist, float *d_rec_paths, int64_t rec_capacity, void *stream);
+                       double *d_rec_dist, float *d_rec_paths, int64_t rec_capacity, double *d_ir, int64_t n_bins,
+                       void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Impulse-response binning (tracer.py:101,116-117):  ir[rx][bin] += amp  if bin < n_bins.

@@ -49,7 +49,7 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),
     "rfrt_trace_receive": (ctypes.c_int, [c_u64, c_u64, ctypes.POINTER(c_f), c_i32, c_void_p, c_i64, c_void_p, c_d,
                                           c_d, c_d, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                          c_void_p, c_i64, c_void_p]),
+                                          c_void_p, c_i64, c_void_p, c_i64, c_void_p]),
     "rfrt_bin_ir": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_i32, c_void_p,
                                    c_void_p]),
     "rfrt_mesh_reserve_rays": (ctypes.c_int, [c_u64, c_i64]),

@@ -851,6 +851,8 @@ struct ReceiveParams {
     double *rec_dist;
     float *rec_paths;
     int64_t rec_capacity;
+    double *ir;      // direct mode: ir[rx * n_bins + bin] += amplitude instead of storing the record (or NULL)
+    int64_t n_bins;
     int32_t stack_depth;
 };
 
@@ -870,6 +872,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RECV_MIN_CTAS) k_trace_receive(
     int64_t n_cand = (int64_t)P.counters[RFRT_CTR_CANDIDATES];
     if (n_cand > P.cand_capacity) n_cand = P.cand_capacity;
     const int row = 3 * (P.max_bounces + 1);
+    unsigned int n_direct = 0; // records binned directly by this thread
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_cand; i += (int64_t)gridDim.x * blockDim.x) {
         uint4 cand = P.candidates[i];
         RecordSink sink;
@@ -918,6 +921,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, RECV_MIN_CTAS) k_trace_receive(
         }
         double samples = __dmul_rn(__ddiv_rn(distance, P.light_speed), P.sample_rate);
         long long bin = (long long)samples; // int() truncation, tracer.py:115
+        if (P.ir) { // tracer.py:116-117 right here: no record list, no second pass over it
+            if (bin >= 0 && bin < P.n_bins) atomicAdd(P.ir + (int64_t)cand.y * P.n_bins + bin, amplitude);
+            ++n_direct;
+            continue;
+        }
         unsigned long long slot = atomicAdd(&P.counters[RFRT_CTR_RECORDS], 1ull);
         if ((int64_t)slot < P.rec_capacity) {
             P.rec_ray[slot] = cand.x;
@@ -931,6 +939,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, RECV_MIN_CTAS) k_trace_receive(
                 for (int k = 0; k < row; ++k) dst[k] = k < 3 * nverts ? p[k] : __int_as_float(0x7fc00000);
             }
         }
+    }
+    if (P.ir) {
+        for (int o = 16; o > 0; o >>= 1) n_direct += __shfl_xor_sync(0xffffffffu, n_direct, o);
+        if ((threadIdx.x & 31) == 0 && n_direct) atomicAdd(&P.counters[RFRT_CTR_RECORDS], (unsigned long long)n_direct);
     }
 }
 
@@ -1181,14 +1193,15 @@ extern "C" int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const
                                   uint64_t *d_counters, double amp0, double light_speed_mps, double sample_rate_hz,
                                   uint32_t *d_rec_ray, int32_t *d_rec_rx, int32_t *d_rec_nverts, int64_t *d_rec_bin,
                                   double *d_rec_amp, double *d_rec_dist, float *d_rec_paths, int64_t rec_capacity,
-                                  void *stream_)
+                                  double *d_ir, int64_t n_bins, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     Mesh *m = get_mesh(env_mesh);
     RxSet *r = get_rxset(rxset);
     if (!m || !r) { set_error("rfrt_trace_receive: unknown handle"); return RFRT_ERR_HANDLE; }
-    if (!h_tx_pos || !d_candidates || !d_counters || !d_rec_ray || !d_rec_rx || !d_rec_nverts || !d_rec_bin ||
-        !d_rec_amp || !d_rec_dist || rec_capacity <= 0 || cand_capacity <= 0) {
+    const bool direct = d_ir != nullptr;
+    if (!h_tx_pos || !d_candidates || !d_counters || cand_capacity <= 0 || (direct && n_bins <= 0) ||
+        (!direct && (!d_rec_ray || !d_rec_rx || !d_rec_nverts || !d_rec_bin || !d_rec_amp || !d_rec_dist || rec_capacity <= 0))) {
         set_error("rfrt_trace_receive: null buffer or empty capacity");
         return RFRT_ERR_INVALID;
     }
@@ -1210,6 +1223,7 @@ extern "C" int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const
     P.amp0 = amp0; P.light_speed = light_speed_mps; P.sample_rate = sample_rate_hz;
     P.rec_ray = d_rec_ray; P.rec_rx = d_rec_rx; P.rec_nverts = d_rec_nverts; P.rec_bin = d_rec_bin;
     P.rec_amp = d_rec_amp; P.rec_dist = d_rec_dist; P.rec_paths = d_rec_paths; P.rec_capacity = rec_capacity;
+    P.ir = d_ir; P.n_bins = n_bins;
     // only the environment BVH is walked here (receiver query: lockstep sweep), except with the Moeller-Trumbore functor
     P.stack_depth = stack_depth_for(m, m->tri_test == RFRT_TRI_TEST_MT ? r : nullptr);
     const bool lstack = P.stack_depth > 16;

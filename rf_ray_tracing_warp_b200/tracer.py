@@ -327,29 +327,34 @@ class Tracer:
             rows_per_rank = -(-n_rx // self._world)
             ir = torch.zeros((rows_per_rank * self._world, L), dtype=torch.float64, device=self.device)
             chunk = int(ray_chunk or min(max(end - begin, 1), 1 << 22))
-            job = TraceJob(self, centers, rx_radius, False, self.max_candidates, self.max_records)
+            job = TraceJob(self, centers, rx_radius, False, self.max_candidates, self.max_records, records=False)
             stats = dict(segments=0, env_hits=0, candidates=0, records=0)
+            records_t = None
             try:
                 pos = begin
                 while pos < end:
                     hi = min(end, pos + chunk)
-                    job.enqueue(tx_pos, tx_power, ray_range=(pos, hi))
-                    c = job.counters()  # one host round trip per chunk: overflow is detected BEFORE binning
-                    if c["candidates"] > job.cand_capacity or c["records"] > job.rec_capacity:
+                    job.enqueue(tx_pos, tx_power, ray_range=(pos, hi), receive=False)
+                    c = job.counters()  # one host round trip per chunk: overflow is detected BEFORE anything is binned
+                    if c["candidates"] > job.cand_capacity:
                         if hi - pos <= 1024:
                             job.close()
                             job = TraceJob(self, centers, rx_radius, False, max(2 * job.cand_capacity, c["candidates"] + 1),
-                                           max(2 * job.rec_capacity, c["candidates"] + 1))
+                                           self.max_records, records=False)
                         else:
                             chunk = max(1024, (hi - pos) // 2)
                         continue
-                    job.bin_into(ir)
-                    for k in stats:
+                    # replay + binning in one kernel: received pairs go straight into the resident impulse responses
+                    # (their count stays on the device until the end)
+                    job.enqueue_receive_into(tx_pos, tx_power, ir)
+                    records_t = job.counters_t[_lib.CTR_RECORDS].clone() if records_t is None else records_t + job.counters_t[_lib.CTR_RECORDS]
+                    for k in ("segments", "env_hits", "candidates"):
                         stats[k] += c[k]
                     pos = hi
-                    # grow / shrink the chunk so the work lists run ~60 % full
-                    fill = max(c["candidates"] / job.cand_capacity, c["records"] / job.rec_capacity, 1e-9)
+                    # grow / shrink the chunk so the candidate list runs ~60 % full
+                    fill = max(c["candidates"] / job.cand_capacity, 1e-9)
                     chunk = int(min(max(1024, chunk * 0.6 / fill), 1 << 26))
+                stats["records"] = int(records_t.item()) if records_t is not None else 0
             finally:
                 job.close()
             rows = (0, n_rx)
@@ -497,7 +502,9 @@ class TraceJob:
     synchronisation: [directions ->] environment trace -> literal replay of the candidates -> (optional)
     impulse-response binning."""
 
-    def __init__(self, tracer, rx_positions, rx_radius, want_paths, cand_capacity, rec_capacity):
+    def __init__(self, tracer, rx_positions, rx_radius, want_paths, cand_capacity, rec_capacity, records=True):
+        """records=False: no record lists are allocated — for jobs that only ever bin directly into dense impulse
+        responses (``enqueue_trace`` + ``enqueue_receive_into``)."""
         self.t = tracer
         dev = tracer.device
         B = tracer.max_bounces
@@ -512,7 +519,7 @@ class TraceJob:
             self.cand_capacity, self.rec_capacity = int(cand_capacity), int(rec_capacity)
             self.counters_t = torch.zeros(_lib.CTR_COUNT, dtype=torch.int64, device=dev)
             self.cands = torch.empty(self.cand_capacity * 4, dtype=torch.int32, device=dev)
-            rc = self.rec_capacity
+            rc = self.rec_capacity if records else 0
             self.rec = dict(ray=torch.empty(rc, dtype=torch.int32, device=dev),
                             rx=torch.empty(rc, dtype=torch.int32, device=dev),
                             nverts=torch.empty(rc, dtype=torch.int32, device=dev),
@@ -522,9 +529,10 @@ class TraceJob:
                             paths=torch.empty((rc, B + 1, 3), dtype=torch.float32, device=dev) if want_paths else None)
         self.kernel_launches = 0
 
-    def enqueue(self, tx_pos, tx_power, ray_range=None, dirs=None, ir=None):
+    def enqueue(self, tx_pos, tx_power, ray_range=None, dirs=None, ir=None, receive=True):
         """dirs: optional (n,4) float32 tensor already filled by ``Tracer.ray_directions`` (one wave, no chunking).
-        ir: optional (R,L) float64 tensor, zeroed here and filled with the order-free (atomic) binning."""
+        ir: optional (R,L) float64 tensor, zeroed here and filled with the order-free (atomic) binning.
+        receive=False: only the environment trace (candidates); follow with ``enqueue_receive_into``."""
         t, lib = self.t, self.t._lib
         begin, end = ray_range if ray_range is not None else t.ray_range
         n, B = end - begin, t.max_bounces
@@ -540,13 +548,15 @@ class TraceJob:
                 check(lib.rfrt_trace(t._env, self.rxset, tx, B, begin, end, _lib.FLAG_DIRS_READY | t.trace_flags, _ptr(dirs), n, _ptr(self.counters_t),
                                      _ptr(self.cands), self.cand_capacity, None, None, _stream_ptr()), "rfrt_trace")
                 self.kernel_launches += 1
+            if not receive:
+                return
             amp0 = tx_power / t.tx_num_rays if t.tx_num_rays else 0.0  # tracer.py:103
             r = self.rec
             check(lib.rfrt_trace_receive(t._env, self.rxset, tx, B, _ptr(self.cands), self.cand_capacity,
                                          _ptr(self.counters_t), float(amp0), float(t.light_speed_mps),
                                          float(t.sample_rate_hz), _ptr(r["ray"]), _ptr(r["rx"]), _ptr(r["nverts"]),
                                          _ptr(r["bin"]), _ptr(r["amp"]), _ptr(r["dist"]), _ptr(r["paths"]),
-                                         self.rec_capacity, _stream_ptr()), "rfrt_trace_receive")
+                                         self.rec_capacity, None, 0, _stream_ptr()), "rfrt_trace_receive")
             self.kernel_launches += 1
             if ir is not None:
                 ir.zero_()
@@ -554,6 +564,18 @@ class TraceJob:
                                       self.counters_t.data_ptr() + 8 * _lib.CTR_RECORDS, self.n_rx, ir.shape[1], 0,
                                       _ptr(ir), _stream_ptr()), "rfrt_bin_ir")
                 self.kernel_launches += 1
+
+    def enqueue_receive_into(self, tx_pos, tx_power, ir):
+        """Literal replay of the last trace's candidates with every received pair binned straight into ``ir`` (R, L)
+        float64 (ACCUMULATED, fp64 atomics): no record list.  The caller has checked that the candidates fit."""
+        t = self.t
+        amp0 = tx_power / t.tx_num_rays if t.tx_num_rays else 0.0  # tracer.py:103
+        with torch.cuda.device(t.device):
+            check(t._lib.rfrt_trace_receive(t._env, self.rxset, float3(tx_pos), t.max_bounces, _ptr(self.cands), self.cand_capacity,
+                                            _ptr(self.counters_t), float(amp0), float(t.light_speed_mps), float(t.sample_rate_hz),
+                                            None, None, None, None, None, None, None, 0, _ptr(ir), ir.shape[1], _stream_ptr()),
+                  "rfrt_trace_receive")
+        self.kernel_launches += 1
 
     def collect(self, seg_capacity, ir=None):
         """Record exchange of the last enqueue, all on the current stream and without host synchronisation:
