@@ -393,3 +393,27 @@ def test_dense_power_kernel_matches_np_convolve(torch_cuda):
         want = np.array([post.rx_power(rows[k], window) for k in range(48)])
         assert np.isnan(got[0]) and np.isnan(want[0])
         np.testing.assert_allclose(got[1:], want[1:], rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("scene", ["room", "terrain"])
+def test_records_do_not_depend_on_keeping_the_paths(torch_cuda, room_stl, scene):
+    """compute_cir_multi with and without return_paths: ray, receiver, vertex count, bin, amplitude and distance of the
+    records are bit-identical (the path-less variants of the replay may post-process differently — a streamed
+    evaluation was tried and measured slower — but never to another result), also with a per-triangle material table."""
+    from rf_ray_tracing_warp_b200 import Tracer, load_mesh, synthetic_terrain
+    if scene == "room":
+        mesh, tx, B = load_mesh(room_stl), [10, 0, 5], 6
+        rxs, r = np.array([[3.0, 6.0, 5.0], [-8.0, 8.0, 3.0], [5.0, -3.0, 2.0], [5.2, -3.1, 2.1]]), 0.6
+    else:
+        mesh, tx, B = synthetic_terrain(96, 20.0, 17), [10, 0, 4.5], 6
+        rxs, r = np.array([[0.0, 0.0, 3.0], [4.0, -3.0, 2.5], [-6.0, 5.0, 3.5]]), 0.9
+    n = 1 << 17
+    tr = Tracer(mesh, C, 100e9, 200e-9, B, n)
+    rng = np.random.default_rng(1)
+    for materials in (None, rng.uniform(1.5, 9.0, size=tr.mesh_info()["n_triangles"])):
+        tr.set_materials(materials)
+        with_paths = {k: v.cpu().numpy() for k, v in tr.compute_cir_multi(tx, 1, rxs, r, return_paths=True)["records"].items() if v is not None}
+        without = {k: v.cpu().numpy() for k, v in tr.compute_cir_multi(tx, 1, rxs, r, return_paths=False)["records"].items() if v is not None}
+        assert with_paths["ray"].shape[0] > 300 and (with_paths["nverts"] > 3).sum() > 20
+        for name in ("ray", "rx", "nverts", "bin", "amp", "dist"):
+            assert np.array_equal(with_paths[name].view(np.uint8), without[name].view(np.uint8)), (name, materials is not None)
