@@ -194,6 +194,11 @@ __device__ __forceinline__ void receivers_lane(const TraceParams &P, float3 pos,
                          fminf(pos.z, ez) <= P.rx_hi[2] && fmaxf(pos.z, ez) >= P.rx_lo[2];
     if (!near_rx) return;
     const SlabRay sr = slab_setup_fast(pos, dir);
+    {   // the segment itself against the set's bounds (the box overlap above is loose for a diagonal segment and a thin
+        // set — C4's 16 receivers on a line: a quarter of the trips had a lane in here, almost all to miss the root)
+        float tn;
+        if (!slab_hit(sr, P.rx_lo[0], P.rx_lo[1], P.rx_lo[2], P.rx_hi[0], P.rx_hi[1], P.rx_hi[2], t_limit, tn)) return;
+    }
     int queue[RX_LANE_QUEUE];
     int qn = 0, sp = 0;
     // next internal node from the stack; leaf entries (deferred while the queue was full) move to the queue on the way.
