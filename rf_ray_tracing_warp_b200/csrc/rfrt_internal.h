@@ -121,9 +121,12 @@ void small_scene_neighbours(const float *soup, int n_tris, const int32_t *slot_t
                             int32_t *tri_slot);
 inline size_t small_image_floats(int n_pairs, int n_tris) { return 30 * (size_t)n_pairs + 17 * (size_t)n_tris; }
 // self-re-hit shortcut (rfrt_trace.cuh): applies to hits of the ray's own triangle within SMALL_TAU_REL * extent
-// (path length); neighbours are collected within SMALL_REACH_REL * extent
-constexpr double SMALL_TAU_REL = 1.0e-4;
-constexpr double SMALL_REACH_REL = 1.0e-3;
+// (path length); neighbours are collected within SMALL_REACH_REL * extent.  A triangle that beats or ties the re-hit is
+// hit within tau of the origin, and the origin lies on the ray's own triangle to fp32 rounding (~1e-6 * extent), so
+// reach only has to exceed tau: 2.5 tau.  (Round 1: 1e-4 and 1e-3 — the boundary strip of width 2 reach + tau + tolerance
+// then made one lane of every third re-hit trip walk its neighbour pairs alone.)
+constexpr double SMALL_TAU_REL = 2.5e-5;
+constexpr double SMALL_REACH_REL = 6.25e-5;
 
 void unit_face_records(const double *unit_v, const int32_t *faces, int n_faces, float *recs);
 

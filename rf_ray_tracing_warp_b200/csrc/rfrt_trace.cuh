@@ -477,7 +477,9 @@ __device__ __forceinline__ bool small_self_rehit(const SmallScene &S, int f, flo
                               fmaf(e1.x, pos.x, fmaf(e1.y, pos.y, fmaf(e1.z, pos.z, e1.w))),
                               fmaf(e2.x, pos.x, fmaf(e2.y, pos.y, fmaf(e2.z, pos.z, e2.w))));
     const uint4 nb = S.nbr[f];
-    const bool inner = clear >= S.erode + rho; // false for NaN
+    // (inside f eroded by `erode`, with a slack of tau + dl for the fp32 clearance — its own rounding error is ~1e-6 *
+    // extent, a twentieth of dl; the full rho of the distance filters below is not needed here)
+    const bool inner = clear >= S.erode + fmaf(S.tau, 1.01f, dl); // false for NaN
     unsigned m = (hf.t == 0.0f) ? (inner ? nb.z : (nb.z | nb.w)) : (inner ? nb.x : (nb.x | nb.y));
     while (m) {
         const int k = 31 - __clz((int)m);

@@ -144,7 +144,7 @@ def test_self_rehit_neighbour_masks(repo_root):
         last = np.where(alive, hit_tri[:, b], last)
         alive = alive & (hit_tri[:, b] >= 0)
     prev = np.concatenate(prev)
-    tau = 1.0e-4 * extent
+    tau = 2.5e-5 * extent
     checked = 0
     for i in np.nonzero(prev >= 0)[0][:60_000]:
         f = int(prev[i])
