@@ -199,7 +199,7 @@ extern "C" int rfrt_mesh_create(const float *d_vertices_xyz, int64_t n_vertices,
             set_error("rfrt_mesh_create: face index out of range");
             return RFRT_ERR_INVALID;
         }
-        int rc = build_lbvh(lo, hi, n_triangles, stream, &m->bvh);
+        int rc = build_lbvh(lo, hi, n_triangles, stream, &m->bvh, BVH_PAD_MESH);
         if (rc) return rc;
         RFRT_CUDA(cudaMalloc(&m->tris, sizeof(BvhTri) * n_triangles));
         RFRT_CUDA(cudaMalloc(&m->normals, sizeof(float4) * n_triangles));
@@ -345,7 +345,7 @@ extern "C" int rfrt_rxset_create(const double *d_centers_xyz, int64_t n_receiver
     k_rx_vertices<<<(unsigned)((n_receivers + T - 1) / T), T, 0, stream>>>(r->centers, n_receivers, radius, d_unit,
                                                                            n_unit_vertices, r->verts, lo, hi);
     RFRT_CUDA(cudaGetLastError());
-    int rc = build_lbvh(lo, hi, n_receivers, stream, &r->bvh);
+    int rc = build_lbvh(lo, hi, n_receivers, stream, &r->bvh, BVH_PAD_RX);
     if (rc) return rc;
     {
         // BVH over the unit icosphere's faces, used (after mapping the ray into unit space) to prune the exact
@@ -369,7 +369,7 @@ extern "C" int rfrt_rxset_create(const double *d_centers_xyz, int64_t n_receiver
         tmp.async_ptrs.push_back({dhi, stream});
         RFRT_CUDA(cudaMemcpyAsync(dlo, ulo.data(), sizeof(float4) * n_faces, cudaMemcpyHostToDevice, stream));
         RFRT_CUDA(cudaMemcpyAsync(dhi, uhi.data(), sizeof(float4) * n_faces, cudaMemcpyHostToDevice, stream));
-        rc = build_lbvh(dlo, dhi, n_faces, stream, &r->unit_bvh); // synchronises the stream
+        rc = build_lbvh(dlo, dhi, n_faces, stream, &r->unit_bvh, BVH_PAD_RX); // synchronises the stream
         if (rc) return rc;
     }
     {

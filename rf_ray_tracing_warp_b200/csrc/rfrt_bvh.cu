@@ -363,7 +363,7 @@ void keep_pool_memory()
     done = true;
 }
 
-int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t stream, Bvh *out)
+int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t stream, Bvh *out, float min_pad)
 {
     keep_pool_memory();
     *out = Bvh();
@@ -407,7 +407,12 @@ int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t s
     RFRT_CUDA(cudaStreamSynchronize(stream));
     float m = 0.0f;
     for (int k = 0; k < 6; ++k) m = fmaxf(m, fabsf(out->bounds[k]));
-    out->pad = fmaxf(1.0e-3f, 1.0e-5f * m);
+    // padding of the boxes: what the slab test and the exact test can disagree by because of the MESH's coordinates
+    // (ulps of max |coordinate| = m: 1e-5 m is ~80 of them); the part that grows with the ray's origin is the slab
+    // test's own per-ray offsets (rfrt_trace.cuh: SlabRay).  RFRT_BVH_PAD overrides the floor of environment meshes for
+    // A/B runs (round 1: 1e-3).
+    if (min_pad == BVH_PAD_MESH && getenv("RFRT_BVH_PAD")) min_pad = (float)atof(getenv("RFRT_BVH_PAD"));
+    out->pad = fmaxf(min_pad, 1.0e-5f * m);
 
     // values: the primitive index; ping-pongs between out->prim_order and vals_b and ends in out->prim_order
     uint32_t *order = reinterpret_cast<uint32_t *>(out->prim_order);

@@ -109,7 +109,11 @@ struct Temporaries {
 
 // Builds a BVH over n axis-aligned boxes (device arrays lo/hi as float4 per primitive, w ignored).
 // Allocates bvh.nodes / bvh.prim_order.  Synchronises the stream.
-int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t stream, Bvh *out);
+// min_pad: floor of the boxes' padding (environment meshes: BVH_PAD_MESH, a formality — the padding is 1e-5 * max
+// |coordinate|; receiver sets and their unit shape: BVH_PAD_RX = Warp's 1e-3)
+constexpr float BVH_PAD_MESH = 1.0e-7f;
+constexpr float BVH_PAD_RX = 1.0e-3f;
+int build_lbvh(const float4 *d_lo, const float4 *d_hi, int64_t n, cudaStream_t stream, Bvh *out, float min_pad);
 void free_bvh(Bvh *b);
 void keep_pool_memory();
 int64_t sort_hist_blocks(int64_t n);

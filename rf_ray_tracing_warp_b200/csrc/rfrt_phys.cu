@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(PHYS_THREADS) k_trace_phys(const PhysParams P)
                                         __dmul_rn((double)dir.z, (double)dir.z));
             const double t_lim = hit ? (double)h.t : 1.0e6;
             const float t_limit = hit ? h.t : 1.0e6f;
-            const SlabRay sr = slab_setup_fast(pos, dir);
+            const RxSlabRay sr = rx_slab_setup(pos, dir);
             int sp = 0;
             int node = 0;
             while (node >= 0) {
@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(PHYS_THREADS) k_trace_phys(const PhysParams P)
                 const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
                 const int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
                 float tn0, tn1;
-                bool h0 = slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_limit, tn0);
-                bool h1 = slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_limit, tn1);
+                bool h0 = rx_slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_limit, tn0);
+                bool h1 = rx_slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_limit, tn1);
                 const int c0 = q3.x, c1 = q3.y;
                 if (c1 == c0) h1 = false;
                 if (h0) {

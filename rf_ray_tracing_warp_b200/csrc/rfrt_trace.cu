@@ -29,7 +29,7 @@ constexpr int RX_CAND_BUF = 256; // receivers staged per warp between two append
 constexpr int RX_COOP_INTS = RX_QUEUE_CAP + RX_CAND_BUF + 4; // per-warp shared memory of the cooperative enumeration
 constexpr int MAX_RECV_BOUNCES = 32;
 #ifndef RECV_MIN_CTAS
-#define RECV_MIN_CTAS 8
+#define RECV_MIN_CTAS 7
 #endif
 #ifndef WALK_MIN_CTAS
 #define WALK_MIN_CTAS 9
@@ -193,11 +193,11 @@ __device__ __forceinline__ void receivers_lane(const TraceParams &P, float3 pos,
                          fminf(pos.y, ey) <= P.rx_hi[1] && fmaxf(pos.y, ey) >= P.rx_lo[1] &&
                          fminf(pos.z, ez) <= P.rx_hi[2] && fmaxf(pos.z, ez) >= P.rx_lo[2];
     if (!near_rx) return;
-    const SlabRay sr = slab_setup_fast(pos, dir);
+    const RxSlabRay sr = rx_slab_setup(pos, dir);
     {   // the segment itself against the set's bounds (the box overlap above is loose for a diagonal segment and a thin
         // set — C4's 16 receivers on a line: a quarter of the trips had a lane in here, almost all to miss the root)
         float tn;
-        if (!slab_hit(sr, P.rx_lo[0], P.rx_lo[1], P.rx_lo[2], P.rx_hi[0], P.rx_hi[1], P.rx_hi[2], t_limit, tn)) return;
+        if (!rx_slab_hit(sr, P.rx_lo[0], P.rx_lo[1], P.rx_lo[2], P.rx_hi[0], P.rx_hi[1], P.rx_hi[2], t_limit, tn)) return;
     }
     int queue[RX_LANE_QUEUE];
     int qn = 0, sp = 0;
@@ -218,8 +218,8 @@ __device__ __forceinline__ void receivers_lane(const TraceParams &P, float3 pos,
             float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
             int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
             float tn0, tn1;
-            bool h0 = slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_limit, tn0);
-            bool h1 = slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_limit, tn1);
+            bool h0 = rx_slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_limit, tn0);
+            bool h1 = rx_slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_limit, tn1);
             const int c0 = q3.x, c1 = q3.y;
             if (c1 == c0) h1 = false;
             if (h0) { if (c0 < 0 && qn < RX_LANE_QUEUE) queue[qn++] = ~c0; else { stack[sp * stride] = c0; ++sp; } }
