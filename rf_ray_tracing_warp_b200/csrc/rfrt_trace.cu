@@ -29,7 +29,7 @@ constexpr int RX_CAND_BUF = 256; // receivers staged per warp between two append
 constexpr int RX_COOP_INTS = RX_QUEUE_CAP + RX_CAND_BUF + 4; // per-warp shared memory of the cooperative enumeration
 constexpr int MAX_RECV_BOUNCES = 32;
 #ifndef RECV_MIN_CTAS
-#define RECV_MIN_CTAS 7
+#define RECV_MIN_CTAS 8
 #endif
 #ifndef WALK_MIN_CTAS
 #define WALK_MIN_CTAS 9
@@ -349,7 +349,9 @@ constexpr int WALK_UNROLL = WALK_UNROLL_N;
 // COOP:   dense receiver sets — the warp enumerates its lanes' segments together (rx_enumerate_coop) at the converged
 //         point of phase A; otherwise every lane handles its own receivers right where its segment is finished
 // MT:     the Moeller-Trumbore functor instead of the reference's watertight test (rfrt_mesh_set_triangle_test) // node steps per vote of the node loop
-template <bool DUMP, bool LSTACK, bool COOP, bool MT>
+// NEAR:   the transmitter stands within 8 x the mesh's largest coordinate of the coordinate origin, so every origin of
+//         a segment does and the plain slab test is enough (rfrt_trace.cuh; +2 % on the 20 M-triangle terrain)
+template <bool DUMP, bool LSTACK, bool COOP, bool MT, bool NEAR = false>
 __global__ void __launch_bounds__(TRACE_THREADS, COOP ? WALK_MIN_CTAS - 1 : WALK_MIN_CTAS) k_trace_walk(const TraceParams P)
 {
     using Ray = typename std::conditional<MT, MtRay, WoopRay>::type;
@@ -376,7 +378,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, COOP ? WALK_MIN_CTAS - 1 : WALK
     int64_t ray = 0;
     Hit h;
     h.t = 1.0e6f; h.face = -1; h.slot = -1;
-    SlabRay sr = slab_setup(pos, dir);
+    using WSlab = typename std::conditional<NEAR, RxSlabRay, SlabRay>::type;
+    WSlab sr = slab_make<WSlab>(pos, dir);
     unsigned int n_seg = 0, n_hit = 0, n_nodes = 0, n_tests = 0;
     unsigned long long csum = 0ull;
     const int FETCH_BLOCK = P.fetch_block;
@@ -443,9 +446,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, COOP ? WALK_MIN_CTAS - 1 : WALK
         if (!__any_sync(FULL, has_ray)) break;
         // ---- start the next segment: scene-box test first (a miss is a finished segment with no hit) ----
         if (has_ray && !walking) {
-            // (approximate reciprocals: the slab test only prunes, and a hit point inside a box padded by >= 1e-3 m leaves
-            // a chord of >= 2e-3 m through it, four orders of magnitude above the 2.4e-7 relative error per axis)
-            sr = slab_setup_fast(pos, dir);
+            // (approximate reciprocals: the slab test only prunes, and a hit point inside a box padded by 1e-5 of the
+            // mesh's largest coordinate leaves a chord through it some thirty times the 2.4e-7 relative error per axis)
+            if constexpr (NEAR) sr = rx_slab_setup(pos, dir);
+            else sr = slab_setup_fast(pos, dir);
             float tn;
             const bool entered = P.n_tris > 0 &&
                                  slab_hit(sr, P.env_lo[0], P.env_lo[1], P.env_lo[2], P.env_hi[0], P.env_hi[1], P.env_hi[2], 1.0e6f, tn);
@@ -693,7 +697,8 @@ struct LiteralEnv {
 
 // kernel.py:38-98 for one ray and one receiver.  Sink receives the vertex writes and RX-hit events.
 // s_recs: unit-space face records in shared memory (lockstep receiver query) or NULL (unit-BVH walk)
-template <bool MT, class Sink>
+// NEAR: every origin of the walk lies within 8 x the mesh's largest coordinate (rfrt_trace.cuh: the plain slab test)
+template <bool MT, bool NEAR = false, class Sink>
 __device__ __forceinline__ void literal_trace(const LiteralEnv &E, const RxView *rx, int n_faces, float3 tx,
                                               int max_bounces, uint32_t tid, int *stack, float *stack_t, int stride,
                                               Sink &sink, const float4 *s_recs = nullptr)
@@ -718,7 +723,8 @@ __device__ __forceinline__ void literal_trace(const LiteralEnv &E, const RxView 
         }
         using Ray = typename std::conditional<MT, MtRay, WoopRay>::type;
         const Ray wr = tri_ray_setup<Ray>(pos, dir);
-        SlabRay sr = slab_setup(pos, dir);
+        using Slab = typename std::conditional<NEAR, RxSlabRay, SlabRay>::type;
+        const Slab sr = slab_make<Slab>(pos, dir);
         float t_rx = 0.0f;
         bool maybe_hit_rx = false; // :71
         if (rx) {
@@ -861,8 +867,8 @@ struct ReceiveParams {
     int32_t stack_depth;
 };
 
-template <bool LSTACK, bool MT>
-__global__ void __launch_bounds__(TRACE_THREADS, RECV_MIN_CTAS) k_trace_receive(const ReceiveParams P)
+template <bool LSTACK, bool MT, bool NEAR>
+__global__ void __launch_bounds__(TRACE_THREADS, NEAR ? RECV_MIN_CTAS : RECV_MIN_CTAS - 1) k_trace_receive(const ReceiveParams P)
 {
     extern __shared__ __align__(16) int s_stack_raw[];
     int l_stack[LSTACK ? 64 : 1];
@@ -891,7 +897,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RECV_MIN_CTAS) k_trace_receive(
         rx.unit_nodes = P.unit_nodes; rx.unit_order = P.unit_order;
         rx.cx = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y); rx.cy = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y + 1);
         rx.cz = (float)__ldg(P.rx_centers + 3 * (int64_t)cand.y + 2); rx.inv_r = P.inv_r;
-        literal_trace<MT>(P.env, &rx, P.n_faces, P.tx, P.max_bounces, cand.x, stack, stack_t, STRIDE, sink, MT ? nullptr : s_recs);
+        literal_trace<MT, NEAR>(P.env, &rx, P.n_faces, P.tx, P.max_bounces, cand.x, stack, stack_t, STRIDE, sink, MT ? nullptr : s_recs);
         // a candidate raised at a later bounce than the replay's first receiver hit is a duplicate
         if (sink.last_rx_bounce < 0 || sink.first_rx_bounce != (int)cand.z) continue;
         int nverts = sink.last_rx_bounce + 2;
@@ -971,6 +977,17 @@ k_query(LiteralEnv E, const float *__restrict__ origins, const float *__restrict
         t_out[i] = h.t;
         face_out[i] = h.face;
     }
+}
+
+// Every origin of a segment (the transmitter, then hit points) within 8 x the mesh's largest coordinate m of the
+// coordinate origin: the origin-dependent slack of the slab test, 2^-21 * 8 m, then fits inside the boxes' padding of
+// 1e-5 m and the walks use the plain test.  RFRT_SLAB_FAR=1 forces the general test (A/B runs, tests).
+bool tx_is_near(const Mesh *m, const float *h_tx_pos)
+{
+    float m_coord = 0.0f, tx_coord = 0.0f;
+    for (int k = 0; k < 6; ++k) m_coord = fmaxf(m_coord, fabsf(m->bvh.bounds[k]));
+    for (int k = 0; k < 3; ++k) tx_coord = fmaxf(tx_coord, fabsf(h_tx_pos[k]));
+    return tx_coord <= 8.0f * m_coord && m->bvh.pad >= 1.0e-5f * m_coord && !getenv("RFRT_SLAB_FAR");
 }
 
 int stack_depth_for(const Mesh *m, const RxSet *r)
@@ -1152,6 +1169,13 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
         P.walk_refill = getenv("RFRT_WALK_REFILL") ? atoi(getenv("RFRT_WALK_REFILL")) : 24;
         P.walk_node_min = getenv("RFRT_WALK_NODE_MIN") ? atoi(getenv("RFRT_WALK_NODE_MIN")) : 8;
         kern = walk_kerns[mt ? 1 : 0][P.rx_coop ? 1 : 0][lstack ? 1 : 0][dump ? 1 : 0];
+        static const kern_t near_kerns[2][2][2] = {
+            {{k_trace_walk<false, false, false, false, true>, k_trace_walk<true, false, false, false, true>},
+             {k_trace_walk<false, true, false, false, true>, k_trace_walk<true, true, false, false, true>}},
+            {{k_trace_walk<false, false, true, false, true>, k_trace_walk<true, false, true, false, true>},
+             {k_trace_walk<false, true, true, false, true>, k_trace_walk<true, true, true, false, true>}},
+        };
+        if (!mt && tx_is_near(m, h_tx_pos)) kern = near_kerns[P.rx_coop ? 1 : 0][lstack ? 1 : 0][dump ? 1 : 0];
     }
     int grid = 0;
     int rc = grid_for((const void *)kern, smem, &grid, small);
@@ -1237,9 +1261,15 @@ extern "C" int rfrt_trace_receive(rfrt_handle env_mesh, rfrt_handle rxset, const
     const size_t smem = stack_bytes(P.stack_depth) + sizeof(float4) * 4 * (size_t)r->n_faces;
     int grid = 0;
     typedef void (*recv_kern_t)(const ReceiveParams);
-    static const recv_kern_t recv_kerns[2][2] = {{k_trace_receive<false, false>, k_trace_receive<true, false>},
-                                                 {k_trace_receive<false, true>, k_trace_receive<true, true>}};
-    const recv_kern_t recv_kern = recv_kerns[m->tri_test == RFRT_TRI_TEST_MT ? 1 : 0][lstack ? 1 : 0];
+    static const recv_kern_t recv_kerns[2][2][2] = {
+        {{k_trace_receive<false, false, false>, k_trace_receive<false, false, true>},
+         {k_trace_receive<true, false, false>, k_trace_receive<true, false, true>}},
+        {{k_trace_receive<false, true, false>, k_trace_receive<false, true, true>},
+         {k_trace_receive<true, true, false>, k_trace_receive<true, true, true>}}};
+    // the replay's origins are the transmitter and hit points: with the transmitter within 8 x the mesh's largest
+    // coordinate the boxes' padding covers the origin-dependent error and the plain slab test is enough
+    const bool near_tx = tx_is_near(m, h_tx_pos);
+    const recv_kern_t recv_kern = recv_kerns[m->tri_test == RFRT_TRI_TEST_MT ? 1 : 0][lstack ? 1 : 0][near_tx ? 1 : 0];
     int rc = grid_for((const void *)recv_kern, smem, &grid);
     if (rc) return rc;
     rc = upload_faces(r, stream);

@@ -104,6 +104,22 @@ __device__ __forceinline__ bool rx_slab_hit(const RxSlabRay &s, float lx, float 
     t_near = tn;
     return tn <= tf * 1.0000004f + 1.0e-30f;
 }
+// The plain test is also enough for an ENVIRONMENT walk whose origins all lie within 8 x the mesh's largest coordinate
+// m of the coordinate origin: delta <= 2^-21 * 8 m = 3.8e-6 m then sits inside the boxes' padding of 1e-5 m with more
+// than half of it to spare.  The replay (k_trace_receive) knows that per launch — its origins are the transmitter and
+// hit points — and picks this cheaper ray (three registers fewer through its walk) unless the transmitter stands far
+// outside the scene.
+__device__ __forceinline__ bool slab_hit(const RxSlabRay &s, float lx, float ly, float lz, float hx, float hy, float hz,
+                                         float t_max, float &t_near)
+{
+    return rx_slab_hit(s, lx, ly, lz, hx, hy, hz, t_max, t_near);
+}
+template <class SLAB>
+__device__ __forceinline__ SLAB slab_make(float3 p, float3 d)
+{
+    if constexpr (std::is_same<SLAB, RxSlabRay>::value) return rx_slab_setup(p, d);
+    else return slab_setup(p, d);
+}
 
 __device__ __forceinline__ void tri_vertices(const BvhTri *__restrict__ tris, int slot, float3 &a, float3 &b,
                                              float3 &c, int &index)
@@ -138,7 +154,8 @@ __device__ __forceinline__ int stack_pop(int *stack, float *stack_t, int stride,
 
 // visit one internal node: slab-test both child boxes (4 x 128-bit loads), go to the nearer hit child and
 // defer the other (with its entry distance) on the stack.  Returns the next state code.
-__device__ __forceinline__ int node_step(const BvhNode *__restrict__ nodes, int node, const SlabRay &sr, float best_t,
+template <class SLAB>
+__device__ __forceinline__ int node_step(const BvhNode *__restrict__ nodes, int node, const SLAB &sr, float best_t,
                                          int *stack, float *stack_t, int stride, int &sp)
 {
     const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
@@ -189,9 +206,9 @@ __device__ __forceinline__ int leaf_step(const BvhTri *__restrict__ tris, int no
 // every trip (several `continue` back-edges let sub-groups of lanes run the loop separately: measured 6/32
 // lanes active; testing leaves inside the node loop: 3/32 active in the triangle test).
 // COUNT: also count the internal nodes fetched and the triangles tested (RFRT_CTR_NODE_VISITS / RFRT_CTR_TRI_TESTS)
-template <bool COUNT = false, class RAY = WoopRay>
+template <bool COUNT = false, class RAY = WoopRay, class SLAB = SlabRay>
 __device__ __forceinline__ void closest_hit(const BvhNode *__restrict__ nodes, const BvhTri *__restrict__ tris,
-                                            int64_t n_prims, const RAY &wr, const SlabRay &sr, int *stack,
+                                            int64_t n_prims, const RAY &wr, const SLAB &sr, int *stack,
                                             float *stack_t, int stride, Hit &h, int skip = -1,
                                             unsigned *n_nodes = nullptr, unsigned *n_tests = nullptr)
 {

@@ -244,3 +244,41 @@ def test_receiver_enumeration_paths_agree(torch_cuda, room_stl, monkeypatch):
         assert np.array_equal(a["ray"][sel].astype(np.uint32), np.nonzero(o["mask"])[0].astype(np.uint32))
         for row, nv, op in zip(a["paths"][sel], a["nverts"][sel], o_paths):
             assert np.array_equal(row[:nv].view(np.uint32), op.view(np.uint32))
+
+
+def test_plain_and_general_slab_tests_agree(torch_cuda, room_stl, monkeypatch):
+    """The walks use the plain slab test when the transmitter stands within 8 x the mesh's largest coordinate and the
+    general one (per-axis origin-dependent offsets) otherwise.  Same hits either way and both equal to brute force:
+    a fine terrain (triangles of 0.4 m in boxes padded by 2e-4), near transmitter with the general test forced, a
+    transmitter ten times the scene's size away (general test picked by the library), and the replay's records."""
+    from oracle import cpu
+    from rf_ray_tracing_warp_b200 import Tracer, load_mesh, synthetic_terrain
+    mesh = synthetic_terrain(96, 20.0, 5)
+    soup = mesh.vertices[mesh.faces].astype(np.float32)
+    n, B = 1 << 16, 5
+    for tx, n in (([10.0, 0.0, 4.5], 1 << 16), ([200.0, -30.0, 60.0], 1 << 18)):   # 8 x 20 m = 160 m is the switch
+        outs = []
+        for far in (None, "1"):
+            if far:
+                monkeypatch.setenv("RFRT_SLAB_FAR", far)
+            tr = Tracer(mesh, C, 100e9, 200e-9, B, n)
+            out = tr.trace_segments(tx, dump=True)
+            outs.append((out["segments"], out["hit_tri"].cpu().numpy(), out["hit_t"].cpu().numpy().view(np.uint32)))
+            if far:
+                monkeypatch.delenv("RFRT_SLAB_FAR")
+        seg, tri, t = cpu.trace_env(soup, tx, B, 0, n)
+        assert (tri >= 0).sum() > 50
+        for o in outs:
+            assert o[0] == seg and np.array_equal(o[1], tri) and np.array_equal(o[2], t.view(np.uint32)), tx
+    recs, n = [], 1 << 18
+    for far in (None, "1"):
+        if far:
+            monkeypatch.setenv("RFRT_SLAB_FAR", far)
+        tr = Tracer(load_mesh(room_stl), C, 100e9, 200e-9, 4, n, force_bvh=True)
+        out = tr.compute_cir_multi([10, 0, 5], 1, np.array([[-10.0, 0, 5], [0.0, 3.0, 4.0]]), 1.0, return_paths=True)
+        recs.append({k: v.cpu().numpy() for k, v in out["records"].items()})
+        if far:
+            monkeypatch.delenv("RFRT_SLAB_FAR")
+    assert recs[0]["ray"].shape[0] > 50
+    for name in recs[0]:
+        assert np.array_equal(recs[0][name].view(np.uint8), recs[1][name].view(np.uint8)), name
