@@ -152,15 +152,35 @@ __device__ __forceinline__ int stack_pop(int *stack, float *stack_t, int stride,
     return next;
 }
 
+// One 64-byte node = two 256-bit loads (LDG.E.ENL2.256 on sm_100a; nodes come from cudaMalloc and are 64-byte aligned):
+// half the load instructions of four 128-bit loads for lanes that all sit on different nodes (+2 % on the 20 M-triangle
+// terrain).  Only the environment walks use it: in the receiver walk of k_trace_small the eight-register alignment of
+// the wide load costs the kernel its register allocation (C4 kernel 10.36 -> 10.97 ms).
+__device__ __forceinline__ void load_node(const BvhNode *__restrict__ nd, float4 &q0, float4 &q1, float4 &q2, int4 &q3)
+{
+#ifdef RFRT_NODE_LDG128
+    const float4 *np = reinterpret_cast<const float4 *>(nd);
+    q0 = __ldg(np); q1 = __ldg(np + 1); q2 = __ldg(np + 2);
+    q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
+#else
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w), "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w)
+        : "l"(nd));
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w), "=r"(q3.x), "=r"(q3.y), "=r"(q3.z), "=r"(q3.w)
+        : "l"(reinterpret_cast<const char *>(nd) + 32));
+#endif
+}
+
 // visit one internal node: slab-test both child boxes (4 x 128-bit loads), go to the nearer hit child and
 // defer the other (with its entry distance) on the stack.  Returns the next state code.
 template <class SLAB>
 __device__ __forceinline__ int node_step(const BvhNode *__restrict__ nodes, int node, const SLAB &sr, float best_t,
                                          int *stack, float *stack_t, int stride, int &sp)
 {
-    const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
-    float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-    int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
+    float4 q0, q1, q2;
+    int4 q3;
+    load_node(nodes + node, q0, q1, q2, q3);
     float tn0, tn1;
     bool h0 = slab_hit(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, best_t, tn0);
     bool h1 = slab_hit(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, best_t, tn1);
