@@ -102,6 +102,7 @@ void release_mesh(Mesh *m)
     if (m->ray_keys[0]) cudaFree(m->ray_keys[0]);
     if (m->ray_keys[1]) cudaFree(m->ray_keys[1]);
     if (m->ray_hist) cudaFree(m->ray_hist);
+    if (m->ray_cells) cudaFree(m->ray_cells);
     *m = Mesh();
 }
 

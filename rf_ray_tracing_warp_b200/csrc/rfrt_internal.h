@@ -58,6 +58,7 @@ struct Mesh {
     // BVH scenes: workspace of the direction-coherent ray order (grown on demand by rfrt_trace, freed with the mesh)
     uint64_t *ray_keys[2] = {nullptr, nullptr};
     uint32_t *ray_hist = nullptr;
+    uint32_t *ray_cells = nullptr; // counters of the 2^24 direction cells + their block sums (counting sort of a wave)
     int64_t ray_cap = 0;
 };
 

@@ -14,6 +14,7 @@
 //   k_query         test probe for closest_hit
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "rfrt_trace.cuh"
@@ -62,6 +63,7 @@ struct TraceParams {
     int64_t chunk_n;
     const float4 *dirs;
     const uint64_t *order; // BVH scenes: (direction cell << 32 | ray index in chunk), sorted -> coherent warps; or NULL
+    const uint32_t *order32; // ... or as 32-bit ray numbers (counting sort by direction cell)
     // outputs
     unsigned long long *counters;
     uint4 *candidates;
@@ -104,8 +106,11 @@ __device__ __forceinline__ uint32_t spread12(uint32_t v)
 // their chord through the box, longest first, brought nothing more).  What remains of the fixed ~1.1 ms per wave is
 // 0.5 ms of drain after the last fetch and 0.6 ms before it (measured with %globaltimer probes); waves of 2^26 rays
 // amortise it (4.7e9 segments/s on 20 M triangles against 4.05e9 at 2^24 and 2.6e9 at 2^22).
+// CELLS: also count the ray into its direction cell (the 24-bit code) and keep its arrival rank there instead of its
+// id: the input of the counting sort below.
+template <bool CELLS>
 __global__ void k_dir_keys(const float4 *__restrict__ dirs, int64_t n, uint64_t *__restrict__ keys, float3 tx, float3 env_lo,
-                           float3 env_hi)
+                           float3 env_hi, uint32_t *__restrict__ cells, int cell_shift)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -122,7 +127,103 @@ __global__ void k_dir_keys(const float4 *__restrict__ dirs, int64_t n, uint64_t 
     const uint32_t qu = (uint32_t)fminf(fmaxf((u * 0.5f + 0.5f) * 4096.0f, 0.0f), 4095.0f);
     const uint32_t qv = (uint32_t)fminf(fmaxf((v * 0.5f + 0.5f) * 4096.0f, 0.0f), 4095.0f);
     const uint32_t code = ((spread12(qu) | (spread12(qv) << 1)) >> 1) | (enters ? 0u : 0x800000u);
-    keys[i] = ((uint64_t)code << 32) | (uint64_t)(uint32_t)i;
+    if (CELLS) keys[i] = ((uint64_t)code << 32) | (uint64_t)atomicAdd(cells + (code >> cell_shift), 1u);
+    else keys[i] = ((uint64_t)code << 32) | (uint64_t)(uint32_t)i;
+}
+
+// ---- counting sort of a wave's rays by direction cell ---------------------------------------------------------------
+// The key is a 24-bit cell number and the rays spread over the cells about evenly (one per cell at 2^24 rays), so the
+// order needs no general sort: count the rays of every cell with one atomic each (k_dir_keys<true>, which keeps the
+// arrival rank), scan the 2^24 counters (three small kernels over 67 MB), place every ray at its cell's offset + rank.
+// Measured per 16.8 M rays: keys + atomics 169 us, scan 44 us, placement ~250 us against 86 + 3 x 265 us of the radix
+// sort (wave of the 20 M-triangle terrain 6.0 -> 5.7 ms).
+// The order inside a cell is the arrival order of the atomics — the hits of a ray do not depend on the order the rays
+// are traced in.
+constexpr int RAY_CELLS = 1 << 24;   // most cells a wave is ordered by (the whole 24-bit code)
+constexpr int CELL_BLOCK = 4096;     // cells per CTA of the scan: 256 threads x 16 cells; <= 4096 block sums, scanned by one CTA
+
+__device__ __forceinline__ uint32_t cell_thread_load(const uint32_t *cells, uint32_t (&v)[16])
+{
+    const uint4 *p = reinterpret_cast<const uint4 *>(cells + (size_t)blockIdx.x * CELL_BLOCK + threadIdx.x * 16);
+    uint32_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint4 q = p[j];
+        v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+        sum += q.x + q.y + q.z + q.w;
+    }
+    return sum;
+}
+
+// exclusive prefix of one value per thread over the CTA (blockDim.x <= 1024); total to every thread
+__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t x, uint32_t &total)
+{
+    __shared__ uint32_t warp_sums[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint32_t incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t prefix = 0, tot = 0;
+    for (int w = 0; w < nwarps; ++w) {
+        const uint32_t ws = warp_sums[w];
+        if (w < warp) prefix += ws;
+        tot += ws;
+    }
+    __syncthreads();
+    total = tot;
+    return prefix + incl - x;
+}
+
+__global__ void __launch_bounds__(256) k_cells_reduce(const uint32_t *__restrict__ cells, uint32_t *__restrict__ block_sums)
+{
+    uint32_t v[16], total;
+    const uint32_t sum = cell_thread_load(cells, v);
+    cta_exclusive_scan(sum, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_cells_scan_sums(uint32_t *block_sums)
+{
+    uint4 q = reinterpret_cast<uint4 *>(block_sums)[threadIdx.x];
+    uint32_t total;
+    uint32_t base = cta_exclusive_scan(q.x + q.y + q.z + q.w, total);
+    uint4 o;
+    o.x = base; o.y = base + q.x; o.z = o.y + q.y; o.w = o.z + q.z;
+    reinterpret_cast<uint4 *>(block_sums)[threadIdx.x] = o;
+}
+
+__global__ void __launch_bounds__(256) k_cells_apply(uint32_t *__restrict__ cells, const uint32_t *__restrict__ block_sums)
+{
+    uint32_t v[16], total;
+    const uint32_t sum = cell_thread_load(cells, v);
+    uint32_t run = cta_exclusive_scan(sum, total) + block_sums[blockIdx.x];
+    uint4 *p = reinterpret_cast<uint4 *>(cells + (size_t)blockIdx.x * CELL_BLOCK + threadIdx.x * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = run; run += v[4 * j];
+        o.y = run; run += v[4 * j + 1];
+        o.z = run; run += v[4 * j + 2];
+        o.w = run; run += v[4 * j + 3];
+        p[j] = o;
+    }
+}
+
+// keys[i] = (code << 32 | rank in the cell)  ->  order[offset of the cell + rank] = ray.  32-bit entries: the order of
+// a 2^24-ray wave is 67 MB and its scattered 4-byte stores merge in L2 (64-bit entries = 134 MB did not: 563 us)
+__global__ void k_cells_place(const uint64_t *__restrict__ keys, int64_t n, const uint32_t *__restrict__ cell_offset,
+                              int cell_shift, uint32_t *__restrict__ order)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = keys[i];
+    const uint32_t cell = (uint32_t)(key >> 32) >> cell_shift;
+    order[(size_t)__ldg(cell_offset + cell) + (uint32_t)key] = (uint32_t)i;
 }
 
 // Conservative sphere filter in front of the exact 80-triangle receiver query: can the segment
@@ -430,7 +531,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, COOP ? WALK_MIN_CTAS - 1 : WALK
                 if (!has_ray) {
                     int64_t r = blk_next + __popc(idle & ((1u << lane) - 1u));
                     if (r < blk_end) {
-                        if (P.order) r = (int64_t)(uint32_t)__ldg(P.order + r); // direction-coherent order
+                        if (P.order32) r = (int64_t)__ldg(P.order32 + r);             // direction-coherent order
+                        else if (P.order) r = (int64_t)(uint32_t)__ldg(P.order + r);
                         float4 d4 = __ldg(P.dirs + r);
                         dir = make_float3(d4.x, d4.y, d4.z);
                         pos = P.tx;
@@ -1017,17 +1119,24 @@ int grid_for(const void *kernel, size_t smem, int *out_grid, bool all_smem = fal
     return RFRT_OK;
 }
 
-// workspace of the direction-coherent ray order (BVH scenes): two key buffers + the sort's histograms
+// waves of at least this many rays are ordered by the counting sort over the 2^24 direction cells (its cost has a fixed
+// part: ~0.3 GB of counter traffic), smaller ones by the radix sort; RFRT_RAY_ORDER=radix|cells forces one (A/B, tests)
+constexpr int64_t RAY_CELLS_MIN_RAYS = 1 << 21;
+
+// workspace of the direction-coherent ray order (BVH scenes): two key buffers + the sort's histograms + the cell counters
 int reserve_ray_sort(Mesh *m, int64_t cap)
 {
     if (m->ray_cap >= cap) return RFRT_OK;
     if (m->ray_keys[0]) cudaFree(m->ray_keys[0]);
     if (m->ray_keys[1]) cudaFree(m->ray_keys[1]);
     if (m->ray_hist) cudaFree(m->ray_hist);
-    m->ray_keys[0] = m->ray_keys[1] = nullptr; m->ray_hist = nullptr; m->ray_cap = 0;
+    if (m->ray_cells) cudaFree(m->ray_cells);
+    m->ray_keys[0] = m->ray_keys[1] = nullptr; m->ray_hist = nullptr; m->ray_cells = nullptr; m->ray_cap = 0;
     RFRT_CUDA(cudaMalloc(&m->ray_keys[0], sizeof(uint64_t) * cap));
     RFRT_CUDA(cudaMalloc(&m->ray_keys[1], sizeof(uint64_t) * cap));
     RFRT_CUDA(cudaMalloc(&m->ray_hist, sizeof(uint32_t) * 256 * ((size_t)sort_hist_blocks(cap) + 1)));
+    const char *order_env = getenv("RFRT_RAY_ORDER");
+    if (cap >= RAY_CELLS_MIN_RAYS || (order_env && strcmp(order_env, "cells") == 0)) RFRT_CUDA(cudaMalloc(&m->ray_cells, sizeof(uint32_t) * ((size_t)RAY_CELLS + RAY_CELLS / CELL_BLOCK)));
     m->ray_cap = cap;
     return RFRT_OK;
 }
@@ -1194,15 +1303,33 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
     for (int64_t c0 = ray_begin; c0 < ray_end; c0 += chunk_rays) {
         int64_t cn = ray_end - c0 < chunk_rays ? ray_end - c0 : chunk_rays;
         if (!dirs_ready) k_gen_dirs<<<(unsigned)((cn + 255) / 256), 256, 0, stream>>>(c0, cn, (float4 *)d_dir_scratch);
-        P.order = nullptr;
+        P.order = nullptr; P.order32 = nullptr;
         if (sorted) {
-            k_dir_keys<<<(unsigned)((cn + 255) / 256), 256, 0, stream>>>((const float4 *)d_dir_scratch, cn, m->ray_keys[0], P.tx,
-                                                                         make_float3(P.env_lo[0], P.env_lo[1], P.env_lo[2]),
-                                                                         make_float3(P.env_hi[0], P.env_hi[1], P.env_hi[2]));
+            const char *order_env = getenv("RFRT_RAY_ORDER");
+            const bool by_cells = m->ray_cells && (order_env ? strcmp(order_env, "cells") == 0 : cn >= RAY_CELLS_MIN_RAYS);
+            const float3 blo = make_float3(P.env_lo[0], P.env_lo[1], P.env_lo[2]), bhi = make_float3(P.env_hi[0], P.env_hi[1], P.env_hi[2]);
+            const unsigned key_blocks = (unsigned)((cn + 255) / 256);
+            if (by_cells) {
+                // 2^22 cells (the top 22 bits of the code): counters (16 MB) + order (4 B per ray) stay in L2 for a
+                // wave of 2^24 rays; RFRT_RAY_CELL_BITS is a tuning aid
+                int cell_bits = getenv("RFRT_RAY_CELL_BITS") ? atoi(getenv("RFRT_RAY_CELL_BITS")) : 22;
+                cell_bits = cell_bits < 20 ? 20 : (cell_bits > 24 ? 24 : cell_bits);
+                const int n_cells = 1 << cell_bits, cell_blocks = n_cells / CELL_BLOCK, cell_shift = 24 - cell_bits;
+                uint32_t *block_sums = m->ray_cells + RAY_CELLS;
+                RFRT_CUDA(cudaMemsetAsync(m->ray_cells, 0, sizeof(uint32_t) * n_cells, stream));
+                k_dir_keys<true><<<key_blocks, 256, 0, stream>>>((const float4 *)d_dir_scratch, cn, m->ray_keys[0], P.tx, blo, bhi, m->ray_cells, cell_shift);
+                k_cells_reduce<<<cell_blocks, 256, 0, stream>>>(m->ray_cells, block_sums);
+                k_cells_scan_sums<<<1, cell_blocks / 4, 0, stream>>>(block_sums);
+                k_cells_apply<<<cell_blocks, 256, 0, stream>>>(m->ray_cells, block_sums);
+                k_cells_place<<<key_blocks, 256, 0, stream>>>(m->ray_keys[0], cn, m->ray_cells, cell_shift, reinterpret_cast<uint32_t *>(m->ray_keys[1]));
+                P.order32 = reinterpret_cast<const uint32_t *>(m->ray_keys[1]);
+            } else {
+            k_dir_keys<false><<<key_blocks, 256, 0, stream>>>((const float4 *)d_dir_scratch, cn, m->ray_keys[0], P.tx, blo, bhi, nullptr, 0);
             // (radix passes over the 24-bit direction code, from its top: 3 / 2 / 1 passes = 3.90 / 3.95 / 3.65e9 segments/s
             // on the 20 M-triangle terrain, 5.88 / 5.84 / 5.18e9 on 2 M triangles; the variable is a tuning aid)
             const int sort_passes = getenv("RFRT_RAY_SORT_PASSES") ? atoi(getenv("RFRT_RAY_SORT_PASSES")) : 3;
             P.order = radix_sort_u64(m->ray_keys[0], m->ray_keys[1], m->ray_hist, cn, 32 + 8 * (3 - sort_passes), sort_passes, stream);
+            }
         }
         RFRT_CUDA(cudaMemsetAsync(d_counters + RFRT_CTR_NEXT_RAY, 0, sizeof(uint64_t), stream));
         P.chunk_begin = c0; P.chunk_n = cn;

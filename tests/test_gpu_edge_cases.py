@@ -282,3 +282,28 @@ def test_plain_and_general_slab_tests_agree(torch_cuda, room_stl, monkeypatch):
     assert recs[0]["ray"].shape[0] > 50
     for name in recs[0]:
         assert np.array_equal(recs[0][name].view(np.uint8), recs[1][name].view(np.uint8)), name
+
+
+def test_ray_order_by_cells_equals_radix_order(torch_cuda, monkeypatch):
+    """Waves of a BVH scene are traced in direction-coherent order: a counting sort over the 2^24 direction cells for
+    big waves, a radix sort for small ones.  Both are permutations of the wave's rays, so every ray's trajectory must be
+    the same either way (and the same as with no ordering at all)."""
+    from rf_ray_tracing_warp_b200 import Tracer, _lib, synthetic_terrain
+    mesh = synthetic_terrain(96, 20.0, 5)
+    n, B, tx = (1 << 18) + 777, 4, [10.0, 0.0, 4.5]
+    outs = []
+    for order in ("radix", "cells", None):
+        if order:
+            monkeypatch.setenv("RFRT_RAY_ORDER", order)
+        tr = Tracer(mesh, C, 100e9, 200e-9, B, n)
+        if order is None:
+            tr.trace_flags |= _lib.FLAG_NO_RAY_SORT
+        out = tr.trace_segments(tx, dump=True, checksum=True)
+        outs.append((out["segments"], out["env_hits"], out["checksum"], out["hit_tri"].cpu().numpy(),
+                     out["hit_t"].cpu().numpy().view(np.uint32)))
+        if order:
+            monkeypatch.delenv("RFRT_RAY_ORDER")
+    assert outs[0][0] > n and outs[0][1] > 1000
+    for o in outs[1:]:
+        assert o[:3] == outs[0][:3]
+        assert np.array_equal(o[3], outs[0][3]) and np.array_equal(o[4], outs[0][4])
