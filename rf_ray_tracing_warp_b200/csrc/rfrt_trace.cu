@@ -108,13 +108,22 @@ __device__ __forceinline__ uint32_t spread12(uint32_t v)
 // amortise it (4.7e9 segments/s on 20 M triangles against 4.05e9 at 2^24 and 2.6e9 at 2^22).
 // CELLS: also count the ray into its direction cell (the 24-bit code) and keep its arrival rank there instead of its
 // id: the input of the counting sort below.
-template <bool CELLS>
-__global__ void k_dir_keys(const float4 *__restrict__ dirs, int64_t n, uint64_t *__restrict__ keys, float3 tx, float3 env_lo,
-                           float3 env_hi, uint32_t *__restrict__ cells, int cell_shift)
+// GEN: the directions are generated here (and stored for the walk) instead of being read back from k_gen_dirs' output:
+// the fp64 series then run under the latency of the cell atomics.
+template <bool CELLS, bool GEN = false>
+__global__ void k_dir_keys(float4 *__restrict__ dirs, int64_t n, uint64_t *__restrict__ keys, float3 tx, float3 env_lo,
+                           float3 env_hi, uint32_t *__restrict__ cells, int cell_shift, int64_t ray_begin = 0)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 d = dirs[i];
+    float4 d;
+    if (GEN) {
+        const float3 g = ray_direction((uint32_t)(ray_begin + i));
+        d = make_float4(g.x, g.y, g.z, 0.0f);
+        dirs[i] = d;
+    } else {
+        d = dirs[i];
+    }
     float tn;
     const bool enters = slab_hit(slab_setup_fast(tx, make_float3(d.x, d.y, d.z)), env_lo.x, env_lo.y, env_lo.z, env_hi.x, env_hi.y,
                                  env_hi.z, 1.0e6f, tn);
@@ -1302,11 +1311,12 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
 
     for (int64_t c0 = ray_begin; c0 < ray_end; c0 += chunk_rays) {
         int64_t cn = ray_end - c0 < chunk_rays ? ray_end - c0 : chunk_rays;
-        if (!dirs_ready) k_gen_dirs<<<(unsigned)((cn + 255) / 256), 256, 0, stream>>>(c0, cn, (float4 *)d_dir_scratch);
+        const char *order_env = getenv("RFRT_RAY_ORDER");
+        const bool by_cells = sorted && m->ray_cells && (order_env ? strcmp(order_env, "cells") == 0 : cn >= RAY_CELLS_MIN_RAYS);
+        const bool fuse_gen = by_cells && !dirs_ready && !getenv("RFRT_NO_FUSED_GEN");
+        if (!dirs_ready && !fuse_gen) k_gen_dirs<<<(unsigned)((cn + 255) / 256), 256, 0, stream>>>(c0, cn, (float4 *)d_dir_scratch);
         P.order = nullptr; P.order32 = nullptr;
         if (sorted) {
-            const char *order_env = getenv("RFRT_RAY_ORDER");
-            const bool by_cells = m->ray_cells && (order_env ? strcmp(order_env, "cells") == 0 : cn >= RAY_CELLS_MIN_RAYS);
             const float3 blo = make_float3(P.env_lo[0], P.env_lo[1], P.env_lo[2]), bhi = make_float3(P.env_hi[0], P.env_hi[1], P.env_hi[2]);
             const unsigned key_blocks = (unsigned)((cn + 255) / 256);
             if (by_cells) {
@@ -1317,14 +1327,15 @@ extern "C" int rfrt_trace(rfrt_handle env_mesh, rfrt_handle rxset, const float *
                 const int n_cells = 1 << cell_bits, cell_blocks = n_cells / CELL_BLOCK, cell_shift = 24 - cell_bits;
                 uint32_t *block_sums = m->ray_cells + RAY_CELLS;
                 RFRT_CUDA(cudaMemsetAsync(m->ray_cells, 0, sizeof(uint32_t) * n_cells, stream));
-                k_dir_keys<true><<<key_blocks, 256, 0, stream>>>((const float4 *)d_dir_scratch, cn, m->ray_keys[0], P.tx, blo, bhi, m->ray_cells, cell_shift);
+                if (fuse_gen) k_dir_keys<true, true><<<key_blocks, 256, 0, stream>>>((float4 *)d_dir_scratch, cn, m->ray_keys[0], P.tx, blo, bhi, m->ray_cells, cell_shift, c0);
+                else k_dir_keys<true><<<key_blocks, 256, 0, stream>>>((float4 *)d_dir_scratch, cn, m->ray_keys[0], P.tx, blo, bhi, m->ray_cells, cell_shift);
                 k_cells_reduce<<<cell_blocks, 256, 0, stream>>>(m->ray_cells, block_sums);
                 k_cells_scan_sums<<<1, cell_blocks / 4, 0, stream>>>(block_sums);
                 k_cells_apply<<<cell_blocks, 256, 0, stream>>>(m->ray_cells, block_sums);
                 k_cells_place<<<key_blocks, 256, 0, stream>>>(m->ray_keys[0], cn, m->ray_cells, cell_shift, reinterpret_cast<uint32_t *>(m->ray_keys[1]));
                 P.order32 = reinterpret_cast<const uint32_t *>(m->ray_keys[1]);
             } else {
-            k_dir_keys<false><<<key_blocks, 256, 0, stream>>>((const float4 *)d_dir_scratch, cn, m->ray_keys[0], P.tx, blo, bhi, nullptr, 0);
+            k_dir_keys<false><<<key_blocks, 256, 0, stream>>>((float4 *)d_dir_scratch, cn, m->ray_keys[0], P.tx, blo, bhi, nullptr, 0);
             // (radix passes over the 24-bit direction code, from its top: 3 / 2 / 1 passes = 3.90 / 3.95 / 3.65e9 segments/s
             // on the 20 M-triangle terrain, 5.88 / 5.84 / 5.18e9 on 2 M triangles; the variable is a tuning aid)
             const int sort_passes = getenv("RFRT_RAY_SORT_PASSES") ? atoi(getenv("RFRT_RAY_SORT_PASSES")) : 3;
