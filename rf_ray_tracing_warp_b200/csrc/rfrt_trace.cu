@@ -1092,7 +1092,10 @@ k_query(LiteralEnv E, const float *__restrict__ origins, const float *__restrict
 
 // Every origin of a segment (the transmitter, then hit points) within 8 x the mesh's largest coordinate m of the
 // coordinate origin: the origin-dependent slack of the slab test, 2^-21 * 8 m, then fits inside the boxes' padding of
-// 1e-5 m and the walks use the plain test.  RFRT_SLAB_FAR=1 forces the general test (A/B runs, tests).
+// 1e-5 m and the walks use the plain test.  (The replay also starts walks at receiver hit points, which may lie
+// anywhere: one outside that cube of half-size 8 m is on a straight line that has left the cube — it contains the
+// transmitter and the whole mesh — for good, so no hit exists that a cull could lose; the ray only turns at
+// environment hits.)  RFRT_SLAB_FAR=1 forces the general test (A/B runs, tests).
 bool tx_is_near(const Mesh *m, const float *h_tx_pos)
 {
     float m_coord = 0.0f, tx_coord = 0.0f;
