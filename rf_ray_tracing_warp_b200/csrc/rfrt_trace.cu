@@ -144,8 +144,9 @@ __global__ void k_dir_keys(float4 *__restrict__ dirs, int64_t n, uint64_t *__res
 // The key is a 24-bit cell number and the rays spread over the cells about evenly (one per cell at 2^24 rays), so the
 // order needs no general sort: count the rays of every cell with one atomic each (k_dir_keys<true>, which keeps the
 // arrival rank), scan the 2^24 counters (three small kernels over 67 MB), place every ray at its cell's offset + rank.
-// Measured per 16.8 M rays: keys + atomics 169 us, scan 44 us, placement ~250 us against 86 + 3 x 265 us of the radix
-// sort (wave of the 20 M-triangle terrain 6.0 -> 5.7 ms).
+// Measured per 16.8 M rays (profiles/launches_terrain_r02_final.csv): directions + keys + atomics 227 us, scan 19 us,
+// placement 180 us, against 163 (k_gen_dirs) + 86 + 3 x 265 us with the radix sort (wave of the 20 M-triangle terrain
+// 6.0 -> 5.6 ms).
 // The order inside a cell is the arrival order of the atomics — the hits of a ray do not depend on the order the rays
 // are traced in.
 constexpr int RAY_CELLS = 1 << 24;   // most cells a wave is ordered by (the whole 24-bit code)
